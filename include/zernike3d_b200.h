@@ -1,0 +1,112 @@
+/*
+ * zernike3d_b200 - C ABI of the B200-native spharm 3D-Zernike decomposition / reconstruction path.
+ *
+ * The reference (charbj/zernike3d) has no FFI / plugin seam: its hot path is three Python methods on
+ * ZernikeSpherical (zernike_master.py, "zm" below).  Each entry point here names the reference
+ * code it replaces; INTEGRATION.md shows the ctypes binding a maintainer would add to zm.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a Z3D_ERR_* code otherwise (no exceptions or aborts
+ *     cross the boundary); z3d_last_error() returns a thread-local description of the last failure;
+ *   - the caller owns all buffers; "d_" pointers are device pointers on the plan's device, "h_" are
+ *     host pointers; device entry points are asynchronous on `stream` (a cudaStream_t passed as
+ *     void*, NULL = legacy default stream);
+ *   - volumes are float32 [batch][N][N][N], C-contiguous, indexed exactly like `mrc.data` in
+ *     zm:2851-2852 / the 'xy' meshgrid of zm:2241 (array index [i][j][k] -> y=side[i], x=side[j],
+ *     z=side[k]);
+ *   - moments are complex64 (float re, float im) [batch][z3d_num_moments(order)] in the reference's
+ *     flat order: sorted (n, l, m), m >= 0 only (zm:378-382, indexing.py:191-228), already scaled by
+ *     coeff(n) = 2(2n+3) / (3*sqrt(3)*pi*N^3) (zm:2198);
+ *   - there is no CPU fallback: every entry point that computes needs a CUDA device.
+ */
+#ifndef ZERNIKE3D_B200_H
+#define ZERNIKE3D_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Z3D_OK 0
+#define Z3D_ERR_INVALID 1   /* bad argument */
+#define Z3D_ERR_CUDA 2      /* CUDA runtime error (see z3d_last_error) */
+#define Z3D_ERR_NODEVICE 3  /* no CUDA device / wrong architecture */
+#define Z3D_ERR_WORKSPACE 4 /* workspace too small */
+#define Z3D_ERR_UNSUPPORTED 5
+
+typedef struct z3d_plan z3d_plan;
+
+/* Library version (major * 10000 + minor * 100 + patch). */
+int z3d_version(void);
+
+/* Thread-local text of the last error raised by any z3d_* call on this thread. */
+const char *z3d_last_error(void);
+
+/* Index arithmetic (host only, no device needed).
+ * z3d_num_moments  = mu_(order) + 1        indexing.py:140-162   (12051 at order 50)
+ * z3d_num_radial   = number of (n, l) pairs = mu_R(order) + 1    indexing.py:13-28 (676 at order 50)
+ * z3d_num_harmonics= number of (l, m>=0)    = mu_Y(order)        indexing.py:87-99 (1326 at order 50)
+ * z3d_nlm_table fills nlm[3 * num_moments] with (n, l, m) per flat index (indexing.py:191-228). */
+int z3d_num_moments(int order);
+int z3d_num_radial(int order);
+int z3d_num_harmonics(int order);
+int z3d_nlm_table(int order, int *nlm);
+
+/* Plan = everything ZernikeSpherical.CalculatePolynomials (zm:2237-2323) prepares, minus the
+ * materialised basis: recurrence coefficient tables (zm:1992-1998, 2013-2024), per-l tile tables and
+ * the launch geometry, uploaded once to `device`.  No R_nl / Y_lm voxel grid is ever built. */
+int z3d_plan_create(int order, int dim, int device, z3d_plan **out);
+int z3d_plan_destroy(z3d_plan *plan);
+
+/* Plan queries (host only). info[]: 0 order, 1 dim, 2 num_moments, 3 passes, 4 CTAs per launch,
+ * 5 threads per CTA, 6 tiles per thread, 7 dynamic smem bytes, 8 voxels per chunk, 9 SM count,
+ * 10 useful accumulators, 11 padded accumulators. */
+int z3d_plan_info(const z3d_plan *plan, int *info, int n_info);
+
+/* Bytes of device scratch z3d_decompose / z3d_reconstruct need for `batch` volumes. */
+size_t z3d_workspace_bytes(const z3d_plan *plan, int batch);
+
+/* Analysis  (replaces ZernikeSpherical.Decompose -> _calculate_Z_GPU, zm:2492-2504, 2194-2217):
+ *   moments[b][mu(n,l,m)] = coeff(n) * sum_v vol[b][v] * R_nl(r_v) * conj(Y_lm(v)).
+ * `half_lo`, `half_hi` select the voxel slab this call sums over, in units of mirrored plane pairs of
+ * array axis 0: pair p in [half_lo, half_hi) is planes i = p and i = N-1-p (0 <= p < ceil(N/2)).
+ * Pass 0, ceil(N/2) for the whole volume; a sub-range yields the slab's partial (already scaled)
+ * moments, which add up across slabs (the multi-GPU path all-reduces them).  Only the planes of the
+ * selected pairs are read from d_vol. */
+int z3d_decompose(const z3d_plan *plan, const float *d_vol, int batch, int half_lo, int half_hi,
+                  float *d_moments /* [batch][num_moments][2] */, void *d_workspace, size_t workspace_bytes,
+                  void *stream);
+
+/* Synthesis (replaces ZernikeSpherical.Reconstruct -> _calculate_cum_GPU, zm:2642-2715, 2596-2614):
+ *   vol[b][v] = Re sum_{n,l,m>=0} [ O R_nl Y_lm + (m != 0) conj(O) R_nl conj(Y_lm) ].
+ * Only the planes of pairs [half_lo, half_hi) are written (the rest of d_vol is left untouched), so
+ * slab-sharded reconstruction needs no collective. */
+int z3d_reconstruct(const z3d_plan *plan, const float *d_moments /* [batch][num_moments][2] */, int batch,
+                    int half_lo, int half_hi, float *d_vol /* [batch][N][N][N] */, void *d_workspace,
+                    size_t workspace_bytes, void *stream);
+
+/* Rotational invariants F_nl = || Omega_nl. ||_2 over m = -l..l  (Moments.calculate_invariants,
+ * zm:62-76): d_invariants [batch][num_radial] float32 in sorted (n, l) order. */
+int z3d_invariants(const z3d_plan *plan, const float *d_moments, int batch, float *d_invariants, void *stream);
+
+/* Host-buffer convenience calls: the same operations for callers that hold numpy / C arrays, the way
+ * zm's Decompose(volume, ...) receives `mrc.data` and Reconstruct() returns a host map.  They stage
+ * through pinned memory owned by the plan, overlap H2D copies with compute in chunks of volumes, and
+ * return after the results are in the host buffers.  Not thread-safe per plan. */
+int z3d_decompose_host(z3d_plan *plan, const float *h_vol, int batch, float *h_moments);
+int z3d_reconstruct_host(z3d_plan *plan, const float *h_moments, int batch, float *h_vol);
+
+/* Number of kernels launched by this library since load (all plans, all threads); bench.py reports
+ * the difference across its timed region as "gpu_launches". */
+unsigned long long z3d_launch_count(void);
+
+/* FP32 FMA micro-benchmark used to pin the roofline denominator: runs `iters`
+ * dependent-chain FFMA rounds on every SM and returns achieved TFLOP/s in *tflops.
+ * variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2. */
+int z3d_fma_peak(int device, int variant, int iters, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZERNIKE3D_B200_H */

@@ -1,0 +1,577 @@
+// zernike3d_b200 - host planner and C ABI (see include/zernike3d_b200.h for the contract).
+#include "../../include/zernike3d_b200.h"
+#include "z3d_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace z3d;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(Z3D_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+inline int num_moments(int order) {
+    int c = 0;
+    for (int n = 0; n <= order; ++n)
+        for (int l = n & 1; l <= n; l += 2) c += l + 1;
+    return c;
+}
+inline int num_radial(int order) {
+    int c = 0;
+    for (int n = 0; n <= order; ++n) c += n / 2 + 1;
+    return c;
+}
+inline int pad4(int x) { return (x + 3) & ~3; }
+
+template <class T>
+int upload(const std::vector<T> &h, T **d, std::vector<void *> &owned) {
+    CUDA_TRY(cudaMalloc((void **)d, std::max<size_t>(1, h.size()) * sizeof(T)));
+    owned.push_back(*d);
+    if (!h.empty()) CUDA_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return Z3D_OK;
+}
+
+}  // namespace
+
+struct z3d_plan {
+    int order = 0, dim = 0, device = 0, H = 0, nmom = 0, nrad = 0, npass = 0, nsplit = 0, num_sms = 0;
+    int smem_bytes = 0, useful_acc = 0, padded_acc = 0;
+    DevPlan dev{};
+    // reduce / prepare tables
+    int *d_src = nullptr;        // [2*nmom]  pass*SLOT_WORDS + word
+    double *d_scale = nullptr;   // [nmom]    coeff(n) * kappa_lm
+    int *d_omap = nullptr;       // [npass*SLOT_WORDS] -> 2*mu+reim or -1
+    double *d_ofac = nullptr;    // [nmom]    kappa_lm * w_m
+    int *d_nl_base = nullptr, *d_nl_l = nullptr;  // invariants
+    std::vector<void *> owned;
+    // host-call staging
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    float *d_stage_vol[2] = {nullptr, nullptr};
+    float *d_stage_mom[2] = {nullptr, nullptr};
+    void *d_stage_ws[2] = {nullptr, nullptr};
+    int stage_batch = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int z3d_version(void) { return 100; }
+extern "C" const char *z3d_last_error(void) { return g_err.c_str(); }
+extern "C" unsigned long long z3d_launch_count(void) { return g_launches.load(); }
+
+extern "C" int z3d_num_moments(int order) { return order < 0 ? -1 : num_moments(order); }
+extern "C" int z3d_num_radial(int order) { return order < 0 ? -1 : num_radial(order); }
+extern "C" int z3d_num_harmonics(int order) { return order < 0 ? -1 : (order + 1) * (order + 2) / 2; }
+extern "C" int z3d_nlm_table(int order, int *nlm) {
+    if (order < 0 || !nlm) return fail(Z3D_ERR_INVALID, "z3d_nlm_table: bad arguments");
+    int mu = 0;
+    for (int n = 0; n <= order; ++n)
+        for (int l = n & 1; l <= n; l += 2)
+            for (int m = 0; m <= l; ++m, ++mu) {
+                nlm[3 * mu] = n;
+                nlm[3 * mu + 1] = l;
+                nlm[3 * mu + 2] = m;
+            }
+    return Z3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// planner
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct HostPlan {
+    int L, npass;
+    std::vector<int> lpass, roffw, poffw, rbase, ownl, nown, ntiles, gen_tasks;
+    std::vector<int2> tiles;
+    std::vector<float> beta;
+    std::vector<float4> rk;
+    std::vector<double> kappa;  // [(L+1)*(L+1)] kappa[l*(L+1)+m]
+    std::vector<int> src, omap;
+    int useful = 0, padded = 0;
+};
+
+// pass(l): same parity inside a pass (the synthesis kernel relies on it), round-robin over l/2
+inline int pass_of(int l, int npass) { return (l & 1) + 2 * ((l >> 1) % (npass / 2)); }
+
+bool layout_fits(int L, int npass) {
+    for (int p = 0; p < npass; ++p) {
+        int rw = 0, pw = 0, nt = 0;
+        for (int l = 0; l <= L; ++l) {
+            if (pass_of(l, npass) != p) continue;
+            const int nn = (L - l) / 2 + 1, m2 = 2 * (l + 1);
+            rw += pad4(nn);
+            pw += pad4(m2);
+            nt += (pad4(nn) / 4) * (pad4(m2) / 4);
+        }
+        if (rw > RS || pw > PS || nt > NT * TS) return false;
+    }
+    return true;
+}
+
+int build_host_plan(int L, HostPlan &hp) {
+    hp.L = L;
+    int npass = 2;
+    while (npass <= 64 && !layout_fits(L, npass)) npass += 2;
+    if (npass > 64) return fail(Z3D_ERR_UNSUPPORTED, "order %d too large for this build", L);
+    hp.npass = npass;
+    const int S = L + 1;
+    hp.lpass.assign(S, 0);
+    hp.roffw.assign(S, 0);
+    hp.poffw.assign(S, 0);
+    hp.rbase.assign(S, 0);
+    hp.ownl.assign((size_t)npass * S, -1);
+    hp.nown.assign(npass, 0);
+    hp.ntiles.assign(npass, 0);
+    hp.tiles.assign((size_t)npass * NT * TS, make_int2(0, 0));
+    hp.gen_tasks.assign((size_t)npass * NWARP * MAXTASK, 0);
+
+    // ---- coefficient tables (float64 on the host, like the reference's Python scalars)
+    // Legendre: C1, C2 of zm:2017-2024, C3 of zm:2013; kappa_mm = P_mm / sin^m, kappa_lm = kappa_{l-1,m} C1/2
+    hp.kappa.assign((size_t)S * S, 0.0);
+    hp.beta.assign((size_t)S * S, 0.0f);
+    std::vector<double> C1((size_t)S * S, 0.0), C2((size_t)S * S, 0.0);
+    for (int l = 1; l <= L; ++l)
+        for (int m = 0; m < l; ++m) {
+            const double c0 = std::sqrt((2.0 * l + 1.0) / ((double)(l + m) * (double)(l - m)));
+            C1[(size_t)l * S + m] = c0 * std::sqrt(2.0 * l - 1.0);
+            if (m < l - 1) C2[(size_t)l * S + m] = c0 * std::sqrt(((double)(l + m - 1) * (double)(l - m - 1)) / (2.0 * l - 3.0));
+        }
+    double kmm = 0.5 * std::sqrt(1.0 / M_PI);  // zm:2011
+    for (int m = 0; m <= L; ++m) {
+        if (m > 0) kmm *= -std::sqrt((2.0 * m + 1.0) / (2.0 * m));  // zm:2013-2014
+        hp.kappa[(size_t)m * S + m] = kmm;
+        for (int l = m + 1; l <= L; ++l) {
+            hp.kappa[(size_t)l * S + m] = hp.kappa[(size_t)(l - 1) * S + m] * C1[(size_t)l * S + m] * 0.5;
+            if (l >= m + 2)
+                hp.beta[(size_t)m * S + l] =
+                    (float)(C2[(size_t)l * S + m] * 4.0 / (C1[(size_t)l * S + m] * C1[(size_t)(l - 1) * S + m]));
+        }
+    }
+    // Radial: K1, K2, K3 of zm:1992-1998, l-major
+    hp.rk.clear();
+    for (int l = 0; l <= L; ++l) {
+        hp.rbase[l] = (int)hp.rk.size();
+        for (int n = l; n <= L; n += 2) {
+            float4 K = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n > l) {
+                const double k0 = (double)(n - l) * (n + l + 1) * (2 * n - 3);
+                const double k1 = (double)(2 * n - 1) * (2 * n + 1) * (2 * n - 3);
+                const double k2 = 0.5 * (double)(-2 * n + 1) * (double)((2 * l + 1) * (2 * l + 1)) - k1 / 2.0;
+                const double k3 = -1.0 * (double)(n - l - 2) * (n + l - 1) * (2 * n + 1);
+                K = make_float4((float)(k1 / k0), (float)(k2 / k0), (float)(k3 / k0), 0.f);
+            }
+            hp.rk.push_back(K);
+        }
+    }
+
+    // ---- per-pass panel layout and tile enumeration
+    const int nmom = num_moments(L);
+    hp.src.assign((size_t)2 * nmom, -1);
+    hp.omap.assign((size_t)npass * SLOT_WORDS, -1);
+    // mu base per (n, l)
+    std::vector<int> mubase((size_t)S * S, -1);
+    {
+        int mu = 0;
+        for (int n = 0; n <= L; ++n)
+            for (int l = n & 1; l <= n; l += 2) {
+                mubase[(size_t)n * S + l] = mu;
+                mu += l + 1;
+            }
+    }
+    for (int p = 0; p < npass; ++p) {
+        int rw = 0, pw = 0, t = 0, no = 0;
+        for (int l = 0; l <= L; ++l) {
+            if (pass_of(l, npass) != p) continue;
+            hp.lpass[l] = p;
+            hp.ownl[(size_t)p * S + no++] = l;
+            hp.roffw[l] = rw;
+            hp.poffw[l] = pw;
+            const int nn = (L - l) / 2 + 1, m2 = 2 * (l + 1);
+            for (int nb = 0; nb < pad4(nn) / 4; ++nb)
+                for (int mb = 0; mb < pad4(m2) / 4; ++mb, ++t) {
+                    const int slot = t / NT, tid = t % NT;
+                    hp.tiles[((size_t)p * TS + slot) * NT + tid] = make_int2(rw + 4 * nb, pw + 4 * mb);
+                    for (int i = 0; i < 4; ++i)
+                        for (int j = 0; j < 4; ++j) {
+                            const int ni = 4 * nb + i, c = 4 * mb + j;
+                            hp.padded++;
+                            if (ni >= nn || c >= m2) continue;
+                            const int n = l + 2 * ni, m = c >> 1, reim = c & 1;
+                            const int e = 2 * (mubase[(size_t)n * S + l] + m) + reim;
+                            const int word = (slot * NT + tid) * 16 + i * 4 + j;
+                            hp.src[e] = p * SLOT_WORDS + word;
+                            hp.omap[(size_t)p * SLOT_WORDS + word] = e;
+                            hp.useful++;
+                        }
+                }
+            rw += pad4(nn);
+            pw += pad4(m2);
+        }
+        hp.nown[p] = no;
+        hp.ntiles[p] = t;
+
+        // ---- generation tasks: groups of SUBS chains, longest-processing-time first over the warps
+        struct Task { int code; int cost; };
+        std::vector<Task> tasks;
+        for (int m0 = 0; m0 <= L; m0 += SUBS) tasks.push_back({(1 << 16) | m0, (L - m0 + 1) * 8 + 24});
+        for (int b = 0; b < no; b += SUBS) {
+            const int l0 = hp.ownl[(size_t)p * S + b];
+            tasks.push_back({(2 << 16) | b, ((L - l0) / 2 + 1) * 7 + 24});
+        }
+        std::sort(tasks.begin(), tasks.end(), [](const Task &a, const Task &b) { return a.cost > b.cost; });
+        int load[NWARP] = {0}, cnt[NWARP] = {0};
+        for (const Task &tk : tasks) {
+            int w = 0;
+            for (int q = 1; q < NWARP; ++q)
+                if (load[q] < load[w]) w = q;
+            if (cnt[w] >= MAXTASK) return fail(Z3D_ERR_UNSUPPORTED, "order %d: too many generation tasks", L);
+            hp.gen_tasks[((size_t)p * NWARP + w) * MAXTASK + cnt[w]++] = tk.code;
+            load[w] += tk.cost;
+        }
+    }
+    for (int e = 0; e < 2 * nmom; ++e)
+        if (hp.src[e] < 0) return fail(Z3D_ERR_INVALID, "internal: output %d has no tile", e);
+    return Z3D_OK;
+}
+
+int set_kernel_attrs(int smem) {
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    return Z3D_OK;
+}
+
+}  // namespace
+
+extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
+    if (!out) return fail(Z3D_ERR_INVALID, "z3d_plan_create: out is NULL");
+    *out = nullptr;
+    if (order < 0 || order > 0xfff0) return fail(Z3D_ERR_INVALID, "z3d_plan_create: bad order %d", order);
+    if (dim < 2 || dim > 4096) return fail(Z3D_ERR_INVALID, "z3d_plan_create: bad dim %d (need 2..4096)", dim);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(Z3D_ERR_NODEVICE, "z3d_plan_create: no CUDA device (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(Z3D_ERR_INVALID, "z3d_plan_create: device %d of %d", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(Z3D_ERR_NODEVICE, "z3d_plan_create: device %d is sm_%d%d; this build is sm_100a only", device,
+                    prop.major, prop.minor);
+
+    HostPlan hp;
+    int rc = build_host_plan(order, hp);
+    if (rc) return rc;
+
+    z3d_plan *pl = new z3d_plan();
+    pl->order = order;
+    pl->dim = dim;
+    pl->device = device;
+    pl->H = (dim + 1) / 2;
+    pl->nmom = num_moments(order);
+    pl->nrad = num_radial(order);
+    pl->npass = hp.npass;
+    pl->num_sms = prop.multiProcessorCount;
+    pl->nsplit = std::max(1, (prop.multiProcessorCount * CTAS_PER_SM) / hp.npass);
+    pl->useful_acc = hp.useful;
+    pl->padded_acc = hp.padded;
+    const SmemMap mp = smem_map(order, dim, pl->H);
+    pl->smem_bytes = mp.total;
+    if ((size_t)mp.total > prop.sharedMemPerBlockOptin) {
+        delete pl;
+        return fail(Z3D_ERR_UNSUPPORTED, "plan needs %d B of shared memory per CTA (device allows %zu)", mp.total,
+                    prop.sharedMemPerBlockOptin);
+    }
+
+    // side = np.linspace(-1/sqrt(3), 1/sqrt(3), dim)  (zm:2240): start + k*step, last point = stop
+    std::vector<double> side(dim);
+    {
+        const double stop = 1.0 / std::sqrt(3.0), start = -stop, step = (stop - start) / (double)(dim - 1);
+        for (int k = 0; k < dim; ++k) side[k] = (double)k * step + start;
+        side[dim - 1] = stop;
+    }
+    // scale tables
+    const int S = order + 1;
+    std::vector<double> scale(pl->nmom), ofac(pl->nmom);
+    std::vector<int> nl_base(pl->nrad), nl_l(pl->nrad);
+    {
+        int mu = 0, q = 0;
+        const double d3 = (double)dim * dim * dim;
+        for (int n = 0; n <= order; ++n) {
+            const double coeff = (2.0 * (2.0 * n + 3.0)) / (3.0 * std::sqrt(3.0) * M_PI * d3);  // zm:2198
+            for (int l = n & 1; l <= n; l += 2, ++q) {
+                nl_base[q] = mu;
+                nl_l[q] = l;
+                for (int m = 0; m <= l; ++m, ++mu) {
+                    const double k = hp.kappa[(size_t)l * S + m];
+                    scale[mu] = coeff * k;
+                    ofac[mu] = k * (m == 0 ? 1.0 : 2.0);
+                }
+            }
+        }
+    }
+
+    DevPlan &d = pl->dev;
+    d.order = order;
+    d.dim = dim;
+    d.H = pl->H;
+    d.npass = pl->npass;
+    d.nsplit = pl->nsplit;
+    d.dim_vec4 = (dim % 4 == 0);
+    auto &ow = pl->owned;
+    double *d_side; float *d_beta; float4 *d_rk; int *d_rbase, *d_roffw, *d_poffw, *d_lpass, *d_ownl, *d_nown, *d_ntiles, *d_gen;
+    int2 *d_tiles;
+#define UP(h, dptr)                          \
+    if ((rc = upload(h, &dptr, ow)) != 0) {  \
+        z3d_plan_destroy(pl);                \
+        return rc;                           \
+    }
+    UP(side, d_side) UP(hp.beta, d_beta) UP(hp.rk, d_rk) UP(hp.rbase, d_rbase) UP(hp.roffw, d_roffw)
+    UP(hp.poffw, d_poffw) UP(hp.lpass, d_lpass) UP(hp.ownl, d_ownl) UP(hp.nown, d_nown) UP(hp.ntiles, d_ntiles)
+    UP(hp.gen_tasks, d_gen) UP(hp.tiles, d_tiles)
+    UP(hp.src, pl->d_src) UP(scale, pl->d_scale) UP(hp.omap, pl->d_omap) UP(ofac, pl->d_ofac)
+    UP(nl_base, pl->d_nl_base) UP(nl_l, pl->d_nl_l)
+#undef UP
+    d.side = d_side; d.beta = d_beta; d.rk = d_rk; d.rbase = d_rbase; d.roffw = d_roffw; d.poffw = d_poffw;
+    d.lpass = d_lpass; d.ownl = d_ownl; d.nown = d_nown; d.ntiles = d_ntiles; d.tiles = d_tiles; d.gen_tasks = d_gen;
+
+    rc = set_kernel_attrs(pl->smem_bytes);
+    if (rc) {
+        z3d_plan_destroy(pl);
+        return rc;
+    }
+    *out = pl;
+    return Z3D_OK;
+}
+
+extern "C" int z3d_plan_destroy(z3d_plan *pl) {
+    if (!pl) return Z3D_OK;
+    cudaSetDevice(pl->device);
+    for (void *p : pl->owned) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (pl->d_stage_vol[i]) cudaFree(pl->d_stage_vol[i]);
+        if (pl->d_stage_mom[i]) cudaFree(pl->d_stage_mom[i]);
+        if (pl->d_stage_ws[i]) cudaFree(pl->d_stage_ws[i]);
+        if (pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]);
+        if (pl->ev_done[i]) cudaEventDestroy(pl->ev_done[i]);
+    }
+    if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
+    if (pl->s_comp) cudaStreamDestroy(pl->s_comp);
+    delete pl;
+    return Z3D_OK;
+}
+
+extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
+    if (!pl || !info) return fail(Z3D_ERR_INVALID, "z3d_plan_info: NULL argument");
+    const int v[12] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
+                       KC, pl->num_sms, pl->useful_acc, pl->padded_acc};
+    for (int i = 0; i < n && i < 12; ++i) info[i] = v[i];
+    return Z3D_OK;
+}
+
+static size_t ws_decompose(const z3d_plan *pl, int batch) {
+    return (size_t)batch * pl->npass * pl->nsplit * SLOT_WORDS * sizeof(float);
+}
+static size_t ws_reconstruct(const z3d_plan *pl, int batch) {
+    const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
+    return ((size_t)batch * pl->npass * SLOT_WORDS + (size_t)pl->npass * batch * N3) * sizeof(float);
+}
+extern "C" size_t z3d_workspace_bytes(const z3d_plan *pl, int batch) {
+    if (!pl || batch < 1) return 0;
+    return std::max(ws_decompose(pl, batch), ws_reconstruct(pl, batch));
+}
+
+static int check_range(const z3d_plan *pl, int batch, int lo, int hi, const char *who) {
+    if (!pl) return fail(Z3D_ERR_INVALID, "%s: plan is NULL", who);
+    if (batch < 1) return fail(Z3D_ERR_INVALID, "%s: batch %d < 1", who, batch);
+    if (lo < 0 || hi > pl->H || lo > hi) return fail(Z3D_ERR_INVALID, "%s: pair range [%d, %d) outside [0, %d]", who, lo, hi, pl->H);
+    return Z3D_OK;
+}
+
+extern "C" int z3d_decompose(const z3d_plan *pl, const float *d_vol, int batch, int half_lo, int half_hi,
+                             float *d_moments, void *d_ws, size_t ws_bytes, void *stream) {
+    int rc = check_range(pl, batch, half_lo, half_hi, "z3d_decompose");
+    if (rc) return rc;
+    if (!d_vol || !d_moments || !d_ws) return fail(Z3D_ERR_INVALID, "z3d_decompose: NULL buffer");
+    if (ws_bytes < ws_decompose(pl, batch))
+        return fail(Z3D_ERR_WORKSPACE, "z3d_decompose: workspace %zu < %zu bytes", ws_bytes, ws_decompose(pl, batch));
+    CUDA_TRY(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    float *partial = (float *)d_ws;
+    k_decompose<<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, half_lo, half_hi, partial);
+    CUDA_TRY(cudaGetLastError());
+    dim3 g((2 * pl->nmom + 255) / 256, batch);
+    k_reduce_moments<<<g, 256, 0, st>>>(partial, pl->d_src, pl->d_scale, pl->nmom, pl->npass, pl->nsplit, batch, d_moments);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 2;
+    return Z3D_OK;
+}
+
+extern "C" int z3d_reconstruct(const z3d_plan *pl, const float *d_moments, int batch, int half_lo, int half_hi,
+                               float *d_vol, void *d_ws, size_t ws_bytes, void *stream) {
+    int rc = check_range(pl, batch, half_lo, half_hi, "z3d_reconstruct");
+    if (rc) return rc;
+    if (!d_vol || !d_moments || !d_ws) return fail(Z3D_ERR_INVALID, "z3d_reconstruct: NULL buffer");
+    if (ws_bytes < ws_reconstruct(pl, batch))
+        return fail(Z3D_ERR_WORKSPACE, "z3d_reconstruct: workspace %zu < %zu bytes", ws_bytes, ws_reconstruct(pl, batch));
+    if (half_lo == half_hi) return Z3D_OK;
+    CUDA_TRY(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    float *otiles = (float *)d_ws;
+    float *pvol = otiles + (size_t)batch * pl->npass * SLOT_WORDS;
+    dim3 g((pl->npass * SLOT_WORDS + 255) / 256, batch);
+    k_prepare_tiles<<<g, 256, 0, st>>>(d_moments, pl->d_omap, pl->d_ofac, pl->nmom, pl->npass, batch, otiles);
+    CUDA_TRY(cudaGetLastError());
+    k_reconstruct<<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, otiles, batch, half_lo, half_hi, pvol);
+    CUDA_TRY(cudaGetLastError());
+    const size_t total = (size_t)2 * (half_hi - half_lo) * pl->dim * pl->dim * batch;
+    k_sum_passes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pvol, pl->npass, batch, pl->dim, half_lo, half_hi, d_vol);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 3;
+    return Z3D_OK;
+}
+
+extern "C" int z3d_invariants(const z3d_plan *pl, const float *d_moments, int batch, float *d_inv, void *stream) {
+    if (!pl || !d_moments || !d_inv || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_invariants: bad arguments");
+    CUDA_TRY(cudaSetDevice(pl->device));
+    dim3 g((pl->nrad + 127) / 128, batch);
+    k_invariants<<<g, 128, 0, (cudaStream_t)stream>>>(d_moments, pl->d_nl_base, pl->d_nl_l, pl->nrad, pl->nmom, batch, d_inv);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    return Z3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer calls: double-buffered groups of volumes, H2D on one stream, compute + D2H on another
+// ------------------------------------------------------------------------------------------------
+static int ensure_staging(z3d_plan *pl) {
+    if (pl->s_copy) return Z3D_OK;
+    CUDA_TRY(cudaSetDevice(pl->device));
+    const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
+    // group size: ~32 MiB of volume data per stage, at least 1 volume, at most 32
+    int gb = (int)std::min<size_t>(32, std::max<size_t>(1, ((size_t)32 << 20) / (N3 * sizeof(float))));
+    pl->stage_batch = gb;
+    CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaMalloc((void **)&pl->d_stage_vol[i], (size_t)gb * N3 * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void **)&pl->d_stage_mom[i], (size_t)gb * pl->nmom * 2 * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&pl->d_stage_ws[i], z3d_workspace_bytes(pl, gb)));
+    }
+    return Z3D_OK;
+}
+
+extern "C" int z3d_decompose_host(z3d_plan *pl, const float *h_vol, int batch, float *h_mom) {
+    if (!pl || !h_vol || !h_mom || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_decompose_host: bad arguments");
+    int rc = ensure_staging(pl);
+    if (rc) return rc;
+    const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
+    const int gb = pl->stage_batch;
+    int stage = 0;
+    for (int b0 = 0; b0 < batch; b0 += gb, stage ^= 1) {
+        const int nb = std::min(gb, batch - b0);
+        // the stage's previous compute + D2H must be finished before its input buffer is overwritten
+        CUDA_TRY(cudaStreamWaitEvent(pl->s_copy, pl->ev_done[stage], 0));
+        CUDA_TRY(cudaMemcpyAsync(pl->d_stage_vol[stage], h_vol + (size_t)b0 * N3, (size_t)nb * N3 * sizeof(float),
+                                 cudaMemcpyHostToDevice, pl->s_copy));
+        CUDA_TRY(cudaEventRecord(pl->ev_in[stage], pl->s_copy));
+        CUDA_TRY(cudaStreamWaitEvent(pl->s_comp, pl->ev_in[stage], 0));
+        rc = z3d_decompose(pl, pl->d_stage_vol[stage], nb, 0, pl->H, pl->d_stage_mom[stage], pl->d_stage_ws[stage],
+                           z3d_workspace_bytes(pl, gb), pl->s_comp);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_mom + (size_t)b0 * pl->nmom * 2, pl->d_stage_mom[stage],
+                                 (size_t)nb * pl->nmom * 2 * sizeof(float), cudaMemcpyDeviceToHost, pl->s_comp));
+        CUDA_TRY(cudaEventRecord(pl->ev_done[stage], pl->s_comp));
+    }
+    CUDA_TRY(cudaStreamSynchronize(pl->s_comp));
+    CUDA_TRY(cudaStreamSynchronize(pl->s_copy));
+    return Z3D_OK;
+}
+
+extern "C" int z3d_reconstruct_host(z3d_plan *pl, const float *h_mom, int batch, float *h_vol) {
+    if (!pl || !h_vol || !h_mom || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_reconstruct_host: bad arguments");
+    int rc = ensure_staging(pl);
+    if (rc) return rc;
+    const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
+    const int gb = pl->stage_batch;
+    int stage = 0;
+    for (int b0 = 0; b0 < batch; b0 += gb, stage ^= 1) {
+        const int nb = std::min(gb, batch - b0);
+        CUDA_TRY(cudaStreamWaitEvent(pl->s_copy, pl->ev_done[stage], 0));
+        CUDA_TRY(cudaMemcpyAsync(pl->d_stage_mom[stage], h_mom + (size_t)b0 * pl->nmom * 2,
+                                 (size_t)nb * pl->nmom * 2 * sizeof(float), cudaMemcpyHostToDevice, pl->s_copy));
+        CUDA_TRY(cudaEventRecord(pl->ev_in[stage], pl->s_copy));
+        CUDA_TRY(cudaStreamWaitEvent(pl->s_comp, pl->ev_in[stage], 0));
+        rc = z3d_reconstruct(pl, pl->d_stage_mom[stage], nb, 0, pl->H, pl->d_stage_vol[stage], pl->d_stage_ws[stage],
+                             z3d_workspace_bytes(pl, gb), pl->s_comp);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_vol + (size_t)b0 * N3, pl->d_stage_vol[stage], (size_t)nb * N3 * sizeof(float),
+                                 cudaMemcpyDeviceToHost, pl->s_comp));
+        CUDA_TRY(cudaEventRecord(pl->ev_done[stage], pl->s_comp));
+    }
+    CUDA_TRY(cudaStreamSynchronize(pl->s_comp));
+    CUDA_TRY(cudaStreamSynchronize(pl->s_copy));
+    return Z3D_OK;
+}
+
+extern "C" int z3d_fma_peak(int device, int variant, int iters, double *tflops) {
+    if (!tflops || iters < 1) return fail(Z3D_ERR_INVALID, "z3d_fma_peak: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) {
+        cudaGetLastError();
+        return fail(Z3D_ERR_NODEVICE, "z3d_fma_peak: no such CUDA device");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 4, threads = 512;
+    float *d_out;
+    CUDA_TRY(cudaMalloc((void **)&d_out, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    k_fma_peak<<<blocks, threads>>>(iters, d_out, variant);  // warm-up
+    CUDA_TRY(cudaEventRecord(e0));
+    k_fma_peak<<<blocks, threads>>>(iters, d_out, variant);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    g_launches += 2;
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = (double)blocks * threads * (double)iters * 8.0 * 8.0 * 2.0;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return Z3D_OK;
+}

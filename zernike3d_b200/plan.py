@@ -1,0 +1,152 @@
+"""``Plan``: thin host object around one ``z3d_plan`` (order, box size, device).
+
+It replaces what ``ZernikeSpherical.CalculatePolynomials`` builds in the reference (zernike_master.py:
+2237-2323) - but holds only recurrence-coefficient and tile tables (a few hundred KB), never an
+R_nl / Y_lm voxel grid.  PyTorch owns the device buffers and streams; all arithmetic happens in the
+hand-written sm_100a kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Plan:
+    INFO_KEYS = ("order", "dim", "num_moments", "passes", "ctas", "threads", "tiles_per_thread", "smem_bytes",
+                 "voxels_per_chunk", "sms", "useful_accumulators", "padded_accumulators")
+
+    def __init__(self, order: int, dim: int, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise _lib.Z3DError(_lib.ERR_NODEVICE, "no CUDA device: zernike3d_b200 has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._L = _lib.lib()
+        h = ctypes.c_void_p()
+        _lib.check(self._L.z3d_plan_create(int(order), int(dim), self.device, ctypes.byref(h)))
+        self._h = h
+        self.order, self.dim = int(order), int(dim)
+        self.num_moments = self._L.z3d_num_moments(self.order)
+        self.num_radial = self._L.z3d_num_radial(self.order)
+        self.half = (self.dim + 1) // 2
+        self._ws = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._L.z3d_plan_destroy(h)
+            except Exception:
+                pass
+
+    # ------------------------------------------------------------------ helpers
+    def info(self) -> dict:
+        arr = (ctypes.c_int * 12)()
+        _lib.check(self._L.z3d_plan_info(self._h, arr, 12))
+        return dict(zip(self.INFO_KEYS, list(arr)))
+
+    def workspace_bytes(self, batch: int) -> int:
+        return int(self._L.z3d_workspace_bytes(self._h, int(batch)))
+
+    def _workspace(self, batch: int) -> torch.Tensor:
+        need = self.workspace_bytes(batch)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
+        return self._ws
+
+    @staticmethod
+    def _stream(stream) -> ctypes.c_void_p:
+        s = torch.cuda.current_stream() if stream is None else stream
+        return ctypes.c_void_p(s.cuda_stream)
+
+    def _pairs(self, pairs):
+        lo, hi = (0, self.half) if pairs is None else pairs
+        return int(lo), int(hi)
+
+    # ------------------------------------------------------------------ device-buffer API
+    def decompose(self, vol: torch.Tensor, pairs=None, out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
+        """``vol`` float32 CUDA ``[B, N, N, N]`` (or ``[N, N, N]``) -> complex64 ``[B, num_moments]``.
+
+        ``pairs=(lo, hi)`` restricts the voxel sum to the mirrored plane pairs lo..hi-1 of axis 0
+        (slab partial for the multi-GPU path); the default is the whole volume."""
+        single = vol.dim() == 3
+        v = vol.unsqueeze(0) if single else vol
+        N = self.dim
+        if v.dtype != torch.float32 or not v.is_cuda or tuple(v.shape[1:]) != (N, N, N):
+            raise ValueError(f"expected a float32 CUDA tensor [B,{N},{N},{N}], got {v.dtype} {tuple(v.shape)} on {v.device}")
+        v = v.contiguous()
+        B = v.shape[0]
+        if out is None:
+            out = torch.empty((B, self.num_moments), dtype=torch.complex64, device=v.device)
+        ws = self._workspace(B)
+        lo, hi = self._pairs(pairs)
+        _lib.check(self._L.z3d_decompose(self._h, _ptr(v), B, lo, hi, _ptr(out), _ptr(ws), ws.numel(),
+                                         self._stream(stream)))
+        return out[0] if single else out
+
+    def reconstruct(self, moments: torch.Tensor, pairs=None, out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
+        """complex64 CUDA ``[B, num_moments]`` -> float32 ``[B, N, N, N]`` (planes outside ``pairs`` untouched)."""
+        single = moments.dim() == 1
+        m = moments.unsqueeze(0) if single else moments
+        if m.dtype != torch.complex64 or not m.is_cuda or m.shape[1] != self.num_moments:
+            raise ValueError(f"expected complex64 CUDA [B,{self.num_moments}], got {m.dtype} {tuple(m.shape)}")
+        m = m.contiguous()
+        B, N = m.shape[0], self.dim
+        if out is None:
+            out = torch.zeros((B, N, N, N), dtype=torch.float32, device=m.device)
+        ws = self._workspace(B)
+        lo, hi = self._pairs(pairs)
+        _lib.check(self._L.z3d_reconstruct(self._h, _ptr(m), B, lo, hi, _ptr(out), _ptr(ws), ws.numel(),
+                                           self._stream(stream)))
+        return out[0] if single else out
+
+    def invariants(self, moments: torch.Tensor, stream=None) -> torch.Tensor:
+        single = moments.dim() == 1
+        m = (moments.unsqueeze(0) if single else moments).contiguous()
+        out = torch.empty((m.shape[0], self.num_radial), dtype=torch.float32, device=m.device)
+        _lib.check(self._L.z3d_invariants(self._h, _ptr(m), m.shape[0], _ptr(out), self._stream(stream)))
+        return out[0] if single else out
+
+    # ------------------------------------------------------------------ host-buffer API
+    def decompose_host(self, vol, out=None):
+        """numpy / pinned-tensor volumes ``[B, N, N, N]`` float32 -> numpy complex64 ``[B, num_moments]``.
+        H2D, kernels and D2H are pipelined inside the library (``z3d_decompose_host``)."""
+        v = vol.numpy() if isinstance(vol, torch.Tensor) else np.asarray(vol)
+        single = v.ndim == 3
+        v = np.ascontiguousarray(v[None] if single else v, dtype=np.float32)
+        B = v.shape[0]
+        if out is None:
+            out = np.empty((B, self.num_moments), dtype=np.complex64)
+        o = out.numpy() if isinstance(out, torch.Tensor) else out
+        _lib.check(self._L.z3d_decompose_host(self._h, ctypes.c_void_p(v.ctypes.data), B,
+                                              ctypes.c_void_p(o.ctypes.data)))
+        return out[0] if single else out
+
+    def reconstruct_host(self, moments, out=None):
+        m = moments.numpy() if isinstance(moments, torch.Tensor) else np.asarray(moments)
+        single = m.ndim == 1
+        m = np.ascontiguousarray(m[None] if single else m, dtype=np.complex64)
+        B, N = m.shape[0], self.dim
+        if out is None:
+            out = np.empty((B, N, N, N), dtype=np.float32)
+        o = out.numpy() if isinstance(out, torch.Tensor) else out
+        _lib.check(self._L.z3d_reconstruct_host(self._h, ctypes.c_void_p(m.ctypes.data), B,
+                                                ctypes.c_void_p(o.ctypes.data)))
+        return out[0] if single else out
+
+
+def launch_count() -> int:
+    return int(_lib.lib().z3d_launch_count())
+
+
+def fma_peak_tflops(device: int = 0, variant: int = 0, iters: int = 4096) -> float:
+    v = ctypes.c_double()
+    _lib.check(_lib.lib().z3d_fma_peak(device, variant, iters, ctypes.byref(v)))
+    return v.value
