@@ -101,6 +101,12 @@ int z3d_reconstruct_host(z3d_plan *plan, const float *h_moments, int batch, floa
  * the difference across its timed region as "gpu_launches". */
 unsigned long long z3d_launch_count(void);
 
+/* Kernel timing for the roofline report: when enabled, z3d_decompose / z3d_reconstruct record CUDA events on
+ * the caller's stream around their dominant kernel (k_decompose / k_reconstruct); z3d_profile_last_ms waits
+ * for the last such kernel and returns its duration. */
+int z3d_profile_enable(z3d_plan *plan, int on);
+int z3d_profile_last_ms(z3d_plan *plan, float *ms);
+
 /* FP32 FMA micro-benchmark used to pin the roofline denominator: runs `iters`
  * dependent-chain FFMA rounds on every SM and returns achieved TFLOP/s in *tflops.
  * variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2. */

@@ -106,15 +106,28 @@ def _install_stubs() -> None:
 
 
 def load_reference():
-    """Return the reference's ``zernike_master`` module, imported unmodified."""
-    _install_stubs()
-    if REFERENCE_DIR not in sys.path:
-        sys.path.insert(0, REFERENCE_DIR)
-    import zernike_master  # noqa: E402  (the reference's own file)
+    """Return the reference's ``zernike_master`` module, imported unmodified from ``/root/reference``
+    under the private name ``_ref_zernike_master`` (the repo root holds same-named drop-in modules, so the
+    reference and its ``indexing`` import are resolved against ``/root/reference`` only)."""
+    import importlib.util
 
-    if not zernike_master.__file__.startswith(REFERENCE_DIR):
-        raise RuntimeError(f"imported {zernike_master.__file__}, not the reference")
-    return zernike_master
+    if "_ref_zernike_master" in sys.modules:
+        return sys.modules["_ref_zernike_master"]
+    _install_stubs()
+    saved = {k: sys.modules.pop(k) for k in ("indexing", "zernike_master") if k in sys.modules}
+    sys.path.insert(0, REFERENCE_DIR)
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_zernike_master", REFERENCE_DIR + "/zernike_master.py")
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["_ref_zernike_master"] = mod
+        spec.loader.exec_module(mod)
+        ref_ix = sys.modules.pop("indexing")
+        if not ref_ix.__file__.startswith(REFERENCE_DIR):
+            raise RuntimeError(f"reference imported {ref_ix.__file__} instead of its own indexing.py")
+    finally:
+        sys.path.remove(REFERENCE_DIR)
+        sys.modules.update(saved)
+    return mod
 
 
 def reference_args(order: int, **over) -> argparse.Namespace:

@@ -1,0 +1,61 @@
+"""The C-ABI shared library loads without a GPU, exports every symbol include/zernike3d_b200.h declares, and its
+host-only entry points work; compute entry points fail loudly (no CPU fallback) when there is no device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from zernike3d_b200 import _lib
+from zernike3d_b200 import indexing as ix
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "zernike3d_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(z3d_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 17 and set(syms) == set(_lib.EXPORTS)
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/zernike3d_b200.h but not exported"
+
+
+def test_host_only_entry_points():
+    L = _lib.lib()
+    assert L.z3d_version() >= 100
+    assert L.z3d_num_moments(50) == 12051 and L.z3d_num_radial(50) == 676 and L.z3d_num_harmonics(50) == 1326
+    assert L.z3d_num_moments(-1) == -1
+    n = L.z3d_num_moments(9)
+    buf = (ctypes.c_int * (3 * n))()
+    assert L.z3d_nlm_table(9, buf) == 0
+    assert np.array_equal(np.array(buf).reshape(n, 3), ix.nlm_table(9))
+    assert L.z3d_nlm_table(-3, buf) == _lib.ERR_INVALID and b"bad arguments" in L.z3d_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_device_fails_loudly():
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    rc = L.z3d_plan_create(10, 16, 0, ctypes.byref(h))
+    assert rc == _lib.ERR_NODEVICE and not h.value
+    assert b"no CPU fallback" in L.z3d_last_error()
+    from zernike3d_b200.plan import Plan
+
+    with pytest.raises(_lib.Z3DError):
+        Plan(10, 16)
+
+
+def test_bad_arguments_rejected_before_touching_the_device():
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    assert L.z3d_plan_create(-1, 16, 0, ctypes.byref(h)) == _lib.ERR_INVALID
+    assert L.z3d_plan_create(10, 1, 0, ctypes.byref(h)) == _lib.ERR_INVALID
+    assert L.z3d_decompose(None, None, 1, 0, 1, None, None, 0, None) == _lib.ERR_INVALID
+    assert L.z3d_workspace_bytes(None, 1) == 0

@@ -1,0 +1,249 @@
+"""Parity of the CUDA path (through the C ABI) with the reference goldens and the CPU oracle.
+
+Tolerances are the north-star's, norm-wise (relative L2 over the whole vector):
+  moments <= 1e-5, reconstructed map <= 1e-5, invariant vector <= 1e-6.
+The reference itself is 2e-6 (64^3) .. 5e-6 (128^3) away from an exact evaluation because it sums float32
+products in BLAS (zm:2210); against the float64 oracle the kernels are held to a tighter 1.5e-6.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_l2
+from zernike3d_b200.synthetic import bundle_3dva, volume
+
+pytestmark = pytest.mark.gpu
+
+TOL_MOM, TOL_MAP, TOL_INV = 1e-5, 1e-5, 1e-6
+TOL_EXACT = 1.5e-6
+
+
+@pytest.fixture(scope="module")
+def plans():
+    from zernike3d_b200.plan import Plan
+
+    cache = {}
+
+    def get(order, dim):
+        if (order, dim) not in cache:
+            cache[(order, dim)] = Plan(order, dim)
+        return cache[(order, dim)]
+
+    yield get
+    cache.clear()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name", ["d16_o10", "d15_o8", "d32_o20", "d20_o25", "c1_d64_o50", "c3_d128_o50", "c5_d96_o60"])
+def test_decompose_vs_reference_golden(plans, oracle_mod, name):
+    g = golden(name)
+    order, dim = int(g["order"]), int(g["dim"])
+    P = plans(order, dim)
+    for si, seed in enumerate(g["seeds"]):
+        v = volume(int(seed), dim)
+        mom = P.decompose(dev(v)).cpu().numpy()
+        assert mom.dtype == np.complex64 and mom.shape == (P.num_moments,)
+        assert rel_l2(mom, g["moments"][si]) < TOL_MOM
+        inv = P.invariants(dev(mom)).cpu().numpy()
+        # the 1e-6 bar on invariants holds against the exact oracle everywhere; against the reference's own
+        # float32-BLAS numbers it holds up to 96^3 and is 2.3e-6 at 128^3 (reference noise)
+        assert rel_l2(inv, oracle_mod.invariants(mom, order)) < 2e-7
+        if dim <= 96:
+            assert rel_l2(inv, g["invariants"][si]) < TOL_INV
+        else:
+            assert rel_l2(inv, g["invariants"][si]) < 5e-6
+        if dim <= 64:
+            exact = oracle_mod.decompose(v, order, oracle_mod.EXACT)
+            assert rel_l2(mom, exact) < TOL_EXACT
+            assert rel_l2(inv, oracle_mod.invariants(exact, order)) < TOL_INV
+
+
+@pytest.mark.parametrize("name", ["d16_o10", "d15_o8", "d32_o20", "d20_o25", "c1_d64_o50"])
+def test_reconstruct_vs_reference_golden(plans, name):
+    g = golden(name)
+    order, dim = int(g["order"]), int(g["dim"])
+    P = plans(order, dim)
+    for si in range(len(g["seeds"])):
+        rec = P.reconstruct(dev(g["moments"][si])).cpu().numpy()
+        assert rec.dtype == np.float32 and rec.shape == (dim, dim, dim)
+        assert np.isfinite(rec).all()
+        assert rel_l2(rec, g["recon"][si]) < TOL_MAP
+
+
+def test_128_order50_against_exact_oracle_rows(plans, oracle_mod):
+    """Headline configuration against the float64 oracle on a bounded sample: slab partials of 4 plane pairs."""
+    order, dim = 50, 128
+    P = plans(order, dim)
+    v = volume(1, dim)
+    dv = dev(v)
+    for lo, hi in [(0, 1), (37, 38), (63, 64)]:
+        got = P.decompose(dv, pairs=(lo, hi)).cpu().numpy()
+        want = (oracle_mod.decompose(v, order, oracle_mod.EXACT, rows=(lo, hi), return_f64=True)
+                + oracle_mod.decompose(v, order, oracle_mod.EXACT, rows=(dim - hi, dim - lo), return_f64=True))
+        assert rel_l2(got, want) < TOL_EXACT
+    mom = golden("c3_d128_o50")["moments"][0]
+    rec = P.reconstruct(dev(mom)).cpu().numpy()
+    scale = np.sqrt(np.mean(rec.astype(np.float64) ** 2))        # whole-map RMS: the bar is norm-wise over the map
+    for p in [0, 40, 64, 127]:
+        want = oracle_mod.reconstruct(mom, dim, order, oracle_mod.EXACT, rows=(p, p + 1))[0]
+        assert rel_l2(rec[p], want) < TOL_MAP                    # even per plane (edge planes are ~100x fainter)
+        assert np.sqrt(np.mean((rec[p] - want) ** 2)) / scale < TOL_EXACT
+
+
+def test_3dva_bundle_batched(plans):
+    g = golden("3dva_d24_o12")
+    order, dim = int(g["order"]), int(g["dim"])
+    _, cons, comps = bundle_3dva(dim, components=5, particles=64, seed=2)
+    vols = np.stack([cons, *comps])
+    P = plans(order, dim)
+    moms = P.decompose(dev(vols)).cpu().numpy()       # one batched call for base map + 5 components
+    assert moms.shape == (6, P.num_moments)
+    for i in range(6):
+        assert rel_l2(moms[i], g["moments"][i]) < TOL_MOM
+    one_by_one = np.stack([P.decompose(dev(v)).cpu().numpy() for v in vols])
+    assert np.array_equal(moms, one_by_one)           # batching does not change a single bit
+
+
+def test_slab_partials_are_additive_and_only_read_their_planes(plans):
+    order, dim = 20, 32
+    P = plans(order, dim)
+    v = volume(9, dim)
+    full = P.decompose(dev(v)).cpu().numpy()
+    h = P.half
+    acc = np.zeros_like(full)
+    for lo, hi in [(0, 3), (3, 11), (11, h)]:
+        poisoned = np.full_like(v, np.nan)
+        planes = list(range(lo, hi)) + [dim - 1 - p for p in range(lo, hi)]
+        poisoned[planes] = v[planes]
+        part = P.decompose(dev(poisoned), pairs=(lo, hi)).cpu().numpy()
+        assert np.isfinite(part).all()
+        acc += part
+    assert rel_l2(acc, full) < 5e-7
+    # reconstruction writes only its planes
+    out = torch.full((1, dim, dim, dim), 7.0, device="cuda")
+    P.reconstruct(dev(full).unsqueeze(0), pairs=(2, 5), out=out)
+    out = out[0].cpu().numpy()
+    ref = P.reconstruct(dev(full)).cpu().numpy()
+    touched = [2, 3, 4, dim - 3, dim - 4, dim - 5]
+    for p in range(dim):
+        assert np.array_equal(out[p], ref[p]) if p in touched else np.all(out[p] == 7.0)
+
+
+def test_deterministic_and_linear(plans):
+    order, dim = 50, 64
+    P = plans(order, dim)
+    a, b = dev(volume(1, dim)), dev(volume(2, dim))
+    m1 = P.decompose(a)
+    m2 = P.decompose(a)
+    assert torch.equal(torch.view_as_real(m1), torch.view_as_real(m2))     # fixed-order partial combination
+    mab = P.decompose(2.0 * a - 0.5 * b).cpu().numpy()
+    lin = (2.0 * m1 - 0.5 * P.decompose(b)).cpu().numpy()
+    assert rel_l2(mab, lin) < 2e-6
+
+
+def test_invariants_under_axis_permutation_and_flips(plans):
+    """F_nl is rotation invariant; the 90-degree rotations / mirror flips that map the symmetric grid onto itself
+    are exact symmetries of the discrete sum, so the invariants agree to float32 round-off."""
+    order, dim = 30, 48
+    P = plans(order, dim)
+    v = volume(4, dim)
+    base = P.invariants(P.decompose(dev(v))).cpu().numpy()
+    for w in (np.rot90(v, 1, axes=(0, 1)), np.rot90(v, 1, axes=(1, 2)), v[::-1, ::-1, :], np.transpose(v, (2, 0, 1))):
+        inv = P.invariants(P.decompose(dev(np.ascontiguousarray(w)))).cpu().numpy()
+        assert rel_l2(inv, base) < TOL_INV
+
+
+def test_round_trip_full_size_properties(plans):
+    """BASELINE sizes without a CPU oracle run: decompose -> reconstruct gain ~ 1/(4 pi) ((N-1)/N)^3 (zm:2198)."""
+    for order, dim in [(50, 128), (60, 96)]:
+        P = plans(order, dim)
+        v = volume(3, dim)
+        rec = P.reconstruct(P.decompose(dev(v))).cpu().numpy().astype(np.float64)
+        gain = float(np.vdot(rec.ravel(), v.ravel()) / np.vdot(v.ravel(), v.ravel()))
+        want = (1 / (4 * np.pi)) * ((dim - 1) / dim) ** 3
+        assert abs(gain / want - 1) < 0.1
+        smooth = rec / gain
+        cc = np.corrcoef(smooth.ravel(), v.ravel())[0, 1]
+        assert cc > 0.9
+
+
+def test_256_stress_case(plans):
+    """C5b: 256^3 order 50 (the reference would need a 223 GB basis).  Size-independent checks: slab additivity,
+    real m = 0 moments, determinism."""
+    order, dim = 50, 256
+    P = plans(order, dim)
+    dv = dev(volume(8, dim))
+    full = P.decompose(dv)
+    parts = P.decompose(dv, pairs=(0, 50)) + P.decompose(dv, pairs=(50, 128))
+    assert rel_l2(parts.cpu().numpy(), full.cpu().numpy()) < 5e-7
+    from zernike3d_b200.indexing import nlm_table
+
+    m0 = nlm_table(order)[:, 2] == 0
+    f = full.cpu().numpy()
+    assert np.all(f.imag[m0] == 0) and np.isfinite(f.view(np.float32)).all()
+
+
+def test_host_buffer_api_matches_device_api(plans):
+    order, dim = 50, 64
+    P = plans(order, dim)
+    vols = np.stack([volume(s, dim) for s in range(5)])
+    pinned = torch.from_numpy(vols).pin_memory()
+    mh = P.decompose_host(pinned)
+    md = P.decompose(dev(vols)).cpu().numpy()
+    assert np.array_equal(mh, md)
+    rh = P.reconstruct_host(mh)
+    rd = P.reconstruct(dev(mh)).cpu().numpy()
+    assert np.array_equal(rh, rd)
+
+
+def test_error_paths(plans):
+    from zernike3d_b200 import _lib
+
+    P = plans(10, 16)
+    with pytest.raises(ValueError):
+        P.decompose(torch.zeros(16, 16, 8, device="cuda"))
+    with pytest.raises(ValueError):
+        P.decompose(torch.zeros(16, 16, 16))
+    with pytest.raises(_lib.Z3DError):
+        P.decompose(torch.zeros(16, 16, 16, device="cuda"), pairs=(0, 99))
+    with pytest.raises(ValueError):
+        P.reconstruct(torch.zeros(5, dtype=torch.complex64, device="cuda"))
+
+
+def test_cli_end_to_end(tmp_path, oracle_mod):
+    """`zernike_master.py decomposition` -> .npz -> `reconstruct` -> .mrc, compared with the oracle."""
+    import zernike_master as cli
+    from zernike3d_b200 import mrc
+    from zernike3d_b200.moments import Moments
+
+    order, dim = 12, 24
+    v = volume(6, dim)
+    src = str(tmp_path / "in.mrc")
+    mrc.write(src, v, 1.4)
+    out = str(tmp_path / "mom")
+    assert cli.main(f"decomposition --mode spharm --input {src} --order {order} --compute_mode 3 --output {out} --verbose".split()) == 0
+    with np.load(out + ".npz") as f:
+        assert sorted(f.files) == ["apix", "arr_0", "dim"] and int(f["dim"]) == dim and abs(float(f["apix"]) - 1.4) < 1e-6
+        mom = f["arr_0"]
+    assert rel_l2(mom, oracle_mod.decompose(v, order, oracle_mod.EXACT)) < TOL_EXACT
+    rec = str(tmp_path / "rec.mrc")
+    assert cli.main(f"reconstruct --mode spharm --moments {out}.npz --order {order} --dimensions {dim} --output {rec}".split()) == 0
+    back = mrc.read(str(tmp_path / "rec_0.mrc")).data          # `<out>_<rec>.mrc` (zm:2714)
+    assert rel_l2(back, oracle_mod.reconstruct(mom, dim, order, oracle_mod.EXACT)) < TOL_EXACT
+
+    # 3DVA bundle in, latents + arr_0..arr_K out, then a latent-scaled reconstruction
+    part, cons, comps = bundle_3dva(dim, components=2, particles=16, seed=2)
+    bundle = str(tmp_path / "bundle.npz")
+    np.savez(bundle, particles=part, consensus_map=cons, components=comps)
+    out2 = str(tmp_path / "mom3dva.npz")
+    assert cli.main(f"decomposition --mode spharm --input {bundle} --order {order} --output {out2}".split()) == 0
+    M = Moments(quiet=True)
+    assert M.load(out2) == 3 and M.latents.shape == (16, 2)
+    assert cli.main(f"reconstruct --mode spharm --moments {out2} --order {order} --dimensions {dim} --z_ind 3 --output {rec}".split()) == 0
+    scaled = mrc.read(str(tmp_path / "rec_scaled_3.mrc")).data
+    w = np.concatenate([[1.0], M.latents[3]]).astype(np.float32)
+    want = oracle_mod.reconstruct((w[:, None] * M.as_matrix()).sum(0).astype(np.complex64), dim, order, oracle_mod.EXACT)
+    assert rel_l2(scaled, want) < 5e-6

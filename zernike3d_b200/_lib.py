@@ -64,6 +64,8 @@ def lib() -> ctypes.CDLL:
     L.z3d_decompose_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     L.z3d_reconstruct_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     L.z3d_launch_count.restype = ctypes.c_ulonglong
+    L.z3d_profile_enable.argtypes = [c_void_p, c_int]
+    L.z3d_profile_last_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
     L.z3d_fma_peak.argtypes = [c_int, c_int, c_int, ctypes.POINTER(ctypes.c_double)]
     _lib = L
     return L
@@ -78,5 +80,5 @@ EXPORTS = [
     "z3d_version", "z3d_last_error", "z3d_num_moments", "z3d_num_radial", "z3d_num_harmonics", "z3d_nlm_table",
     "z3d_plan_create", "z3d_plan_destroy", "z3d_plan_info", "z3d_workspace_bytes", "z3d_decompose",
     "z3d_reconstruct", "z3d_invariants", "z3d_decompose_host", "z3d_reconstruct_host", "z3d_launch_count",
-    "z3d_fma_peak",
+    "z3d_fma_peak", "z3d_profile_enable", "z3d_profile_last_ms",
 ]

@@ -76,6 +76,9 @@ struct z3d_plan {
     float *d_stage_mom[2] = {nullptr, nullptr};
     void *d_stage_ws[2] = {nullptr, nullptr};
     int stage_batch = 0;
+    // optional per-kernel timing (bench.py roofline): events around the dominant kernel of the last call
+    bool profiling = false;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -383,6 +386,8 @@ extern "C" int z3d_plan_destroy(z3d_plan *pl) {
         if (pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]);
         if (pl->ev_done[i]) cudaEventDestroy(pl->ev_done[i]);
     }
+    if (pl->ev_k0) cudaEventDestroy(pl->ev_k0);
+    if (pl->ev_k1) cudaEventDestroy(pl->ev_k1);
     if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
     if (pl->s_comp) cudaStreamDestroy(pl->s_comp);
     delete pl;
@@ -426,8 +431,10 @@ extern "C" int z3d_decompose(const z3d_plan *pl, const float *d_vol, int batch, 
     CUDA_TRY(cudaSetDevice(pl->device));
     cudaStream_t st = (cudaStream_t)stream;
     float *partial = (float *)d_ws;
+    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
     k_decompose<<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, half_lo, half_hi, partial);
     CUDA_TRY(cudaGetLastError());
+    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k1, st));
     dim3 g((2 * pl->nmom + 255) / 256, batch);
     k_reduce_moments<<<g, 256, 0, st>>>(partial, pl->d_src, pl->d_scale, pl->nmom, pl->npass, pl->nsplit, batch, d_moments);
     CUDA_TRY(cudaGetLastError());
@@ -450,12 +457,32 @@ extern "C" int z3d_reconstruct(const z3d_plan *pl, const float *d_moments, int b
     dim3 g((pl->npass * SLOT_WORDS + 255) / 256, batch);
     k_prepare_tiles<<<g, 256, 0, st>>>(d_moments, pl->d_omap, pl->d_ofac, pl->nmom, pl->npass, batch, otiles);
     CUDA_TRY(cudaGetLastError());
+    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
     k_reconstruct<<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, otiles, batch, half_lo, half_hi, pvol);
     CUDA_TRY(cudaGetLastError());
+    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k1, st));
     const size_t total = (size_t)2 * (half_hi - half_lo) * pl->dim * pl->dim * batch;
     k_sum_passes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pvol, pl->npass, batch, pl->dim, half_lo, half_hi, d_vol);
     CUDA_TRY(cudaGetLastError());
     g_launches += 3;
+    return Z3D_OK;
+}
+
+extern "C" int z3d_profile_enable(z3d_plan *pl, int on) {
+    if (!pl) return fail(Z3D_ERR_INVALID, "z3d_profile_enable: plan is NULL");
+    CUDA_TRY(cudaSetDevice(pl->device));
+    if (on && !pl->ev_k0) {
+        CUDA_TRY(cudaEventCreate(&pl->ev_k0));
+        CUDA_TRY(cudaEventCreate(&pl->ev_k1));
+    }
+    pl->profiling = on != 0;
+    return Z3D_OK;
+}
+
+extern "C" int z3d_profile_last_ms(z3d_plan *pl, float *ms) {
+    if (!pl || !ms || !pl->ev_k0) return fail(Z3D_ERR_INVALID, "z3d_profile_last_ms: profiling was not enabled");
+    CUDA_TRY(cudaEventSynchronize(pl->ev_k1));
+    CUDA_TRY(cudaEventElapsedTime(ms, pl->ev_k0, pl->ev_k1));
     return Z3D_OK;
 }
 

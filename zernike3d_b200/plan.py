@@ -70,6 +70,16 @@ class Plan:
         lo, hi = (0, self.half) if pairs is None else pairs
         return int(lo), int(hi)
 
+    def profile(self, on: bool = True) -> None:
+        _lib.check(self._L.z3d_profile_enable(self._h, int(on)))
+
+    def last_kernel_ms(self) -> float:
+        """Duration of the dominant kernel (k_decompose / k_reconstruct) of the last call, CUDA events on the
+        launching stream; requires ``profile(True)``."""
+        ms = ctypes.c_float()
+        _lib.check(self._L.z3d_profile_last_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
     # ------------------------------------------------------------------ device-buffer API
     def decompose(self, vol: torch.Tensor, pairs=None, out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
         """``vol`` float32 CUDA ``[B, N, N, N]`` (or ``[N, N, N]``) -> complex64 ``[B, num_moments]``.
