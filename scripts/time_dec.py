@@ -1,0 +1,13 @@
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import torch
+from zernike3d_b200.plan import Plan
+from zernike3d_b200.synthetic import volume
+dim, order, B = int(sys.argv[1]), int(sys.argv[2]), 4
+P = Plan(order, dim); P.profile(True)
+v = torch.from_numpy(volume(1, dim)).cuda().unsqueeze(0).repeat(B, 1, 1, 1).contiguous()
+for _ in range(3): P.decompose(v)
+ms = []
+for _ in range(5):
+    P.decompose(v); ms.append(P.last_kernel_ms() / B)
+print(os.environ.get("Z3D_LIB_OVERRIDE", "default"), f"k_decompose {min(ms):.3f} ms/vol")

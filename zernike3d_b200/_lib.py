@@ -10,7 +10,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libz3d_b200.so")
+LIB_PATH = os.environ.get("Z3D_LIB_OVERRIDE") or os.path.join(HERE, "libz3d_b200.so")  # override: developer experiments only
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NODEVICE, ERR_WORKSPACE, ERR_UNSUPPORTED = range(6)
 

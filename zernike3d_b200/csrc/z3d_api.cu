@@ -110,28 +110,33 @@ namespace {
 struct HostPlan {
     int L, npass;
     std::vector<int> lpass, roffw, poffw, rbase, ownl, nown, ntiles, gen_tasks;
-    std::vector<int2> tiles;
-    std::vector<float> beta;
-    std::vector<float4> rk;
+    std::vector<TileDesc> tiles;
+    std::vector<float2> gd;     // [npass][GD_MAX] (gamma, -delta) of the parity-decoupled Legendre recurrence
+    std::vector<int> goff;      // [npass][L+1]
+    std::vector<float4> rk;     // [npass][RK_MAX]
     std::vector<double> kappa;  // [(L+1)*(L+1)] kappa[l*(L+1)+m]
     std::vector<int> src, omap;
     int useful = 0, padded = 0;
 };
+
+inline int padT(int x) { return (x + TILE - 1) / TILE * TILE; }
 
 // pass(l): same parity inside a pass (the synthesis kernel relies on it), round-robin over l/2
 inline int pass_of(int l, int npass) { return (l & 1) + 2 * ((l >> 1) % (npass / 2)); }
 
 bool layout_fits(int L, int npass) {
     for (int p = 0; p < npass; ++p) {
-        int rw = 0, pw = 0, nt = 0;
+        int rw = 0, pw = 0, nt = 0, nrk = 0, ngd = 8;
         for (int l = 0; l <= L; ++l) {
             if (pass_of(l, npass) != p) continue;
             const int nn = (L - l) / 2 + 1, m2 = 2 * (l + 1);
-            rw += pad4(nn);
-            pw += pad4(m2);
-            nt += (pad4(nn) / 4) * (pad4(m2) / 4);
+            rw += padT(nn);
+            pw += padT(m2);
+            nt += (padT(nn) / TILE) * (padT(m2) / TILE);
+            nrk += nn;
         }
-        if (rw > RS || pw > PS || nt > NT * TS) return false;
+        for (int m = 0; m <= L; ++m) ngd += (L - m) / 2 + 2;
+        if (rw > RS || pw > PS || nt > NT * TS || nrk > RK_MAX || ngd > GD_MAX) return false;
     }
     return true;
 }
@@ -150,13 +155,13 @@ int build_host_plan(int L, HostPlan &hp) {
     hp.ownl.assign((size_t)npass * S, -1);
     hp.nown.assign(npass, 0);
     hp.ntiles.assign(npass, 0);
-    hp.tiles.assign((size_t)npass * NT * TS, make_int2(0, 0));
+    hp.tiles.assign((size_t)npass * NT * TS, TileDesc{0, 4, 0, 4});
     hp.gen_tasks.assign((size_t)npass * NWARP * MAXTASK, 0);
 
     // ---- coefficient tables (float64 on the host, like the reference's Python scalars)
     // Legendre: C1, C2 of zm:2017-2024, C3 of zm:2013; kappa_mm = P_mm / sin^m, kappa_lm = kappa_{l-1,m} C1/2
     hp.kappa.assign((size_t)S * S, 0.0);
-    hp.beta.assign((size_t)S * S, 0.0f);
+    std::vector<double> beta((size_t)S * (S + 3), 0.0);  // beta[m*(S+3) + l], zero for l <= m+1 and l > L
     std::vector<double> C1((size_t)S * S, 0.0), C2((size_t)S * S, 0.0);
     for (int l = 1; l <= L; ++l)
         for (int m = 0; m < l; ++m) {
@@ -171,24 +176,43 @@ int build_host_plan(int L, HostPlan &hp) {
         for (int l = m + 1; l <= L; ++l) {
             hp.kappa[(size_t)l * S + m] = hp.kappa[(size_t)(l - 1) * S + m] * C1[(size_t)l * S + m] * 0.5;
             if (l >= m + 2)
-                hp.beta[(size_t)m * S + l] =
-                    (float)(C2[(size_t)l * S + m] * 4.0 / (C1[(size_t)l * S + m] * C1[(size_t)(l - 1) * S + m]));
+                beta[(size_t)m * (S + 3) + l] = C2[(size_t)l * S + m] * 4.0 / (C1[(size_t)l * S + m] * C1[(size_t)(l - 1) * S + m]);
         }
     }
-    // Radial: K1, K2, K3 of zm:1992-1998, l-major
-    hp.rk.clear();
-    for (int l = 0; l <= L; ++l) {
-        hp.rbase[l] = (int)hp.rk.size();
-        for (int n = l; n <= L; n += 2) {
-            float4 K = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n > l) {
-                const double k0 = (double)(n - l) * (n + l + 1) * (2 * n - 3);
-                const double k1 = (double)(2 * n - 1) * (2 * n + 1) * (2 * n - 3);
-                const double k2 = 0.5 * (double)(-2 * n + 1) * (double)((2 * l + 1) * (2 * l + 1)) - k1 / 2.0;
-                const double k3 = -1.0 * (double)(n - l - 2) * (n + l - 1) * (2 * n + 1);
-                K = make_float4((float)(k1 / k0), (float)(k2 / k0), (float)(k3 / k0), 0.f);
+    // parity-decoupled form: Q_{l+2} = (4c^2 - gamma) Q_l - delta Q_{l-2}, gamma = beta_{l+2} + beta_{l+1},
+    // delta = beta_{l+1} beta_l; chain (parity, m) starts at l0 = first l >= m of that parity.  One table per pass
+    // (only the pass's parity), copied to shared memory by the kernels.
+    hp.gd.assign((size_t)npass * GD_MAX, make_float2(0.f, 0.f));
+    hp.goff.assign((size_t)npass * S, 0);
+    for (int p = 0; p < npass; ++p) {
+        const int par = p & 1;
+        int pos = 8;  // readable pad in front: lanes whose chain has not started index a few entries before it
+        for (int m = 0; m <= L; ++m) {
+            hp.goff[(size_t)p * S + m] = pos;
+            const double *bm = &beta[(size_t)m * (S + 3)];
+            for (int l = m + ((m ^ par) & 1); l + 2 <= L; l += 2)
+                hp.gd[(size_t)p * GD_MAX + pos++] = make_float2((float)(bm[l + 2] + bm[l + 1]), (float)(-(bm[l + 1] * bm[l])));
+            pos++;  // one spare entry per chain
+        }
+    }
+    // Radial: K1, K2, K3 of zm:1992-1998 for the pass's own l, l-major
+    hp.rk.assign((size_t)npass * RK_MAX, make_float4(0.f, 0.f, 0.f, 0.f));
+    {
+        std::vector<int> pos(npass, 0);
+        for (int l = 0; l <= L; ++l) {
+            const int p = pass_of(l, npass);
+            hp.rbase[l] = pos[p];
+            for (int n = l; n <= L; n += 2) {
+                float4 K = make_float4(0.f, 0.f, 1.f, 0.f);  // n == l: R = 1 * seed (R_ll = r^l, zm:1983-1984)
+                if (n > l) {
+                    const double k0 = (double)(n - l) * (n + l + 1) * (2 * n - 3);
+                    const double k1 = (double)(2 * n - 1) * (2 * n + 1) * (2 * n - 3);
+                    const double k2 = 0.5 * (double)(-2 * n + 1) * (double)((2 * l + 1) * (2 * l + 1)) - k1 / 2.0;
+                    const double k3 = -1.0 * (double)(n - l - 2) * (n + l - 1) * (2 * n + 1);
+                    K = make_float4((float)(k1 / k0), (float)(k2 / k0), (float)(k3 / k0), 0.f);
+                }
+                hp.rk[(size_t)p * RK_MAX + pos[p]++] = K;
             }
-            hp.rk.push_back(K);
         }
     }
 
@@ -196,8 +220,7 @@ int build_host_plan(int L, HostPlan &hp) {
     const int nmom = num_moments(L);
     hp.src.assign((size_t)2 * nmom, -1);
     hp.omap.assign((size_t)npass * SLOT_WORDS, -1);
-    // mu base per (n, l)
-    std::vector<int> mubase((size_t)S * S, -1);
+    std::vector<int> mubase((size_t)S * S, -1);  // flat index of (n, l, 0)
     {
         int mu = 0;
         for (int n = 0; n <= L; ++n)
@@ -215,36 +238,48 @@ int build_host_plan(int L, HostPlan &hp) {
             hp.roffw[l] = rw;
             hp.poffw[l] = pw;
             const int nn = (L - l) / 2 + 1, m2 = 2 * (l + 1);
-            for (int nb = 0; nb < pad4(nn) / 4; ++nb)
-                for (int mb = 0; mb < pad4(m2) / 4; ++mb, ++t) {
+            const int NB = padT(nn) / TILE, MB = padT(m2) / TILE;
+            for (int nb = 0; nb < NB; ++nb)
+                for (int mb = 0; mb < MB; ++mb, ++t) {
                     const int slot = t / NT, tid = t % NT;
-                    hp.tiles[((size_t)p * TS + slot) * NT + tid] = make_int2(rw + 4 * nb, pw + 4 * mb);
-                    for (int i = 0; i < 4; ++i)
-                        for (int j = 0; j < 4; ++j) {
-                            const int ni = 4 * nb + i, c = 4 * mb + j;
-                            hp.padded++;
-                            if (ni >= nn || c >= m2) continue;
-                            const int n = l + 2 * ni, m = c >> 1, reim = c & 1;
-                            const int e = 2 * (mubase[(size_t)n * S + l] + m) + reim;
-                            const int word = (slot * NT + tid) * 16 + i * 4 + j;
-                            hp.src[e] = p * SLOT_WORDS + word;
-                            hp.omap[(size_t)p * SLOT_WORDS + word] = e;
-                            hp.useful++;
-                        }
+                    const int roff = rw + TILE * nb, poff = pw + TILE * mb;
+                    // Each lane loads its 8 R rows / 8 P columns as two LDS.128.  Eight lanes of a quarter warp that
+                    // read consecutive 32-byte chunks would hit every 16-byte bank group twice, so lanes whose chunk
+                    // index has bit 2 set load the upper half first; the permutation is undone in src / omap below.
+                    const int fr = (roff / TILE >> 2) & 1, fp = (poff / TILE >> 2) & 1;
+                    hp.tiles[((size_t)p * TS + slot) * NT + tid] =
+                        TileDesc{roff + 4 * fr, roff + 4 * (1 - fr), poff + 4 * fp, poff + 4 * (1 - fp)};
+                    auto rowof = [&](int ip, int e) { return (ip < 2 ? 4 * fr + 2 * ip : 4 * (1 - fr) + 2 * (ip - 2)) + e; };
+                    auto colof = [&](int jp, int e) { return (jp < 2 ? 4 * fp + 2 * jp : 4 * (1 - fp) + 2 * (jp - 2)) + e; };
+                    for (int ip = 0; ip < 4; ++ip)
+                        for (int jp = 0; jp < 4; ++jp)
+                            for (int x = 0; x < 2; ++x)
+                                for (int h = 0; h < 2; ++h) {
+                                    // D pair (x=0): (row e, col e);  X pair (x=1): (row e, col 1-e)
+                                    const int ni = TILE * nb + rowof(ip, h), c = TILE * mb + colof(jp, x ? 1 - h : h);
+                                    hp.padded++;
+                                    if (ni >= nn || c >= m2) continue;
+                                    const int n = l + 2 * ni, m = c >> 1, reim = c & 1;
+                                    const int e = 2 * (mubase[(size_t)n * S + l] + m) + reim;
+                                    const int word = (slot * NT + tid) * TW + ((ip * 4 + jp) * 2 + x) * 2 + h;
+                                    hp.src[e] = p * SLOT_WORDS + word;
+                                    hp.omap[(size_t)p * SLOT_WORDS + word] = e;
+                                    hp.useful++;
+                                }
                 }
-            rw += pad4(nn);
-            pw += pad4(m2);
+            rw += padT(nn);
+            pw += padT(m2);
         }
         hp.nown[p] = no;
         hp.ntiles[p] = t;
 
-        // ---- generation tasks: groups of SUBS chains, longest-processing-time first over the warps
+        // ---- generation tasks: groups of GRP chains, longest-processing-time first over the warps
         struct Task { int code; int cost; };
         std::vector<Task> tasks;
-        for (int m0 = 0; m0 <= L; m0 += SUBS) tasks.push_back({(1 << 16) | m0, (L - m0 + 1) * 8 + 24});
-        for (int b = 0; b < no; b += SUBS) {
+        for (int m0 = 0; m0 <= L; m0 += GRP) tasks.push_back({(1 << 16) | m0, ((L - m0) / 2 + 1) * 20 + 80});
+        for (int b = 0; b < no; b += GRP) {
             const int l0 = hp.ownl[(size_t)p * S + b];
-            tasks.push_back({(2 << 16) | b, ((L - l0) / 2 + 1) * 7 + 24});
+            tasks.push_back({(2 << 16) | b, ((L - l0) / 2 + 1) * 16 + 60});
         }
         std::sort(tasks.begin(), tasks.end(), [](const Task &a, const Task &b) { return a.cost > b.cost; });
         int load[NWARP] = {0}, cnt[NWARP] = {0};
@@ -262,12 +297,18 @@ int build_host_plan(int L, HostPlan &hp) {
     return Z3D_OK;
 }
 
-int set_kernel_attrs(int smem) {
-    CUDA_TRY(cudaFuncSetAttribute(k_decompose, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_decompose, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CUDA_TRY(cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+template <int NPH>
+int set_kernel_attrs_t(int smem) {
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose<NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_reconstruct<NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose<NPH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(k_reconstruct<NPH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return Z3D_OK;
+}
+
+int set_kernel_attrs(int smem) {
+    int rc = set_kernel_attrs_t<1>(smem);
+    return rc ? rc : set_kernel_attrs_t<0>(smem);
 }
 
 }  // namespace
@@ -275,7 +316,7 @@ int set_kernel_attrs(int smem) {
 extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
     if (!out) return fail(Z3D_ERR_INVALID, "z3d_plan_create: out is NULL");
     *out = nullptr;
-    if (order < 0 || order > 0xfff0) return fail(Z3D_ERR_INVALID, "z3d_plan_create: bad order %d", order);
+    if (order < 0 || order > LMAX) return fail(Z3D_ERR_INVALID, "z3d_plan_create: order %d outside 0..%d", order, LMAX);
     if (dim < 2 || dim > 4096) return fail(Z3D_ERR_INVALID, "z3d_plan_create: bad dim %d (need 2..4096)", dim);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -306,7 +347,7 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
     pl->nsplit = std::max(1, (prop.multiProcessorCount * CTAS_PER_SM) / hp.npass);
     pl->useful_acc = hp.useful;
     pl->padded_acc = hp.padded;
-    const SmemMap mp = smem_map(order, dim, pl->H);
+    const SmemMap mp = smem_map(dim, pl->H);
     pl->smem_bytes = mp.total;
     if ((size_t)mp.total > prop.sharedMemPerBlockOptin) {
         delete pl;
@@ -350,21 +391,21 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
     d.nsplit = pl->nsplit;
     d.dim_vec4 = (dim % 4 == 0);
     auto &ow = pl->owned;
-    double *d_side; float *d_beta; float4 *d_rk; int *d_rbase, *d_roffw, *d_poffw, *d_lpass, *d_ownl, *d_nown, *d_ntiles, *d_gen;
-    int2 *d_tiles;
+    double *d_side; float2 *d_gd; int *d_goff; float4 *d_rk; int *d_rbase, *d_roffw, *d_poffw, *d_ownl, *d_nown, *d_ntiles, *d_gen;
+    TileDesc *d_tiles;
 #define UP(h, dptr)                          \
     if ((rc = upload(h, &dptr, ow)) != 0) {  \
         z3d_plan_destroy(pl);                \
         return rc;                           \
     }
-    UP(side, d_side) UP(hp.beta, d_beta) UP(hp.rk, d_rk) UP(hp.rbase, d_rbase) UP(hp.roffw, d_roffw)
-    UP(hp.poffw, d_poffw) UP(hp.lpass, d_lpass) UP(hp.ownl, d_ownl) UP(hp.nown, d_nown) UP(hp.ntiles, d_ntiles)
+    UP(side, d_side) UP(hp.gd, d_gd) UP(hp.goff, d_goff) UP(hp.rk, d_rk) UP(hp.rbase, d_rbase) UP(hp.roffw, d_roffw)
+    UP(hp.poffw, d_poffw) UP(hp.ownl, d_ownl) UP(hp.nown, d_nown) UP(hp.ntiles, d_ntiles)
     UP(hp.gen_tasks, d_gen) UP(hp.tiles, d_tiles)
     UP(hp.src, pl->d_src) UP(scale, pl->d_scale) UP(hp.omap, pl->d_omap) UP(ofac, pl->d_ofac)
     UP(nl_base, pl->d_nl_base) UP(nl_l, pl->d_nl_l)
 #undef UP
-    d.side = d_side; d.beta = d_beta; d.rk = d_rk; d.rbase = d_rbase; d.roffw = d_roffw; d.poffw = d_poffw;
-    d.lpass = d_lpass; d.ownl = d_ownl; d.nown = d_nown; d.ntiles = d_ntiles; d.tiles = d_tiles; d.gen_tasks = d_gen;
+    d.side = d_side; d.gd = d_gd; d.goff = d_goff; d.rk = d_rk; d.rbase = d_rbase; d.roffw = d_roffw; d.poffw = d_poffw;
+    d.ownl = d_ownl; d.nown = d_nown; d.ntiles = d_ntiles; d.tiles = d_tiles; d.gen_tasks = d_gen;
 
     rc = set_kernel_attrs(pl->smem_bytes);
     if (rc) {
@@ -432,7 +473,10 @@ extern "C" int z3d_decompose(const z3d_plan *pl, const float *d_vol, int batch, 
     cudaStream_t st = (cudaStream_t)stream;
     float *partial = (float *)d_ws;
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
-    k_decompose<<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, half_lo, half_hi, partial);
+    if (pl->npass == 2)
+        k_decompose<1><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, half_lo, half_hi, partial);
+    else
+        k_decompose<0><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, half_lo, half_hi, partial);
     CUDA_TRY(cudaGetLastError());
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k1, st));
     dim3 g((2 * pl->nmom + 255) / 256, batch);
@@ -458,7 +502,10 @@ extern "C" int z3d_reconstruct(const z3d_plan *pl, const float *d_moments, int b
     k_prepare_tiles<<<g, 256, 0, st>>>(d_moments, pl->d_omap, pl->d_ofac, pl->nmom, pl->npass, batch, otiles);
     CUDA_TRY(cudaGetLastError());
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
-    k_reconstruct<<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, otiles, batch, half_lo, half_hi, pvol);
+    if (pl->npass == 2)
+        k_reconstruct<1><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, otiles, batch, half_lo, half_hi, pvol);
+    else
+        k_reconstruct<0><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, otiles, batch, half_lo, half_hi, pvol);
     CUDA_TRY(cudaGetLastError());
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k1, st));
     const size_t total = (size_t)2 * (half_hi - half_lo) * pl->dim * pl->dim * batch;

@@ -5,40 +5,49 @@
 //   (0) computes r, cos(theta), sin(theta) once per voxel in float64 (zm:1886-1890) and the per-row
 //       cos(m phi), sin(m phi) once per row group,
 //   (1) runs the reference's recurrences in registers - R_nl in n at fixed l (zm:1980-2002), the
-//       normalised associated Legendre functions in l at fixed m (zm:2006-2026, in monic form, the
-//       normalisation kappa_lm is applied once to the finished sums) - and stages the two operand
+//       normalised associated Legendre functions in l at fixed m (zm:2006-2026, in monic parity-decoupled
+//       form; the normalisation kappa_lm is applied once to the finished sums) - and stages the two operand
 //       panels R[n][k] and a*P[(m,re/im)][k] of the per-l contraction in shared memory,
-//   (2) contracts them over the voxel axis into register-resident 4x4 output tiles (analysis), or
-//       contracts register-resident moment tiles with them into 8 mirror-class sums (synthesis).
+//   (2) contracts them over the voxel axis into register-resident 8x8 output tiles (analysis), or
+//       contracts register-resident moment tiles with them into 8 mirror-class sums (synthesis),
+//       with packed fma.rn.f32x2.
 #pragma once
 #include "z3d_plan.h"
 
 namespace z3d {
 
 // ---------------------------------------------------------------------------------------------
-// shared-memory carve-up (identical on host and device)
+// shared-memory carve-up.  Everything the recurrences and the contraction touch sits at a COMPILE-TIME offset
+// (fixed-size tables first): with 64 accumulators live the compiler otherwise rematerialises the layout arithmetic
+// from kernel parameters inside every recurrence step.  Only the box-size dependent arrays at the end have
+// run-time offsets; they are used in the per-row-group setup only.
 // ---------------------------------------------------------------------------------------------
+constexpr int LMAX = 127;                                   // largest order the fixed tables hold
+constexpr int OFF_RS = 0;                                   // R panel        [KC][RS]
+constexpr int OFF_PS = OFF_RS + KC * RS * 4;                // a*P panel      [KC][PS]
+constexpr int OFF_GD = OFF_PS + KC * PS * 4;                // Legendre coefficients of this pass
+constexpr int OFF_RK = OFF_GD + GD_MAX * 8;                 // radial coefficients of this pass
+constexpr int OFF_TABS = OFF_RK + RK_MAX * 16;              // poffw, roffw, goff, rbase  [4][LMAX+1]
+constexpr int OFF_CM = OFF_TABS + 4 * (LMAX + 1) * 4;       // cos(m phi)
+constexpr int OFF_SM = OFF_CM + (LMAX + 1) * 4;             // sin(m phi)
+constexpr int OFF_RED = OFF_SM + (LMAX + 1) * 4;            // synthesis: cross-warp reduction
+constexpr int OFF_GEO = OFF_RED + 2 * NWARP * 16 * 4;       // per-voxel geometry of one row group, 32 B each
 struct SmemMap {
-    int Rs, Ps, a4, geo, cm, sm, rows, F, tabs, red, V, total;  // byte offsets
+    int F, rows, V, total;  // byte offsets of the box-size dependent arrays
 };
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
-__host__ __device__ inline SmemMap smem_map(int L, int N, int H) {
+__host__ __device__ inline SmemMap smem_map(int N, int H) {
     SmemMap m;
-    int o = 0;
-    m.Rs = o;   o += KC * RS * 4;
-    m.Ps = o;   o += KC * PS * 4;
-    m.a4 = o;   o += align16(KC * (L + 1) * 16);
-    m.geo = o;  o += align16(5 * KC * 4);            // c2, st, st2, r, r2
-    m.cm = o;   o += align16((L + 1) * 4);
-    m.sm = o;   o += align16((L + 1) * 4);
-    m.rows = o; o += align16(4 * N * 4);             // analysis: 4 staged rows
+    int o = OFF_GEO + (H + KC) * 32;
     m.F = o;    o += align16(8 * H * 4);             // analysis: 8 mirror-folded rows
-    m.tabs = o; o += align16(3 * (L + 1) * 4);       // lpass, poffw, roffw
-    m.red = o;  o += NWARP * 32 * 4;                 // synthesis: cross-warp reduction
+    m.rows = o; o += align16(4 * N * 4);             // analysis: 4 staged rows
     m.V = o;    o += align16(4 * H * 4);             // synthesis: class sums of one row group
     m.total = o;
     return m;
 }
+struct Geo {  // one folded voxel
+    float c2, c2sq, st, st2, r, r2, pad0, pad1;
+};
 
 // b^e for small non-negative integer e using squares of b2 = b*b (fewer roundings than from b alone)
 __device__ __forceinline__ float powi2(float b, float b2, int e) {
@@ -53,91 +62,215 @@ __device__ __forceinline__ float powi2(float b, float b2, int e) {
     return res;
 }
 
-struct Ctx {
-    float *Rs, *Ps;
-    float4 *a4;
-    float *c2, *st, *st2, *r, *r2, *cm, *sm;
-    int *lpass, *poffw, *roffw;
+// packed FP32 helpers (sm_100a): two FMAs per issued instruction
+__device__ __forceinline__ void ffma2(unsigned long long &d, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned long long swap2(unsigned long long v) {
+    const float2 f = unpack2(v);
+    return pack2(f.y, f.x);
+}
+
+struct Ctx {  // all members are compile-time offsets from the dynamic shared memory base
+    float *Rs, *Ps, *cm, *sm;
+    int *poffw, *roffw, *goff, *rbase;
+    float2 *gd;
+    float4 *rk;
+    Geo *geo;
 };
+__device__ __forceinline__ Ctx make_ctx(unsigned char *smem) {
+    Ctx c;
+    c.Rs = reinterpret_cast<float *>(smem + OFF_RS);
+    c.Ps = reinterpret_cast<float *>(smem + OFF_PS);
+    c.gd = reinterpret_cast<float2 *>(smem + OFF_GD);
+    c.rk = reinterpret_cast<float4 *>(smem + OFF_RK);
+    int *tabs = reinterpret_cast<int *>(smem + OFF_TABS);
+    c.poffw = tabs;
+    c.roffw = tabs + (LMAX + 1);
+    c.goff = tabs + 2 * (LMAX + 1);
+    c.rbase = tabs + 3 * (LMAX + 1);
+    c.cm = reinterpret_cast<float *>(smem + OFF_CM);
+    c.sm = reinterpret_cast<float *>(smem + OFF_SM);
+    c.geo = reinterpret_cast<Geo *>(smem + OFF_GEO);
+    return c;
+}
 
 // Step (1): every warp advances its share of the recurrence chains for the KC voxels of the chunk.
-// lane -> (voxel gk = lane % KC, chain gsub = lane / KC); tasks are warp-uniform.
-__device__ __forceinline__ void generate_panels(const DevPlan &P, const Ctx &c, int pass, int warp, int lane) {
-    const int L = P.order;
-    const int gk = lane % KC, gsub = lane / KC;
+// lane -> (voxel gk = lane % KC, sub-lane gsub = lane / KC); each lane runs CPL independent chains; tasks are
+// warp-uniform.
+//
+// Legendre chains run in the parity-decoupled monic form: with Q_lm = P_lm / kappa_lm and
+// Q_l = 2c Q_{l-1} - beta_l Q_{l-2} (Y_lm_recurrence zm:2021-2026 divided by kappa), eliminating the
+// other parity gives  Q_{l+2} = (4c^2 - gamma_l) Q_l - delta_l Q_{l-2},  gamma_l = beta_{l+2} + beta_{l+1},
+// delta_l = beta_{l+1} beta_l.  A pass owns one parity of l, so it walks only its own levels, and because
+// the recurrence is linear the chain is run on the two products a_re*Q and a_im*Q directly (the z-mirror
+// parity (l+m)&1 that selects a_re / a_im is constant along such a chain).
+template <int NPH, bool ANALYSIS>  // NPH = npass / 2 when known at compile time (1), 0 = read it from the plan
+__device__ __forceinline__ void generate_panels(const DevPlan &P, const Ctx &c, const float *F, int k0, int pass,
+                                                int warp, int lane) {
+    const int L = P.order, H = P.H;
+    const int gk = lane % KC, gsub = lane / KC, kk = k0 + gk;
+    const int par = pass & 1, nph = NPH ? NPH : (P.npass >> 1), rho = pass >> 1;
     const int *tasks = P.gen_tasks + (pass * NWARP + warp) * MAXTASK;
+    const float4 g0 = reinterpret_cast<const float4 *>(c.geo + kk)[0], g1 = reinterpret_cast<const float4 *>(c.geo + kk)[1];
+    const float c2 = g0.x, c2sq = g0.y, st = g0.z, st2 = g0.w, r = g1.x, r2 = g1.y;
     for (int t = 0; t < MAXTASK; ++t) {
         const int task = __ldg(tasks + t);
         const int type = task >> 16, base = task & 0xffff;
         if (type == 0) break;
         if (type == 1) {
-            // Legendre chains m = base + gsub, l = m..L.  Monic form: Q_l = 2c Q_{l-1} - beta_l Q_{l-2},
-            // Q_mm = sin^m; P_lm = kappa_lm Q_lm (Y_lm_recurrence zm:2012-2026 divided by kappa).
-            const int m = base + gsub;
-            const bool active = (m <= L);
-            const int mm = active ? m : L;
-            const float c2 = c.c2[gk];
-            const float seed = powi2(c.st[gk], c.st2[gk], mm);
-            const float4 a = c.a4[gk * (L + 1) + mm];
-            const float *bp = P.beta + mm * (L + 1);
-            float *dst = c.Ps + gk * PS + 2 * mm;
-            float q1 = 0.0f, q2 = 0.0f;
-            for (int l = base; l <= L; ++l) {
-                const float b = __ldg(bp + l);
-                float q = fmaf(c2, q1, -b * q2);
-                q = (l == mm) ? seed : q;
-                q2 = q1;
-                q1 = q;
-                if (c.lpass[l] == pass && active && l >= m) {
-                    const bool odd = (l + m) & 1;
-                    const float are = odd ? a.z : a.x, aim = odd ? a.w : a.y;
-                    *reinterpret_cast<float2 *>(dst + c.poffw[l]) = make_float2(are * q, aim * q);
+            const int lmin = base + ((base ^ par) & 1);          // warp-uniform first level of the group
+            const int mlast = min(base + GRP - 1, L);
+            const int l0max = min(mlast + ((mlast ^ par) & 1), L);  // all lanes have started after this level
+            int l0[CPL];
+            const float2 *tp[CPL];
+            float *dst[CPL];
+            float sa[CPL], sb[CPL], A1[CPL], A2[CPL], B1[CPL], B2[CPL];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int m = min(base + q * SUBS + gsub, L);    // lanes past L redo chain L (same stores, same values)
+                l0[q] = m + ((m ^ par) & 1);                     // first level of this parity with l >= m
+                // a = (folded f) x trig for analysis (re: even in y, (-1)^m in x; im: odd in y, -(-1)^m in x; z parity
+                // (l+m)&1 = (par+m)&1), plain trig for synthesis
+                float2 a = make_float2(c.cm[m], c.sm[m]);
+                if (ANALYSIS) {
+                    const int px = m & 1, pz = (par + m) & 1;
+                    const bool live = kk < H;
+                    a.x *= live ? F[((px << 1) | pz) * H + kk] : 0.f;
+                    a.y *= live ? -F[(4 | ((px ^ 1) << 1) | pz) * H + kk] : 0.f;
                 }
+                float seed = powi2(st, st2, m);                  // Q_mm = sin^m  (zm:2012-2015 / kappa_mm)
+                if (l0[q] != m) seed *= c2;                      // Q_{m+1,m} = 2c Q_mm (zm:2016-2020 / kappa)
+                sa[q] = a.x * seed;
+                sb[q] = a.y * seed;
+                // table pointer such that entry [p-1] advances level lmin + 2(p-1) -> lmin + 2p for this lane
+                tp[q] = c.gd + c.goff[m] - ((l0[q] - lmin) >> 1);
+                dst[q] = c.Ps + gk * PS + 2 * m;
+                A1[q] = A2[q] = B1[q] = B2[q] = 0.f;
+            }
+            int until = 0;  // positions until the next own level (always 0 when the pass owns its whole parity)
+            if (nph > 1) {
+                until = (rho - (lmin >> 1)) % nph;
+                if (until < 0) until += nph;
+            }
+            int p = 0, l = lmin;
+            // prologue (<= GRP/2 + 1 positions): chains that have not started hold zeros, then take their seed
+            for (; l <= l0max; l += 2, ++p) {
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    if (p > 0) {
+                        const float2 g = tp[q][p - 1];
+                        const float tt = c2sq - g.x;
+                        const float An = fmaf(tt, A1[q], g.y * A2[q]), Bn = fmaf(tt, B1[q], g.y * B2[q]);
+                        A2[q] = A1[q]; A1[q] = An; B2[q] = B1[q]; B1[q] = Bn;
+                    }
+                    if (l <= l0[q]) {
+                        const bool start = (l == l0[q]);
+                        A1[q] = start ? sa[q] : 0.f; B1[q] = start ? sb[q] : 0.f;
+                        A2[q] = 0.f; B2[q] = 0.f;
+                    }
+                }
+                if (until == 0) {
+                    const int off = c.poffw[l];
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q)
+                        if (l >= l0[q]) *reinterpret_cast<float2 *>(dst[q] + off) = make_float2(A1[q], B1[q]);
+                    until = nph;
+                }
+                --until;
+            }
+            // main loop: every chain is live
+#pragma unroll 2
+            for (; l <= L; l += 2, ++p) {
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const float2 g = tp[q][p - 1];
+                    const float tt = c2sq - g.x;
+                    const float An = fmaf(tt, A1[q], g.y * A2[q]), Bn = fmaf(tt, B1[q], g.y * B2[q]);
+                    A2[q] = A1[q]; A1[q] = An; B2[q] = B1[q]; B1[q] = Bn;
+                }
+                if (NPH == 1 || until == 0) {
+                    const int off = c.poffw[l];
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) *reinterpret_cast<float2 *>(dst[q] + off) = make_float2(A1[q], B1[q]);
+                    until = nph;
+                }
+                --until;
             }
         } else {
-            // Radial chains for own l = ownl[base + gsub]: R_ll = r^l, then
-            // R_n = (K1 r^2 + K2) R_{n-2} + K3 R_{n-4}   (R_nl_recurrence zm:1983-2000; the l == n-2
-            // branch is the same formula with K3 = 0).
-            const int oi = base + gsub;
+            // Radial chains for own l = ownl[base + q*SUBS + gsub]:  R_n = (K1 r^2 + K2) R_{n-2} + K3 R_{n-4}
+            // (R_nl_recurrence zm:1991-2000; the l == n-2 branch zm:1987-1988 is the same formula with K3 = 0 and
+            // the seed R_ll = r^l enters through the table entry (0, 0, 1) of n = l).
             const int nown = __ldg(P.nown + pass);
-            const bool active = oi < nown;
-            const int l = __ldg(P.ownl + pass * (L + 1) + (active ? oi : base));
-            const int l0 = __ldg(P.ownl + pass * (L + 1) + base);
-            const int nmax = (L - l0) / 2 + 1;
-            const int nn = active ? (L - l) / 2 + 1 : 0;
-            const float r2 = c.r2[gk];
-            float R1 = powi2(c.r[gk], r2, l), R2 = 0.0f;
-            float *dst = c.Rs + gk * RS + c.roffw[l];
-            const float4 *kp = P.rk + __ldg(P.rbase + l);
-            if (active) dst[0] = R1;
-            for (int ni = 1; ni < nmax; ++ni) {
-                if (ni < nn) {
-                    const float4 K = __ldg(kp + ni);
-                    const float R = fmaf(fmaf(K.x, r2, K.y), R1, K.z * R2);
-                    dst[ni] = R;
-                    R2 = R1;
-                    R1 = R;
+            const int *own = P.ownl + pass * (L + 1);
+            const int nmax = (L - __ldg(own + base)) / 2 + 1;
+            int nn[CPL];
+            float R1[CPL], R2[CPL];
+            float *dst[CPL];
+            const float4 *kp[CPL];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int oi = base + q * SUBS + gsub;
+                const bool active = oi < nown;
+                const int l = __ldg(own + (active ? oi : base));
+                nn[q] = active ? (L - l) / 2 + 1 : 0;
+                R1[q] = 0.0f;
+                R2[q] = powi2(r, r2, l);
+                dst[q] = c.Rs + gk * RS + c.roffw[l];
+                kp[q] = c.rk + c.rbase[l];
+            }
+#pragma unroll 2
+            for (int ni = 0; ni < nmax; ++ni) {
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    if (ni < nn[q]) {
+                        const float4 K = kp[q][ni];
+                        const float R = fmaf(fmaf(K.x, r2, K.y), R1[q], K.z * R2[q]);
+                        dst[q][ni] = R;
+                        R2[q] = R1[q];
+                        R1[q] = R;
+                    }
                 }
             }
         }
     }
 }
 
-// Step (0) geometry for the KC voxels of a chunk; float64 like the reference (zm:2240-2242, 1886-1890).
-__device__ __forceinline__ void chunk_geometry(const DevPlan &P, const Ctx &c, int k, int kk, double rho2, double rho) {
-    const double z = (kk < P.H) ? P.side[kk] : 0.0;
-    const double r2d = rho2 + z * z;
-    const double r = sqrt(r2d);
-    double ct = 1.0, st = 0.0;  // r == 0: theta is NaN in the reference and nan_to_num zeroes Y_lm, l > 0
-    if (r > 0.0) {             // (zm:2298); R_nl(0) = 0 for l > 0 gives the same product here.
-        ct = z / r;
-        st = rho / r;
+// Geometry of the H folded voxels of a row group; float64 like the reference (zm:2240-2242, 1886-1890).
+__device__ __forceinline__ void row_geometry(const DevPlan &P, const Ctx &c, double rho2, double rho) {
+    for (int k = threadIdx.x; k < P.H + KC; k += NT) {
+        const double z = (k < P.H) ? P.side[k] : 0.0;
+        const double r2d = rho2 + z * z;
+        const double r = sqrt(r2d);
+        double ct = 1.0, st = 0.0;  // r == 0: theta is NaN in the reference and nan_to_num zeroes Y_lm, l > 0
+        if (r > 0.0) {             // (zm:2298); R_nl(0) = 0 for l > 0 gives the same product here.
+            ct = z / r;
+            st = rho / r;
+        }
+        float4 *g = reinterpret_cast<float4 *>(c.geo + k);
+        g[0] = make_float4((float)(2.0 * ct), (float)(4.0 * ct * ct), (float)st, (float)(st * st));
+        g[1] = make_float4((float)r, (float)r2d, 0.f, 0.f);
     }
-    c.c2[k] = (float)(2.0 * ct);
-    c.st[k] = (float)st;
-    c.st2[k] = (float)(st * st);
-    c.r[k] = (float)r;
-    c.r2[k] = (float)r2d;
 }
 
 // in-register 8-point Walsh-Hadamard transform: v[c] = sum_img v[img] * (-1)^popcount(c & img)
@@ -155,33 +288,20 @@ __device__ __forceinline__ void wht8(float v[8]) {
     }
 }
 
-__device__ __forceinline__ Ctx make_ctx(unsigned char *smem, const SmemMap &mp) {
-    Ctx c;
-    c.Rs = reinterpret_cast<float *>(smem + mp.Rs);
-    c.Ps = reinterpret_cast<float *>(smem + mp.Ps);
-    c.a4 = reinterpret_cast<float4 *>(smem + mp.a4);
-    float *geo = reinterpret_cast<float *>(smem + mp.geo);
-    c.c2 = geo;
-    c.st = geo + KC;
-    c.st2 = geo + 2 * KC;
-    c.r = geo + 3 * KC;
-    c.r2 = geo + 4 * KC;
-    c.cm = reinterpret_cast<float *>(smem + mp.cm);
-    c.sm = reinterpret_cast<float *>(smem + mp.sm);
-    return c;
-}
-
-__device__ __forceinline__ void load_small_tables(const DevPlan &P, Ctx &c, unsigned char *smem, const SmemMap &mp) {
-    int *tabs = reinterpret_cast<int *>(smem + mp.tabs);
+// per-pass coefficient and offset tables -> smem (read every chunk by the recurrences)
+__device__ __forceinline__ void load_tables(const DevPlan &P, const Ctx &c, int pass) {
     const int L = P.order;
-    c.lpass = tabs;
-    c.poffw = tabs + (L + 1);
-    c.roffw = tabs + 2 * (L + 1);
     for (int i = threadIdx.x; i <= L; i += NT) {
-        c.lpass[i] = P.lpass[i];
         c.poffw[i] = P.poffw[i];
         c.roffw[i] = P.roffw[i];
+        c.goff[i] = P.goff[pass * (L + 1) + i];
+        c.rbase[i] = P.rbase[i];
     }
+    for (int i = threadIdx.x; i < GD_MAX; i += NT) c.gd[i] = P.gd[pass * GD_MAX + i];
+    for (int i = threadIdx.x; i < RK_MAX; i += NT) c.rk[i] = P.rk[pass * RK_MAX + i];
+    // padding rows / columns of the panels are never written by the recurrences but are multiplied into padding
+    // accumulators (analysis) or with zero moment entries (synthesis): they must be finite -> clear both panels once.
+    for (int i = threadIdx.x; i < KC * (RS + PS); i += NT) c.Rs[i] = 0.0f;  // Rs and Ps are contiguous
 }
 
 // cos(m phi0), sin(m phi0) for the row group, float64 like exp(1j m phi) in zm:2297
@@ -198,38 +318,53 @@ __device__ __forceinline__ void row_trig(const DevPlan &P, const Ctx &c, double 
 // ---------------------------------------------------------------------------------------------
 // Analysis: per-CTA partial sums of  sum_v f R_nl P_lm e^{-i m phi}  for one pass and one split.
 // partial layout: [batch][npass][nsplit][SLOT_WORDS]
+//
+// Register tile (8 rows n x 8 columns (m, re/im)) as 32 packed pairs: with row pairs Rp[ip] = (R[a], R[a+1]) and
+// column pairs Pp[jp] = (P[b], P[b+1]) exactly as they come out of LDS.128,
+//   D[ip][jp] += Rp[ip] * Pp[jp]        -> (acc[a][b],   acc[a+1][b+1])
+//   X[ip][jp] += Rp[ip] * swap(Pp[jp])  -> (acc[a][b+1], acc[a+1][b])
+// so no operand has to be duplicated in shared memory or registers.
 // ---------------------------------------------------------------------------------------------
+template <int NPH>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_lo, int half_hi,
             float *__restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = P.order, N = P.dim, H = P.H;
-    const SmemMap mp = smem_map(L, N, H);
-    Ctx c = make_ctx(smem, mp);
-    load_small_tables(P, c, smem, mp);
-    float *rows = reinterpret_cast<float *>(smem + mp.rows);
-    float *F = reinterpret_cast<float *>(smem + mp.F);
-
+    const SmemMap mp = smem_map(N, H);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pass = blockIdx.x % P.npass, split = blockIdx.x / P.npass;
+    const int par = pass & 1;
+    const Ctx c = make_ctx(smem);
+    load_tables(P, c, pass);
+    float *rows = reinterpret_cast<float *>(smem + mp.rows);
+    float *F = reinterpret_cast<float *>(smem + mp.F);
     const int ntile = P.ntiles[pass];
+#ifndef Z3D_NO_STAGGER
+    // the two CTAs of an SM have identical phase lengths; without an offset they
+    // generate and contract in lockstep and never overlap.  Delay the odd pass by about half a chunk period once.
+    if (blockIdx.x >= (gridDim.x >> 1)) {  // CTA b and b + grid/2 share an SM (round-robin block placement)
+        const long long t0 = clock64();
+        while (clock64() - t0 < 3500) {}
+    }
+#endif
 
-    const float *rptr[TS], *pptr[TS];
+    const float *r0p[TS], *r1p[TS], *p0p[TS], *p1p[TS];
 #pragma unroll
     for (int s = 0; s < TS; ++s) {
-        const int2 t = P.tiles[(pass * TS + s) * NT + tid];
-        rptr[s] = c.Rs + t.x;
-        pptr[s] = c.Ps + t.y;
+        const TileDesc t = P.tiles[(pass * TS + s) * NT + tid];
+        r0p[s] = c.Rs + t.r0; r1p[s] = c.Rs + t.r1;
+        p0p[s] = c.Ps + t.p0; p1p[s] = c.Ps + t.p1;
     }
 
     const int nG = (half_hi - half_lo) * H;
     const size_t N3 = (size_t)N * N * N;
     for (int b = 0; b < batch; ++b) {
-        float acc[TS][16];
+        unsigned long long acc[TS][32];  // [(ip*4 + jp)*2 + {D, X}]
 #pragma unroll
         for (int s = 0; s < TS; ++s)
 #pragma unroll
-            for (int e = 0; e < 16; ++e) acc[s][e] = 0.0f;
+            for (int e = 0; e < 32; ++e) acc[s][e] = 0ull;
         const float *vb = vol + (size_t)b * N3;
 
         for (int g = split; g < nG; g += P.nsplit) {
@@ -259,6 +394,7 @@ k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_
                 }
             }
             row_trig(P, c, x0, y0);
+            row_geometry(P, c, rho2, rho);
             __syncthreads();
             // ---- fold the 8 mirror images: F[c][k] = sum_img f_img (-1)^popcount(c & img),
             //      img = sy*4 + sx*2 + sz,  c = py*4 + px*2 + pz
@@ -277,51 +413,46 @@ k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_
             __syncthreads();
 
             for (int k0 = 0; k0 < H; k0 += KC) {
-                // ---- step 0: geometry + a-table (f folded * trig) for the chunk
-                if (tid < KC) chunk_geometry(P, c, tid, k0 + tid, rho2, rho);
-                for (int idx = tid; idx < KC * (L + 1); idx += NT) {
-                    const int k = idx % KC, m = idx / KC, kk = k0 + k;
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (kk < H) {
-                        const int px = m & 1;
-                        const float cmv = c.cm[m], smv = -c.sm[m];
-                        // re: even in y, (-1)^m in x;  im: odd in y, -(-1)^m in x;  z parity = (l+m)&1
-                        a.x = F[((px << 1) | 0) * H + kk] * cmv;
-                        a.z = F[((px << 1) | 1) * H + kk] * cmv;
-                        a.y = F[(4 | ((px ^ 1) << 1) | 0) * H + kk] * smv;
-                        a.w = F[(4 | ((px ^ 1) << 1) | 1) * H + kk] * smv;
-                    }
-                    c.a4[k * (L + 1) + m] = a;
-                }
-                __syncthreads();
+                if (k0) __syncthreads();  // the previous chunk's contraction is done reading the panels
                 // ---- step 1: recurrences -> operand panels in smem
-                generate_panels(P, c, pass, warp, lane);
+#ifndef Z3D_DEBUG_SKIP_GEN
+                generate_panels<NPH, true>(P, c, F, k0, pass, warp, lane);
+#endif
                 __syncthreads();
-                // ---- step 2: contraction over the chunk's voxels into the register tiles
+                // ---- step 2: contraction over the chunk's voxels into the register tiles (fma.rn.f32x2)
+#ifndef Z3D_DEBUG_SKIP_MAC
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
 #pragma unroll
                     for (int s = 0; s < TS; ++s) {
-                        const float4 rv = *reinterpret_cast<const float4 *>(rptr[s] + k * RS);
-                        const float4 pv = *reinterpret_cast<const float4 *>(pptr[s] + k * PS);
-                        const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
-                        const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+                        const ulonglong2 ra = *reinterpret_cast<const ulonglong2 *>(r0p[s] + k * RS);
+                        const ulonglong2 rb = *reinterpret_cast<const ulonglong2 *>(r1p[s] + k * RS);
+                        const ulonglong2 pa = *reinterpret_cast<const ulonglong2 *>(p0p[s] + k * PS);
+                        const ulonglong2 pb = *reinterpret_cast<const ulonglong2 *>(p1p[s] + k * PS);
+                        const unsigned long long Rp[4] = {ra.x, ra.y, rb.x, rb.y};
+                        const unsigned long long Pp[4] = {pa.x, pa.y, pb.x, pb.y};
+                        unsigned long long Px[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) Px[j] = swap2(Pp[j]);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[s][i * 4 + j] = fmaf(rr[i], pp[j], acc[s][i * 4 + j]);
+                            for (int j = 0; j < 4; ++j) {
+                                ffma2(acc[s][(i * 4 + j) * 2], Rp[i], Pp[j]);
+                                ffma2(acc[s][(i * 4 + j) * 2 + 1], Rp[i], Px[j]);
+                            }
                     }
                 }
+#endif
             }
         }
         float *out = partial + (((size_t)b * P.npass + pass) * P.nsplit + split) * SLOT_WORDS;
 #pragma unroll
         for (int s = 0; s < TS; ++s) {
             if (s * NT + tid < ntile) {
-                float4 *o = reinterpret_cast<float4 *>(out + (size_t)(s * NT + tid) * 16);
+                ulonglong2 *o = reinterpret_cast<ulonglong2 *>(out + (size_t)(s * NT + tid) * TW);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    o[q] = make_float4(acc[s][4 * q], acc[s][4 * q + 1], acc[s][4 * q + 2], acc[s][4 * q + 3]);
+                for (int q = 0; q < 16; ++q) o[q] = make_ulonglong2(acc[s][2 * q], acc[s][2 * q + 1]);
             }
         }
     }
@@ -363,10 +494,12 @@ __global__ void k_prepare_tiles(const float *__restrict__ moments, const int *__
     otiles[(size_t)b * npass * SLOT_WORDS + w] = v;
 }
 
-// lane L ends up with sum over lanes of v[L]  (31 shuffles instead of 32 * 5)
-__device__ __forceinline__ float warp_transpose_reduce32(float v[32], int lane) {
+// 16 values per lane -> lanes L and L+16 both end up with the sum over all 32 lanes of v[L & 15]
+__device__ __forceinline__ float warp_transpose_reduce16(float v[16], int lane) {
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
+    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
         const bool upper = lane & off;
 #pragma unroll
         for (int i = 0; i < off; ++i) {
@@ -379,46 +512,46 @@ __device__ __forceinline__ float warp_transpose_reduce32(float v[32], int lane) 
 }
 
 // pvol layout: [npass][batch][N^3]; only planes of the selected pairs are written.
+//
+// Per tile and voxel: t[col] = sum_row O[row][col] R[row] (32 packed FMAs on the resident moment tile, in the same
+// D / X pair layout as the analysis accumulators), then class[col & 3] += P[col] t[col]: the 8 columns of a tile
+// are (m0..m0+3) x (re, im) with m0 a multiple of 4, so column c and c+4 fall in the same mirror class.
+template <int NPH>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 k_reconstruct(const DevPlan P, const float *__restrict__ otiles, int batch, int half_lo, int half_hi,
               float *__restrict__ pvol) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = P.order, N = P.dim, H = P.H;
-    const SmemMap mp = smem_map(L, N, H);
-    Ctx c = make_ctx(smem, mp);
-    load_small_tables(P, c, smem, mp);
-    float *red = reinterpret_cast<float *>(smem + mp.red);
-    float *V = reinterpret_cast<float *>(smem + mp.V);
-    // padding rows / columns of the panels are never written by the recurrences; they meet zero moment
-    // entries in the tiles, so they must be finite: clear both panels once.
-    for (int i = threadIdx.x; i < KC * (RS + PS); i += NT) c.Rs[i] = 0.0f;  // Rs and Ps are contiguous
-
+    const SmemMap mp = smem_map(N, H);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pass = blockIdx.x % P.npass, split = blockIdx.x / P.npass;
     const int par = pass & 1;  // parity of every l in this pass
+    const Ctx c = make_ctx(smem);
+    load_tables(P, c, pass);
+    float *red = reinterpret_cast<float *>(smem + OFF_RED);
+    float *V = reinterpret_cast<float *>(smem + mp.V);
 
-    const float *rptr[TS], *pptr[TS];
+    const float *r0p[TS], *r1p[TS], *p0p[TS], *p1p[TS];
 #pragma unroll
     for (int s = 0; s < TS; ++s) {
-        const int2 t = P.tiles[(pass * TS + s) * NT + tid];
-        rptr[s] = c.Rs + t.x;
-        pptr[s] = c.Ps + t.y;
+        const TileDesc t = P.tiles[(pass * TS + s) * NT + tid];
+        r0p[s] = c.Rs + t.r0; r1p[s] = c.Rs + t.r1;
+        p0p[s] = c.Ps + t.p0; p1p[s] = c.Ps + t.p1;
     }
-    // mirror class c = py*4 + px*2 + pz of tile column j (m0 even): j0 (m0,re) -> par, j1 (m0,im) -> 6|par,
-    // j2 (m0+1,re) -> 2|(par^1), j3 (m0+1,im) -> 4|(par^1)
 
     const int nG = (half_hi - half_lo) * H;
     const size_t N3 = (size_t)N * N * N;
     for (int b = 0; b < batch; ++b) {
-        float om[TS][16];
+        unsigned long long om[TS][32];  // moment tiles, same pair layout as the analysis accumulators
         const float *ob = otiles + ((size_t)b * P.npass + pass) * SLOT_WORDS;
 #pragma unroll
         for (int s = 0; s < TS; ++s) {
-            const float4 *o = reinterpret_cast<const float4 *>(ob + (size_t)(s * NT + tid) * 16);
+            const ulonglong2 *o = reinterpret_cast<const ulonglong2 *>(ob + (size_t)(s * NT + tid) * TW);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 x = __ldg(o + q);
-                om[s][4 * q] = x.x; om[s][4 * q + 1] = x.y; om[s][4 * q + 2] = x.z; om[s][4 * q + 3] = x.w;
+            for (int q = 0; q < 16; ++q) {
+                const ulonglong2 x = __ldg(o + q);
+                om[s][2 * q] = x.x;
+                om[s][2 * q + 1] = x.y;
             }
         }
         float *pv_out = pvol + ((size_t)pass * batch + b) * N3;
@@ -430,51 +563,65 @@ k_reconstruct(const DevPlan P, const float *__restrict__ otiles, int batch, int 
             const double rho2 = x0 * x0 + y0 * y0, rho = sqrt(rho2);
             __syncthreads();
             row_trig(P, c, x0, y0);
+            row_geometry(P, c, rho2, rho);
             __syncthreads();
 
             for (int k0 = 0; k0 < H; k0 += KC) {
-                if (tid < KC) chunk_geometry(P, c, tid, k0 + tid, rho2, rho);
-                for (int idx = tid; idx < KC * (L + 1); idx += NT) {
-                    const int k = idx % KC, m = idx / KC;
-                    const float cmv = c.cm[m], smv = c.sm[m];
-                    c.a4[k * (L + 1) + m] = make_float4(cmv, smv, cmv, smv);
-                }
+                generate_panels<NPH, false>(P, c, nullptr, k0, pass, warp, lane);
                 __syncthreads();
-                generate_panels(P, c, pass, warp, lane);
-                __syncthreads();
-                float vacc[32];  // [k][j]
+#pragma unroll 1
+                for (int kh = 0; kh < 2; ++kh) {  // two half chunks keep the class accumulators at 16 registers
+                    unsigned long long vacc[KC];  // [k in half][column pair parity] -> classes (2jh, 2jh+1)
 #pragma unroll
-                for (int q = 0; q < 32; ++q) vacc[q] = 0.0f;
+                    for (int q = 0; q < KC; ++q) vacc[q] = 0ull;
 #pragma unroll
-                for (int k = 0; k < KC; ++k) {
+                    for (int kk = 0; kk < KC / 2; ++kk) {
+                        const int k = kh * (KC / 2) + kk;
 #pragma unroll
-                    for (int s = 0; s < TS; ++s) {
-                        const float4 rv = *reinterpret_cast<const float4 *>(rptr[s] + k * RS);
-                        const float4 pv = *reinterpret_cast<const float4 *>(pptr[s] + k * PS);
-                        const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
-                        const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+                        for (int s = 0; s < TS; ++s) {
+                            const ulonglong2 ra = *reinterpret_cast<const ulonglong2 *>(r0p[s] + k * RS);
+                            const ulonglong2 rb = *reinterpret_cast<const ulonglong2 *>(r1p[s] + k * RS);
+                            const ulonglong2 pa = *reinterpret_cast<const ulonglong2 *>(p0p[s] + k * PS);
+                            const ulonglong2 pb = *reinterpret_cast<const ulonglong2 *>(p1p[s] + k * PS);
+                            const unsigned long long Rp[4] = {ra.x, ra.y, rb.x, rb.y};
+                            const unsigned long long Pp[4] = {pa.x, pa.y, pb.x, pb.y};
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float t = om[s][j] * rr[0];
+                            for (int j = 0; j < 4; ++j) {
+                                unsigned long long tD = fmul2(Rp[0], om[s][j * 2]);
+                                unsigned long long tX = fmul2(Rp[0], om[s][j * 2 + 1]);
 #pragma unroll
-                            for (int i = 1; i < 4; ++i) t = fmaf(om[s][i * 4 + j], rr[i], t);
-                            vacc[k * 4 + j] = fmaf(pp[j], t, vacc[k * 4 + j]);
+                                for (int i = 1; i < 4; ++i) {
+                                    ffma2(tD, Rp[i], om[s][(i * 4 + j) * 2]);
+                                    ffma2(tX, Rp[i], om[s][(i * 4 + j) * 2 + 1]);
+                                }
+                                ffma2(vacc[kk * 2 + (j & 1)], Pp[j], fadd2(tD, swap2(tX)));
+                            }
                         }
                     }
+                    float v[16];  // [k in half][class column 0..3]
+#pragma unroll
+                    for (int q = 0; q < KC; ++q) {
+                        const float2 u = unpack2(vacc[q]);
+                        v[2 * q] = u.x;
+                        v[2 * q + 1] = u.y;
+                    }
+                    const float tot = warp_transpose_reduce16(v, lane);
+                    if (lane < 16) red[(kh * NWARP + warp) * 16 + lane] = tot;
                 }
-                const float tot = warp_transpose_reduce32(vacc, lane);
-                red[warp * 32 + lane] = tot;
                 __syncthreads();
                 if (tid < 32) {
+                    const int kh = tid >> 4, q = tid & 15;
                     float s = 0.0f;
 #pragma unroll
-                    for (int w = 0; w < NWARP; ++w) s += red[w * 32 + tid];
-                    const int k = tid >> 2, j = tid & 3;
+                    for (int w = 0; w < NWARP; ++w) s += red[(kh * NWARP + w) * 16 + q];
+                    const int k = kh * (KC / 2) + (q >> 2), j = q & 3;
                     if (k0 + k < H) V[j * H + k0 + k] = s;
                 }
             }
             __syncthreads();
-            // ---- unfold the 4 class sums of this pass into the 8 mirror voxels
+            // ---- unfold the 4 class sums of this pass into the 8 mirror voxels.
+            // mirror class c = py*4 + px*2 + pz of class column j: j0 (m even, re) -> par, j1 (m even, im) -> 6|par,
+            // j2 (m odd, re) -> 2|(par^1), j3 (m odd, im) -> 4|(par^1)
             for (int k = tid; k < H; k += NT) {
                 const int k2 = N - 1 - k;
                 float v[8];
@@ -549,13 +696,8 @@ __global__ void k_fma_peak(int iters, float *out, int variant) {
             }
         }
     } else {
-        unsigned long long p0, p1, p2, p3, px, py;
-        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p0) : "f"(a0), "f"(a1));
-        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p1) : "f"(a2), "f"(a3));
-        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p2) : "f"(a4), "f"(a5));
-        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p3) : "f"(a6), "f"(a7));
-        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(px) : "f"(x), "f"(x));
-        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(py) : "f"(y), "f"(y));
+        unsigned long long p0 = pack2(a0, a1), p1 = pack2(a2, a3), p2 = pack2(a4, a5), p3 = pack2(a6, a7);
+        const unsigned long long px = pack2(x, x), py = pack2(y, y);
         for (int i = 0; i < iters; ++i) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -565,10 +707,8 @@ __global__ void k_fma_peak(int iters, float *out, int variant) {
                 asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p3) : "l"(px), "l"(py));
             }
         }
-        asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(p0));
-        asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(a2), "=f"(a3) : "l"(p1));
-        asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(a4), "=f"(a5) : "l"(p2));
-        asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(a6), "=f"(a7) : "l"(p3));
+        const float2 f0 = unpack2(p0), f1 = unpack2(p1), f2 = unpack2(p2), f3 = unpack2(p3);
+        a0 = f0.x; a1 = f0.y; a2 = f1.x; a3 = f1.y; a4 = f2.x; a5 = f2.y; a6 = f3.x; a7 = f3.y;
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
