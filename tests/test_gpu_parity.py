@@ -49,12 +49,10 @@ def test_decompose_vs_reference_golden(plans, oracle_mod, name):
         assert rel_l2(mom, g["moments"][si]) < TOL_MOM
         inv = P.invariants(dev(mom)).cpu().numpy()
         # the 1e-6 bar on invariants holds against the exact oracle everywhere; against the reference's own
-        # float32-BLAS numbers it holds up to 96^3 and is 2.3e-6 at 128^3 (reference noise)
+        # float32-BLAS numbers it holds up to 64^3 and is 1.0e-6 at 96^3 / 2.3e-6 at 128^3 - that is the reference's
+        # summation noise (its moments are 3.3e-6 / 5.4e-6 from the float64 evaluation there), see DESIGN.md
         assert rel_l2(inv, oracle_mod.invariants(mom, order)) < 2e-7
-        if dim <= 96:
-            assert rel_l2(inv, g["invariants"][si]) < TOL_INV
-        else:
-            assert rel_l2(inv, g["invariants"][si]) < 5e-6
+        assert rel_l2(inv, g["invariants"][si]) < (TOL_INV if dim <= 64 else 5e-6)
         if dim <= 64:
             exact = oracle_mod.decompose(v, order, oracle_mod.EXACT)
             assert rel_l2(mom, exact) < TOL_EXACT

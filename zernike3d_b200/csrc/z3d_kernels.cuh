@@ -30,7 +30,9 @@ constexpr int OFF_RK = OFF_GD + GD_MAX * 8;                 // radial coefficien
 constexpr int OFF_TABS = OFF_RK + RK_MAX * 16;              // poffw, roffw, goff, rbase  [4][LMAX+1]
 constexpr int OFF_CM = OFF_TABS + 4 * (LMAX + 1) * 4;       // cos(m phi)
 constexpr int OFF_SM = OFF_CM + (LMAX + 1) * 4;             // sin(m phi)
-constexpr int OFF_RED = OFF_SM + (LMAX + 1) * 4;            // synthesis: cross-warp reduction
+constexpr int OFF_CM2 = OFF_SM + (LMAX + 1) * 4;            // cos / sin(m phi) of the transposed row group (analysis)
+constexpr int OFF_SM2 = OFF_CM2 + (LMAX + 1) * 4;
+constexpr int OFF_RED = OFF_SM2 + (LMAX + 1) * 4;           // synthesis: cross-warp reduction
 constexpr int OFF_GEO = OFF_RED + 2 * NWARP * 16 * 4;       // per-voxel geometry of one row group, 32 B each
 struct SmemMap {
     int F, rows, V, total;  // byte offsets of the box-size dependent arrays
@@ -39,7 +41,7 @@ __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 __host__ __device__ inline SmemMap smem_map(int N, int H) {
     SmemMap m;
     int o = OFF_GEO + (H + KC) * 32;
-    m.F = o;    o += align16(8 * H * 4);             // analysis: 8 mirror-folded rows
+    m.F = o;    o += 2 * align16(8 * H * 4);         // analysis: 8 mirror-folded rows of the row group and of its transpose
     m.rows = o; o += align16(4 * N * 4);             // analysis: 4 staged rows
     m.V = o;    o += align16(4 * H * 4);             // synthesis: class sums of one row group
     m.total = o;
@@ -92,7 +94,7 @@ __device__ __forceinline__ unsigned long long swap2(unsigned long long v) {
 }
 
 struct Ctx {  // all members are compile-time offsets from the dynamic shared memory base
-    float *Rs, *Ps, *cm, *sm;
+    float *Rs, *Ps, *cm, *sm, *cm2, *sm2;
     int *poffw, *roffw, *goff, *rbase;
     float2 *gd;
     float4 *rk;
@@ -111,6 +113,8 @@ __device__ __forceinline__ Ctx make_ctx(unsigned char *smem) {
     c.rbase = tabs + 3 * (LMAX + 1);
     c.cm = reinterpret_cast<float *>(smem + OFF_CM);
     c.sm = reinterpret_cast<float *>(smem + OFF_SM);
+    c.cm2 = reinterpret_cast<float *>(smem + OFF_CM2);
+    c.sm2 = reinterpret_cast<float *>(smem + OFF_SM2);
     c.geo = reinterpret_cast<Geo *>(smem + OFF_GEO);
     return c;
 }
@@ -154,10 +158,14 @@ __device__ __forceinline__ void generate_panels(const DevPlan &P, const Ctx &c, 
                 // (l+m)&1 = (par+m)&1), plain trig for synthesis
                 float2 a = make_float2(c.cm[m], c.sm[m]);
                 if (ANALYSIS) {
+                    // row group A = (i, j) and its transpose B = (j, i) share rho, hence R and Q; the moment sum is
+                    // linear in a, so both are contracted at once with a = F_A trig_A + F_B trig_B (F_B = 0 on the diagonal)
                     const int px = m & 1, pz = (par + m) & 1;
                     const bool live = kk < H;
-                    a.x *= live ? F[((px << 1) | pz) * H + kk] : 0.f;
-                    a.y *= live ? -F[(4 | ((px ^ 1) << 1) | pz) * H + kk] : 0.f;
+                    const int cre = (((px << 1) | pz) * H) + kk, cim = ((4 | ((px ^ 1) << 1) | pz) * H) + kk;
+                    const float *FB = F + 8 * H;
+                    a.x = live ? fmaf(F[cre], a.x, FB[cre] * c.cm2[m]) : 0.f;
+                    a.y = live ? -fmaf(F[cim], a.y, FB[cim] * c.sm2[m]) : 0.f;
                 }
                 float seed = powi2(st, st2, m);                  // Q_mm = sin^m  (zm:2012-2015 / kappa_mm)
                 if (l0[q] != m) seed *= c2;                      // Q_{m+1,m} = 2c Q_mm (zm:2016-2020 / kappa)
@@ -239,17 +247,17 @@ __device__ __forceinline__ void generate_panels(const DevPlan &P, const Ctx &c, 
                 dst[q] = c.Rs + gk * RS + c.roffw[l];
                 kp[q] = c.rk + c.rbase[l];
             }
+            // every lane runs the group's longest chain length; shorter chains keep computing past their end (finite
+            // throw-away values from the next table entries) and only the store is predicated: no divergence
 #pragma unroll 2
             for (int ni = 0; ni < nmax; ++ni) {
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) {
-                    if (ni < nn[q]) {
-                        const float4 K = kp[q][ni];
-                        const float R = fmaf(fmaf(K.x, r2, K.y), R1[q], K.z * R2[q]);
-                        dst[q][ni] = R;
-                        R2[q] = R1[q];
-                        R1[q] = R;
-                    }
+                    const float4 K = kp[q][ni];
+                    const float R = fmaf(fmaf(K.x, r2, K.y), R1[q], K.z * R2[q]);
+                    if (ni < nn[q]) dst[q][ni] = R;
+                    R2[q] = R1[q];
+                    R1[q] = R;
                 }
             }
         }
@@ -304,15 +312,79 @@ __device__ __forceinline__ void load_tables(const DevPlan &P, const Ctx &c, int 
     for (int i = threadIdx.x; i < KC * (RS + PS); i += NT) c.Rs[i] = 0.0f;  // Rs and Ps are contiguous
 }
 
-// cos(m phi0), sin(m phi0) for the row group, float64 like exp(1j m phi) in zm:2297
-__device__ __forceinline__ void row_trig(const DevPlan &P, const Ctx &c, double x0, double y0) {
+// cos(m phi0), sin(m phi0) for a row group, float64 like exp(1j m phi) in zm:2297
+__device__ __forceinline__ void row_trig(const DevPlan &P, float *cm, float *sm, double x0, double y0) {
     if (threadIdx.x <= P.order) {
         const double ph = atan2(y0, x0);
         double s, co;
         sincos((double)threadIdx.x * ph, &s, &co);
-        c.cm[threadIdx.x] = (float)co;
-        c.sm[threadIdx.x] = (float)s;
+        cm[threadIdx.x] = (float)co;
+        sm[threadIdx.x] = (float)s;
     }
+}
+
+// stage the 4 rows (+-y, +-x) of row group (ip, jp) with coalesced float4 loads
+__device__ __forceinline__ void stage_rows(const DevPlan &P, const float *__restrict__ vb, float *rows, int ip, int jp) {
+    const int N = P.dim, tid = threadIdx.x;
+    const int i2 = N - 1 - ip, j2 = N - 1 - jp;
+    if (P.dim_vec4) {
+        const int nv = N >> 2;
+        for (int idx = tid; idx < 4 * nv; idx += NT) {
+            const int rw = idx / nv, q = idx - rw * nv;
+            const int ii = (rw & 2) ? i2 : ip, jj = (rw & 1) ? j2 : jp;
+            const bool dup = ((rw & 2) && i2 == ip) || ((rw & 1) && j2 == jp);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!dup) v = __ldg(reinterpret_cast<const float4 *>(vb + ((size_t)ii * N + jj) * N) + q);
+            reinterpret_cast<float4 *>(rows + rw * N)[q] = v;
+        }
+    } else {
+        for (int idx = tid; idx < 4 * N; idx += NT) {
+            const int rw = idx / N, q = idx - rw * N;
+            const int ii = (rw & 2) ? i2 : ip, jj = (rw & 1) ? j2 : jp;
+            const bool dup = ((rw & 2) && i2 == ip) || ((rw & 1) && j2 == jp);
+            rows[rw * N + q] = dup ? 0.0f : __ldg(vb + ((size_t)ii * N + jj) * N + q);
+        }
+    }
+}
+
+// fold the 8 mirror images of the staged rows: F[c][k] = sum_img f_img (-1)^popcount(c & img),
+// img = sy*4 + sx*2 + sz,  c = py*4 + px*2 + pz
+__device__ __forceinline__ void fold_rows(const DevPlan &P, const float *rows, float *F) {
+    const int N = P.dim, H = P.H;
+    for (int k = threadIdx.x; k < H; k += NT) {
+        const int k2 = N - 1 - k;
+        float v[8];
+#pragma unroll
+        for (int img = 0; img < 8; ++img) {
+            const float x = rows[(img >> 1) * N + ((img & 1) ? k2 : k)];
+            v[img] = ((img & 1) && k2 == k) ? 0.0f : x;
+        }
+        wht8(v);
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) F[cc * H + k] = v[cc];
+    }
+}
+
+// Work items of an analysis call over plane pairs [lo, hi): for ip in [lo, hi) the row groups (ip, jp) with jp outside
+// the slab (single: the transpose's planes are not available), then jp in [ip, hi) (jp > ip: paired with the transpose
+// (jp, ip); jp == ip: diagonal).  Row ip holds H + lo - ip items.
+__host__ __device__ inline int analysis_items(int lo, int hi, int H) {
+    const int n = hi - lo;
+    return n * H - n * (n - 1) / 2;
+}
+__device__ __forceinline__ void decode_item(int item, int lo, int hi, int H, int &ip, int &jp, bool &paired) {
+    // largest t with t*H - t(t-1)/2 <= item
+    const double b = 2.0 * H + 1.0;
+    int t = (int)((b - sqrt(b * b - 8.0 * (double)item)) * 0.5);
+    t = max(0, min(t, hi - lo - 1));
+    while (t > 0 && t * H - t * (t - 1) / 2 > item) --t;
+    while (t + 1 < hi - lo && (t + 1) * H - (t + 1) * t / 2 <= item) ++t;
+    const int rem = item - (t * H - t * (t - 1) / 2);
+    ip = lo + t;
+    const int nout = lo + (H - hi);
+    if (rem < lo) { jp = rem; paired = false; }
+    else if (rem < nout) { jp = hi + (rem - lo); paired = false; }
+    else { jp = ip + (rem - nout); paired = (jp != ip); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -357,7 +429,9 @@ k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_
         p0p[s] = c.Ps + t.p0; p1p[s] = c.Ps + t.p1;
     }
 
-    const int nG = (half_hi - half_lo) * H;
+    const int CPR = (H + KC - 1) / KC;  // chunks per row group
+    const long long total = (long long)analysis_items(half_lo, half_hi, H) * CPR;
+    const long long cbeg = total * split / P.nsplit, cend = total * (split + 1) / P.nsplit;  // this CTA's chunk range
     const size_t N3 = (size_t)N * N * N;
     for (int b = 0; b < batch; ++b) {
         unsigned long long acc[TS][32];  // [(ip*4 + jp)*2 + {D, X}]
@@ -367,53 +441,35 @@ k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_
             for (int e = 0; e < 32; ++e) acc[s][e] = 0ull;
         const float *vb = vol + (size_t)b * N3;
 
-        for (int g = split; g < nG; g += P.nsplit) {
-            const int ip = half_lo + g / H, jp = g % H;
-            const int i2 = N - 1 - ip, j2 = N - 1 - jp;
+        for (long long cc = cbeg; cc < cend;) {
+            const int item = (int)(cc / CPR), kfirst = (int)(cc % CPR);
+            int ip, jp;
+            bool paired;
+            decode_item(item, half_lo, half_hi, H, ip, jp, paired);
             const double y0 = P.side[ip], x0 = P.side[jp];
             const double rho2 = x0 * x0 + y0 * y0, rho = sqrt(rho2);
 
-            // ---- stage the 4 rows (+-y, +-x) of this row group: coalesced float4 loads -> smem
+            // ---- per-item setup: stage + fold the rows of (ip, jp) and of its transpose, trig of both, geometry
             __syncthreads();
-            if (P.dim_vec4) {
-                const int nv = N >> 2;
-                for (int idx = tid; idx < 4 * nv; idx += NT) {
-                    const int rw = idx / nv, q = idx - rw * nv;
-                    const int ii = (rw & 2) ? i2 : ip, jj = (rw & 1) ? j2 : jp;
-                    const bool dup = ((rw & 2) && i2 == ip) || ((rw & 1) && j2 == jp);
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (!dup) v = __ldg(reinterpret_cast<const float4 *>(vb + ((size_t)ii * N + jj) * N) + q);
-                    reinterpret_cast<float4 *>(rows + rw * N)[q] = v;
-                }
-            } else {
-                for (int idx = tid; idx < 4 * N; idx += NT) {
-                    const int rw = idx / N, q = idx - rw * N;
-                    const int ii = (rw & 2) ? i2 : ip, jj = (rw & 1) ? j2 : jp;
-                    const bool dup = ((rw & 2) && i2 == ip) || ((rw & 1) && j2 == jp);
-                    rows[rw * N + q] = dup ? 0.0f : __ldg(vb + ((size_t)ii * N + jj) * N + q);
-                }
-            }
-            row_trig(P, c, x0, y0);
+            stage_rows(P, vb, rows, ip, jp);
+            row_trig(P, c.cm, c.sm, x0, y0);
+            row_trig(P, c.cm2, c.sm2, y0, x0);
             row_geometry(P, c, rho2, rho);
             __syncthreads();
-            // ---- fold the 8 mirror images: F[c][k] = sum_img f_img (-1)^popcount(c & img),
-            //      img = sy*4 + sx*2 + sz,  c = py*4 + px*2 + pz
-            for (int k = tid; k < H; k += NT) {
-                const int k2 = N - 1 - k;
-                float v[8];
-#pragma unroll
-                for (int img = 0; img < 8; ++img) {
-                    const float x = rows[(img >> 1) * N + ((img & 1) ? k2 : k)];
-                    v[img] = ((img & 1) && k2 == k) ? 0.0f : x;
-                }
-                wht8(v);
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) F[cc * H + k] = v[cc];
+            fold_rows(P, rows, F);
+            __syncthreads();
+            if (paired) {
+                stage_rows(P, vb, rows, jp, ip);
+                __syncthreads();
+                fold_rows(P, rows, F + 8 * H);
+            } else {
+                for (int k = tid; k < 8 * H; k += NT) F[8 * H + k] = 0.0f;
             }
             __syncthreads();
 
-            for (int k0 = 0; k0 < H; k0 += KC) {
-                if (k0) __syncthreads();  // the previous chunk's contraction is done reading the panels
+            for (int kc = kfirst; kc < CPR && cc < cend; ++kc, ++cc) {
+                const int k0 = kc * KC;
+                if (kc != kfirst) __syncthreads();  // the previous chunk's contraction is done reading the panels
                 // ---- step 1: recurrences -> operand panels in smem
 #ifndef Z3D_DEBUG_SKIP_GEN
                 generate_panels<NPH, true>(P, c, F, k0, pass, warp, lane);
@@ -562,7 +618,7 @@ k_reconstruct(const DevPlan P, const float *__restrict__ otiles, int batch, int 
             const double y0 = P.side[ip], x0 = P.side[jp];
             const double rho2 = x0 * x0 + y0 * y0, rho = sqrt(rho2);
             __syncthreads();
-            row_trig(P, c, x0, y0);
+            row_trig(P, c.cm, c.sm, x0, y0);
             row_geometry(P, c, rho2, rho);
             __syncthreads();
 
