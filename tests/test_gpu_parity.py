@@ -77,6 +77,10 @@ def test_128_order50_against_exact_oracle_rows(plans, oracle_mod):
     P = plans(order, dim)
     v = volume(1, dim)
     dv = dev(v)
+    exact = oracle_mod.decompose(v, order, oracle_mod.EXACT)     # ~2 s on the GPU box's host cores
+    full = P.decompose(dv).cpu().numpy()
+    assert rel_l2(full, exact) < TOL_EXACT
+    assert rel_l2(P.invariants(dev(full)).cpu().numpy(), oracle_mod.invariants(exact, order)) < TOL_INV
     for lo, hi in [(0, 1), (37, 38), (63, 64)]:
         got = P.decompose(dv, pairs=(lo, hi)).cpu().numpy()
         want = (oracle_mod.decompose(v, order, oracle_mod.EXACT, rows=(lo, hi), return_f64=True)
@@ -176,7 +180,8 @@ def test_256_stress_case(plans):
     dv = dev(volume(8, dim))
     full = P.decompose(dv)
     parts = P.decompose(dv, pairs=(0, 50)) + P.decompose(dv, pairs=(50, 128))
-    assert rel_l2(parts.cpu().numpy(), full.cpu().numpy()) < 5e-7
+    assert rel_l2(parts.cpu().numpy(), full.cpu().numpy()) < 1e-6   # different float32 summation grouping only
+    assert torch.equal(torch.view_as_real(full), torch.view_as_real(P.decompose(dv)))
     from zernike3d_b200.indexing import nlm_table
 
     m0 = nlm_table(order)[:, 2] == 0

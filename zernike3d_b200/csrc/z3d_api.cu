@@ -407,7 +407,7 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
     d.side = d_side; d.gd = d_gd; d.goff = d_goff; d.rk = d_rk; d.rbase = d_rbase; d.roffw = d_roffw; d.poffw = d_poffw;
     d.ownl = d_ownl; d.nown = d_nown; d.ntiles = d_ntiles; d.tiles = d_tiles; d.gen_tasks = d_gen;
 
-    rc = set_kernel_attrs(pl->smem_bytes);
+    rc = set_kernel_attrs((int)prop.sharedMemPerBlockOptin);  // per-function attribute: plans of any size coexist
     if (rc) {
         z3d_plan_destroy(pl);
         return rc;
@@ -649,3 +649,15 @@ extern "C" int z3d_fma_peak(int device, int variant, int iters, double *tflops) 
     cudaFree(d_out);
     return Z3D_OK;
 }
+
+#ifdef Z3D_DEBUG_TIMING
+extern "C" int z3d_debug_dump(long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, z3d::g_dbg, sizeof(long long) * 8);
+    if (reset) {
+        long long z[8] = {0};
+        cudaMemcpyToSymbol(z3d::g_dbg, z, sizeof z);
+    }
+    return 0;
+}
+#endif

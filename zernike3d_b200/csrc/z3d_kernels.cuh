@@ -16,6 +16,16 @@
 
 namespace z3d {
 
+#ifdef Z3D_DEBUG_TIMING
+// developer instrumentation: per-warp cycle totals of the analysis kernel's phases (warp 0 lane 0 of CTA 0..)
+__device__ long long g_dbg[8];
+#define DBG_T(var) const long long var = clock64()
+#define DBG_ADD(slot, t0, t1) do { if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&g_dbg[slot], (unsigned long long)((t1) - (t0))); } while (0)
+#else
+#define DBG_T(var)
+#define DBG_ADD(slot, t0, t1)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // shared-memory carve-up.  Everything the recurrences and the contraction touch sits at a COMPILE-TIME offset
 // (fixed-size tables first): with 64 accumulators live the compiler otherwise rematerialises the layout arithmetic
@@ -207,23 +217,45 @@ __device__ __forceinline__ void generate_panels(const DevPlan &P, const Ctx &c, 
                 }
                 --until;
             }
-            // main loop: every chain is live
-#pragma unroll 2
-            for (; l <= L; l += 2, ++p) {
-#pragma unroll
-                for (int q = 0; q < CPL; ++q) {
-                    const float2 g = tp[q][p - 1];
+            // main loop: every chain is live.  Coefficients and store offsets are fetched one iteration ahead so the
+            // shared-memory latency is off the recurrence's critical path (which is one FFMA per level).
+            if (NPH == 1 && CPL == 1) {
+                const float2 *t0 = tp[0] + p - 1;
+                const int *po = c.poffw + l;
+                float *d0 = dst[0];
+                float2 g = t0[0];
+                int off = po[0];
+                float a1 = A1[0], a2 = A2[0], b1 = B1[0], b2 = B2[0];
+                const int npos = (l <= L) ? (L - l) / 2 + 1 : 0;
+#pragma unroll 4
+                for (int i = 0; i < npos; ++i) {
+                    const float2 gn = t0[i + 1];       // tables are padded: reads past the chain end are discarded
+                    const int offn = po[2 * i + 2];
                     const float tt = c2sq - g.x;
-                    const float An = fmaf(tt, A1[q], g.y * A2[q]), Bn = fmaf(tt, B1[q], g.y * B2[q]);
-                    A2[q] = A1[q]; A1[q] = An; B2[q] = B1[q]; B1[q] = Bn;
+                    const float an = fmaf(tt, a1, g.y * a2), bn = fmaf(tt, b1, g.y * b2);
+                    a2 = a1; a1 = an; b2 = b1; b1 = bn;
+                    *reinterpret_cast<float2 *>(d0 + off) = make_float2(an, bn);
+                    g = gn;
+                    off = offn;
                 }
-                if (NPH == 1 || until == 0) {
-                    const int off = c.poffw[l];
+            } else {
+#pragma unroll 2
+                for (; l <= L; l += 2, ++p) {
 #pragma unroll
-                    for (int q = 0; q < CPL; ++q) *reinterpret_cast<float2 *>(dst[q] + off) = make_float2(A1[q], B1[q]);
-                    until = nph;
+                    for (int q = 0; q < CPL; ++q) {
+                        const float2 g = tp[q][p - 1];
+                        const float tt = c2sq - g.x;
+                        const float An = fmaf(tt, A1[q], g.y * A2[q]), Bn = fmaf(tt, B1[q], g.y * B2[q]);
+                        A2[q] = A1[q]; A1[q] = An; B2[q] = B1[q]; B1[q] = Bn;
+                    }
+                    if (until == 0) {
+                        const int off = c.poffw[l];
+#pragma unroll
+                        for (int q = 0; q < CPL; ++q) *reinterpret_cast<float2 *>(dst[q] + off) = make_float2(A1[q], B1[q]);
+                        until = nph;
+                    }
+                    --until;
                 }
-                --until;
             }
         } else {
             // Radial chains for own l = ownl[base + q*SUBS + gsub]:  R_n = (K1 r^2 + K2) R_{n-2} + K3 R_{n-4}
@@ -249,15 +281,19 @@ __device__ __forceinline__ void generate_panels(const DevPlan &P, const Ctx &c, 
             }
             // every lane runs the group's longest chain length; shorter chains keep computing past their end (finite
             // throw-away values from the next table entries) and only the store is predicated: no divergence
-#pragma unroll 2
+            float4 Kc[CPL];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) Kc[q] = kp[q][0];
+#pragma unroll 4
             for (int ni = 0; ni < nmax; ++ni) {
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) {
-                    const float4 K = kp[q][ni];
-                    const float R = fmaf(fmaf(K.x, r2, K.y), R1[q], K.z * R2[q]);
+                    const float4 Kn = kp[q][ni + 1];  // prefetch (table is padded)
+                    const float R = fmaf(fmaf(Kc[q].x, r2, Kc[q].y), R1[q], Kc[q].z * R2[q]);
                     if (ni < nn[q]) dst[q][ni] = R;
                     R2[q] = R1[q];
                     R1[q] = R;
+                    Kc[q] = Kn;
                 }
             }
         }
@@ -441,6 +477,9 @@ k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_
             for (int e = 0; e < 32; ++e) acc[s][e] = 0ull;
         const float *vb = vol + (size_t)b * N3;
 
+        float *out = partial + (((size_t)b * P.npass + pass) * P.nsplit + split) * SLOT_WORDS;
+        int since_flush = 0;
+        bool flushed = false;
         for (long long cc = cbeg; cc < cend;) {
             const int item = (int)(cc / CPR), kfirst = (int)(cc % CPR);
             int ip, jp;
@@ -450,6 +489,7 @@ k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_
             const double rho2 = x0 * x0 + y0 * y0, rho = sqrt(rho2);
 
             // ---- per-item setup: stage + fold the rows of (ip, jp) and of its transpose, trig of both, geometry
+            DBG_T(ts0);
             __syncthreads();
             stage_rows(P, vb, rows, ip, jp);
             row_trig(P, c.cm, c.sm, x0, y0);
@@ -466,15 +506,24 @@ k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_
                 for (int k = tid; k < 8 * H; k += NT) F[8 * H + k] = 0.0f;
             }
             __syncthreads();
+            DBG_T(ts1);
+            DBG_ADD(0, ts0, ts1);
 
             for (int kc = kfirst; kc < CPR && cc < cend; ++kc, ++cc) {
                 const int k0 = kc * KC;
+                DBG_T(tw0);
                 if (kc != kfirst) __syncthreads();  // the previous chunk's contraction is done reading the panels
+                DBG_T(tg0);
+                DBG_ADD(4, tw0, tg0);
                 // ---- step 1: recurrences -> operand panels in smem
 #ifndef Z3D_DEBUG_SKIP_GEN
                 generate_panels<NPH, true>(P, c, F, k0, pass, warp, lane);
 #endif
+                DBG_T(tg1);
                 __syncthreads();
+                DBG_T(tm0);
+                DBG_ADD(1, tg0, tg1);
+                DBG_ADD(2, tg1, tm0);
                 // ---- step 2: contraction over the chunk's voxels into the register tiles (fma.rn.f32x2)
 #ifndef Z3D_DEBUG_SKIP_MAC
 #pragma unroll
@@ -500,15 +549,49 @@ k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_
                     }
                 }
 #endif
+                DBG_T(tm1);
+                DBG_ADD(3, tm0, tm1);
+            }
+            // two-level summation: every FLUSH_ITEMS row-group items the register tiles are added into this CTA's
+            // partial buffer (owned element-wise by the thread, L2 resident) and cleared, which bounds the length of
+            // any float32 running sum to a few thousand terms whatever the box size
+            if (++since_flush == FLUSH_ITEMS && cc < cend) {
+                since_flush = 0;
+#pragma unroll
+                for (int s = 0; s < TS; ++s) {
+                    if (s * NT + tid < ntile) {
+                        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(out + (size_t)(s * NT + tid) * TW);
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            ulonglong2 v = make_ulonglong2(acc[s][2 * q], acc[s][2 * q + 1]);
+                            if (flushed) {
+                                const ulonglong2 old = o[q];
+                                v.x = fadd2(v.x, old.x);
+                                v.y = fadd2(v.y, old.y);
+                            }
+                            o[q] = v;
+                            acc[s][2 * q] = 0ull;
+                            acc[s][2 * q + 1] = 0ull;
+                        }
+                    }
+                }
+                flushed = true;
             }
         }
-        float *out = partial + (((size_t)b * P.npass + pass) * P.nsplit + split) * SLOT_WORDS;
 #pragma unroll
         for (int s = 0; s < TS; ++s) {
             if (s * NT + tid < ntile) {
                 ulonglong2 *o = reinterpret_cast<ulonglong2 *>(out + (size_t)(s * NT + tid) * TW);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) o[q] = make_ulonglong2(acc[s][2 * q], acc[s][2 * q + 1]);
+                for (int q = 0; q < 16; ++q) {
+                    ulonglong2 v = make_ulonglong2(acc[s][2 * q], acc[s][2 * q + 1]);
+                    if (flushed) {
+                        const ulonglong2 old = o[q];
+                        v.x = fadd2(v.x, old.x);
+                        v.y = fadd2(v.y, old.y);
+                    }
+                    o[q] = v;
+                }
             }
         }
     }
