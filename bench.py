@@ -222,12 +222,12 @@ def run_gpu_arm(args):
     # ---- voxel-sharded single volume (+ one all-reduce of the ~12k moments): latency, max over ranks
     one = dvol[:1].contiguous()
     for _ in range(3):
-        zdist.decompose_slab_sharded(plan.decompose, one, plan.half)
+        zdist.decompose_work_sharded(plan.decompose, one)
     barrier()
     e0.record()
     reps = 20
     for _ in range(reps):
-        zdist.decompose_slab_sharded(plan.decompose, one, plan.half)
+        zdist.decompose_work_sharded(plan.decompose, one)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
@@ -285,7 +285,7 @@ def run_gpu_arm(args):
                          "hbm_frac": (BATCH * (DIM ** 3 * 4 + nmom * 8)) / (k_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6553.0))},
             "cpu_baseline": cpu,
             "sharded_single_volume": {"ms": sharded_ms, "decompositions_per_s": 1e3 / sharded_ms, "gpus": world,
-                                      "how": "one 128^3 volume, mirrored plane pairs split over the ranks, "
+                                      "how": "one 128^3 volume replicated, the kernel's work list split evenly over the ranks, "
                                              "one all-reduce (NCCL) of the partial moments; max over ranks"},
             "reconstructions_per_s_per_gpu": rec_per_s,
         }

@@ -78,6 +78,14 @@ int z3d_decompose(const z3d_plan *plan, const float *d_vol, int batch, int half_
                   float *d_moments /* [batch][num_moments][2] */, void *d_workspace, size_t workspace_bytes,
                   void *stream);
 
+/* Same sum, sharded by WORK instead of by planes: the full-volume work list (row groups paired with their
+ * transposes, which is what lets the kernel fold 16 mirror images per evaluated basis value) is cut into `nparts`
+ * equal ranges and this call sums range `part`.  d_vol must hold the whole volume(s); the partial moments of all
+ * parts add up to z3d_decompose over the whole volume.  This is the balanced way to spread ONE volume over
+ * several GPUs (replicate the 4*N^3 bytes, all-reduce the moments). */
+int z3d_decompose_part(const z3d_plan *plan, const float *d_vol, int batch, int part, int nparts,
+                       float *d_moments, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* Synthesis (replaces ZernikeSpherical.Reconstruct -> _calculate_cum_GPU, zm:2642-2715, 2596-2614):
  *   vol[b][v] = Re sum_{n,l,m>=0} [ O R_nl Y_lm + (m != 0) conj(O) R_nl conj(Y_lm) ].
  * Only the planes of pairs [half_lo, half_hi) are written (the rest of d_vol is left untouched), so

@@ -59,6 +59,14 @@ def _worker(rank, world, port, out_dir):
             mom = zdist.decompose_slab_sharded(local_decompose, torch.from_numpy(local), half, deterministic=det)
             np.save(os.path.join(out_dir, f"slab_{int(det)}_{rank}.npy"), mom.numpy())
 
+        def local_part(vol, part):  # stand-in for Plan.decompose(vol, part=(i, n)): any disjoint split of the voxel sum
+            i, n = part
+            lo, hi = DIM * i // n, DIM * (i + 1) // n
+            return torch.from_numpy(oracle.decompose(vol.numpy(), ORDER, oracle.EXACT, rows=(lo, hi)))
+
+        mom = zdist.decompose_work_sharded(local_part, torch.from_numpy(v), deterministic=True)
+        np.save(os.path.join(out_dir, f"work_{rank}.npy"), mom.numpy())
+
         def local_reconstruct(moments, pairs):
             out = torch.zeros(DIM, DIM, DIM)
             for p in zdist.planes_of_pairs(DIM, *pairs):
@@ -87,6 +95,8 @@ def test_world_size_2_gloo(tmp_path, oracle_mod):
         got = [np.load(tmp_path / f"slab_{det}_{r}.npy") for r in range(world)]
         assert np.array_equal(got[0], got[1])           # every rank ends with the same full vector
         assert rel_l2(got[0], want) < 1e-6
+    work = [np.load(tmp_path / f"work_{r}.npy") for r in range(world)]
+    assert np.array_equal(work[0], work[1]) and rel_l2(work[0], want) < 1e-6
     rec_want = oracle_mod.reconstruct(want, DIM, ORDER, oracle_mod.EXACT)
     for r in range(world):
         assert rel_l2(np.load(tmp_path / f"rec_{r}.npy"), rec_want) < 1e-6

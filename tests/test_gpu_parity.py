@@ -134,6 +134,21 @@ def test_slab_partials_are_additive_and_only_read_their_planes(plans):
         assert np.array_equal(out[p], ref[p]) if p in touched else np.all(out[p] == 7.0)
 
 
+def test_work_parts_are_additive(plans):
+    """z3d_decompose_part: n equal ranges of the work list (multi-GPU sharding of one replicated volume) sum to the whole."""
+    order, dim = 50, 64
+    P = plans(order, dim)
+    dv = dev(volume(12, dim))
+    full = P.decompose(dv).cpu().numpy()
+    for n in (2, 3, 8):
+        acc = sum(P.decompose(dv, part=(i, n)).cpu().numpy() for i in range(n))
+        assert rel_l2(acc, full) < 5e-7
+    with pytest.raises(Exception):
+        P.decompose(dv, part=(3, 3))
+    with pytest.raises(ValueError):
+        P.decompose(dv, part=(0, 2), pairs=(0, 4))
+
+
 def test_deterministic_and_linear(plans):
     order, dim = 50, 64
     P = plans(order, dim)

@@ -462,8 +462,23 @@ static int check_range(const z3d_plan *pl, int batch, int lo, int hi, const char
     return Z3D_OK;
 }
 
+static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int half_lo, int half_hi, int part, int nparts,
+                          float *d_moments, void *d_ws, size_t ws_bytes, void *stream);
+
 extern "C" int z3d_decompose(const z3d_plan *pl, const float *d_vol, int batch, int half_lo, int half_hi,
                              float *d_moments, void *d_ws, size_t ws_bytes, void *stream) {
+    return decompose_impl(pl, d_vol, batch, half_lo, half_hi, 0, 1, d_moments, d_ws, ws_bytes, stream);
+}
+
+extern "C" int z3d_decompose_part(const z3d_plan *pl, const float *d_vol, int batch, int part, int nparts,
+                                  float *d_moments, void *d_ws, size_t ws_bytes, void *stream) {
+    if (!pl) return fail(Z3D_ERR_INVALID, "z3d_decompose_part: plan is NULL");
+    if (nparts < 1 || part < 0 || part >= nparts) return fail(Z3D_ERR_INVALID, "z3d_decompose_part: part %d of %d", part, nparts);
+    return decompose_impl(pl, d_vol, batch, 0, pl->H, part, nparts, d_moments, d_ws, ws_bytes, stream);
+}
+
+static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int half_lo, int half_hi, int part, int nparts,
+                          float *d_moments, void *d_ws, size_t ws_bytes, void *stream) {
     int rc = check_range(pl, batch, half_lo, half_hi, "z3d_decompose");
     if (rc) return rc;
     if (!d_vol || !d_moments || !d_ws) return fail(Z3D_ERR_INVALID, "z3d_decompose: NULL buffer");
@@ -474,9 +489,9 @@ extern "C" int z3d_decompose(const z3d_plan *pl, const float *d_vol, int batch, 
     float *partial = (float *)d_ws;
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
     if (pl->npass == 2)
-        k_decompose<1><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, half_lo, half_hi, partial);
+        k_decompose<1><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, half_lo, half_hi, part, nparts, partial);
     else
-        k_decompose<0><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, half_lo, half_hi, partial);
+        k_decompose<0><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, half_lo, half_hi, part, nparts, partial);
     CUDA_TRY(cudaGetLastError());
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k1, st));
     dim3 g((2 * pl->nmom + 255) / 256, batch);

@@ -435,7 +435,7 @@ __device__ __forceinline__ void decode_item(int item, int lo, int hi, int H, int
 // ---------------------------------------------------------------------------------------------
 template <int NPH>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM)
-k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_lo, int half_hi,
+k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_lo, int half_hi, int part, int nparts,
             float *__restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = P.order, N = P.dim, H = P.H;
@@ -467,7 +467,9 @@ k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_
 
     const int CPR = (H + KC - 1) / KC;  // chunks per row group
     const long long total = (long long)analysis_items(half_lo, half_hi, H) * CPR;
-    const long long cbeg = total * split / P.nsplit, cend = total * (split + 1) / P.nsplit;  // this CTA's chunk range
+    // this launch's share of the work list (part / nparts: multi-GPU work sharding), then this CTA's share of that
+    const long long gbeg = total * part / nparts, glen = total * (part + 1) / nparts - gbeg;
+    const long long cbeg = gbeg + glen * split / P.nsplit, cend = gbeg + glen * (split + 1) / P.nsplit;
     const size_t N3 = (size_t)N * N * N;
     for (int b = 0; b < batch; ++b) {
         unsigned long long acc[TS][32];  // [(ip*4 + jp)*2 + {D, X}]

@@ -79,6 +79,16 @@ def decompose_slab_sharded(local_decompose: Callable[..., torch.Tensor], vol: to
     return allreduce_moments(partial, group=group, deterministic=deterministic)
 
 
+def decompose_work_sharded(local_decompose: Callable[..., torch.Tensor], vol: torch.Tensor, group=None,
+                           deterministic: bool = False) -> torch.Tensor:
+    """One (batch of) volume(s) replicated on every rank, sharded by WORK: rank r sums the r-th of ``world`` equal
+    ranges of the kernel's work list (``Plan.decompose(vol, part=(r, world))``), then one all-reduce.  Unlike plane
+    slabs this keeps the transpose pairing (16-fold mirror folding) intact on every rank, so the ranks stay balanced."""
+    rank, world = _world(group)
+    partial = local_decompose(vol, part=(rank, world))
+    return allreduce_moments(partial, group=group, deterministic=deterministic)
+
+
 def reconstruct_slab_sharded(local_reconstruct: Callable[..., torch.Tensor], moments: torch.Tensor, half: int,
                              group=None, gather: bool = False) -> torch.Tensor:
     """Each rank synthesises only its planes (no collective).  ``gather=True`` additionally sums the

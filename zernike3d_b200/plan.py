@@ -81,11 +81,13 @@ class Plan:
         return float(ms.value)
 
     # ------------------------------------------------------------------ device-buffer API
-    def decompose(self, vol: torch.Tensor, pairs=None, out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
+    def decompose(self, vol: torch.Tensor, pairs=None, out: torch.Tensor | None = None, stream=None,
+                  part=None) -> torch.Tensor:
         """``vol`` float32 CUDA ``[B, N, N, N]`` (or ``[N, N, N]``) -> complex64 ``[B, num_moments]``.
 
-        ``pairs=(lo, hi)`` restricts the voxel sum to the mirrored plane pairs lo..hi-1 of axis 0
-        (slab partial for the multi-GPU path); the default is the whole volume."""
+        ``pairs=(lo, hi)`` restricts the voxel sum to the mirrored plane pairs lo..hi-1 of axis 0 (slab partial: only
+        those planes are read); ``part=(i, n)`` instead sums the i-th of n equal ranges of the full-volume work list
+        (balanced multi-GPU sharding of one replicated volume); the default is the whole volume."""
         single = vol.dim() == 3
         v = vol.unsqueeze(0) if single else vol
         N = self.dim
@@ -96,9 +98,15 @@ class Plan:
         if out is None:
             out = torch.empty((B, self.num_moments), dtype=torch.complex64, device=v.device)
         ws = self._workspace(B)
-        lo, hi = self._pairs(pairs)
-        _lib.check(self._L.z3d_decompose(self._h, _ptr(v), B, lo, hi, _ptr(out), _ptr(ws), ws.numel(),
-                                         self._stream(stream)))
+        if part is not None:
+            if pairs is not None:
+                raise ValueError("give either pairs= or part=, not both")
+            _lib.check(self._L.z3d_decompose_part(self._h, _ptr(v), B, int(part[0]), int(part[1]), _ptr(out), _ptr(ws),
+                                                  ws.numel(), self._stream(stream)))
+        else:
+            lo, hi = self._pairs(pairs)
+            _lib.check(self._L.z3d_decompose(self._h, _ptr(v), B, lo, hi, _ptr(out), _ptr(ws), ws.numel(),
+                                             self._stream(stream)))
         return out[0] if single else out
 
     def reconstruct(self, moments: torch.Tensor, pairs=None, out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
