@@ -219,6 +219,26 @@ def run_gpu_arm(args):
     e2e_value = world * BATCH * args.steps / float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- one volume spread over the ranks, fused reduce + one-shot all-reduce over NVLink peer memory (own kernel)
+    fused_ms = None
+    if world > 1:
+        from zernike3d_b200.plan import PeerComm
+
+        comm = PeerComm(plan, batch_max=1)
+        onev = dvol[:1].contiguous()
+        ref_m = zdist.decompose_work_sharded(plan.decompose, onev, deterministic=True)
+        for _ in range(3):
+            got = plan.decompose_allreduce(onev, comm)
+        barrier()
+        fused_ok = bool(torch.equal(torch.view_as_real(got), torch.view_as_real(ref_m))) and comm.error() == 0
+        e0.record()
+        for _ in range(20):
+            plan.decompose_allreduce(onev, comm)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 20], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        fused_ms = float(t.item())
     # ---- voxel-sharded single volume (+ one all-reduce of the ~12k moments): latency, max over ranks
     one = dvol[:1].contiguous()
     for _ in range(3):
@@ -286,7 +306,12 @@ def run_gpu_arm(args):
             "cpu_baseline": cpu,
             "sharded_single_volume": {"ms": sharded_ms, "decompositions_per_s": 1e3 / sharded_ms, "gpus": world,
                                       "how": "one 128^3 volume replicated, the kernel's work list split evenly over the ranks, "
-                                             "one all-reduce (NCCL) of the partial moments; max over ranks"},
+                                             "one all-reduce (NCCL) of the partial moments; max over ranks",
+                                      "fused_p2p_ms": fused_ms,
+                                      "fused_p2p_matches_rank_ordered_sum_bitwise": (fused_ok if world > 1 else None),
+                                      "fused_how": "z3d_decompose_allreduce: k_decompose share + ONE kernel that reduces the "
+                                                   "partials, publishes them in peer-mapped memory and sums all ranks' "
+                                                   "vectors in rank order through NVLink loads"},
             "reconstructions_per_s_per_gpu": rec_per_s,
         }
         print(json.dumps(line))

@@ -86,6 +86,22 @@ int z3d_decompose(const z3d_plan *plan, const float *d_vol, int batch, int half_
 int z3d_decompose_part(const z3d_plan *plan, const float *d_vol, int batch, int part, int nparts,
                        float *d_moments, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Fused analysis + all-reduce for ONE volume (batch) spread over `world` GPUs, one process per GPU.  No reference
+ * counterpart (the reference has no multi-GPU path).  z3d_comm_create allocates this rank's peer-visible buffer and
+ * returns its 64-byte CUDA IPC handle; the ranks exchange the handles out of band (torch.distributed) and call
+ * z3d_comm_connect with all of them.  z3d_decompose_allreduce then runs the rank's share of the work list
+ * (as z3d_decompose_part(rank, world)) followed by ONE kernel that reduces the rank's partials, publishes them in the
+ * peer-mapped buffer and completes a one-shot all-gather + rank-ordered sum over NVLink peer loads: every rank ends
+ * with the full, bit-identical moments, without an NCCL call on the data path.  d_vol must hold the whole volume(s).
+ * z3d_comm_error returns 1 if an exchange timed out (~2 s; the affected results are NaN) - it never hangs. */
+typedef struct z3d_comm z3d_comm;
+int z3d_comm_create(const z3d_plan *plan, int batch_max, z3d_comm **out, unsigned char *handle64);
+int z3d_comm_connect(z3d_comm *comm, int rank, int world, const unsigned char *handles /* [world][64] */);
+int z3d_comm_destroy(z3d_comm *comm);
+int z3d_comm_error(z3d_comm *comm);
+int z3d_decompose_allreduce(const z3d_plan *plan, z3d_comm *comm, const float *d_vol, int batch, float *d_moments,
+                            void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* Synthesis (replaces ZernikeSpherical.Reconstruct -> _calculate_cum_GPU, zm:2642-2715, 2596-2614):
  *   vol[b][v] = Re sum_{n,l,m>=0} [ O R_nl Y_lm + (m != 0) conj(O) R_nl conj(Y_lm) ].
  * Only the planes of pairs [half_lo, half_hi) are written (the rest of d_vol is left untouched), so

@@ -676,3 +676,110 @@ extern "C" int z3d_debug_dump(long long *out, int reset) {
     return 0;
 }
 #endif
+
+// ------------------------------------------------------------------------------------------------
+// peer-memory communicator for the fused reduce + all-reduce (one process per GPU, CUDA IPC)
+// ------------------------------------------------------------------------------------------------
+struct z3d_comm {
+    int device = 0, rank = -1, world = 0;
+    size_t max_elems = 0, bytes = 0;
+    float *local = nullptr;
+    PeerBufs peers{};
+    bool opened[MAX_RANKS] = {};
+    unsigned *d_done = nullptr;
+    int *d_err = nullptr;
+    unsigned epoch = 0;
+};
+
+extern "C" int z3d_comm_create(const z3d_plan *pl, int batch_max, z3d_comm **out, unsigned char *handle64) {
+    if (!pl || !out || !handle64 || batch_max < 1) return fail(Z3D_ERR_INVALID, "z3d_comm_create: bad arguments");
+    CUDA_TRY(cudaSetDevice(pl->device));
+    z3d_comm *c = new z3d_comm();
+    c->device = pl->device;
+    c->max_elems = (size_t)batch_max * 2 * pl->nmom;
+    c->bytes = 2 * c->max_elems * sizeof(float) + 2 * MAX_RANKS * sizeof(unsigned);
+    CUDA_TRY(cudaMalloc((void **)&c->local, c->bytes));
+    CUDA_TRY(cudaMemset(c->local, 0, c->bytes));
+    CUDA_TRY(cudaMalloc((void **)&c->d_done, sizeof(unsigned)));
+    CUDA_TRY(cudaMemset(c->d_done, 0, sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc((void **)&c->d_err, sizeof(int)));
+    CUDA_TRY(cudaMemset(c->d_err, 0, sizeof(int)));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, c->local));
+    static_assert(sizeof(h) == 64, "IPC handle size");
+    memcpy(handle64, &h, 64);
+    CUDA_TRY(cudaDeviceSynchronize());
+    *out = c;
+    return Z3D_OK;
+}
+
+extern "C" int z3d_comm_connect(z3d_comm *c, int rank, int world, const unsigned char *handles /* [world][64] */) {
+    if (!c || !handles || world < 1 || world > MAX_RANKS || rank < 0 || rank >= world)
+        return fail(Z3D_ERR_INVALID, "z3d_comm_connect: bad arguments (world <= %d)", MAX_RANKS);
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->rank = rank;
+    c->world = world;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            c->peers.data[r] = c->local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * r, 64);
+        void *p = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peers.data[r] = (float *)p;
+        c->opened[r] = true;
+    }
+    return Z3D_OK;
+}
+
+extern "C" int z3d_comm_destroy(z3d_comm *c) {
+    if (!c) return Z3D_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < MAX_RANKS; ++r)
+        if (c->opened[r]) cudaIpcCloseMemHandle(c->peers.data[r]);
+    if (c->local) cudaFree(c->local);
+    if (c->d_done) cudaFree(c->d_done);
+    if (c->d_err) cudaFree(c->d_err);
+    delete c;
+    return Z3D_OK;
+}
+
+extern "C" int z3d_decompose_allreduce(const z3d_plan *pl, z3d_comm *c, const float *d_vol, int batch, float *d_moments,
+                                       void *d_ws, size_t ws_bytes, void *stream) {
+    if (!pl || !c || c->rank < 0) return fail(Z3D_ERR_INVALID, "z3d_decompose_allreduce: communicator not connected");
+    if (!d_vol || !d_moments || !d_ws || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_decompose_allreduce: bad arguments");
+    if ((size_t)batch * 2 * pl->nmom > c->max_elems) return fail(Z3D_ERR_INVALID, "z3d_decompose_allreduce: batch exceeds communicator");
+    if (ws_bytes < ws_decompose(pl, batch)) return fail(Z3D_ERR_WORKSPACE, "z3d_decompose_allreduce: workspace too small");
+    CUDA_TRY(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    float *partial = (float *)d_ws;
+    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
+    if (pl->npass == 2)
+        k_decompose<1><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, 0, pl->H, c->rank, c->world, partial);
+    else
+        k_decompose<0><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, 0, pl->H, c->rank, c->world, partial);
+    CUDA_TRY(cudaGetLastError());
+    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k1, st));
+    dim3 g((2 * pl->nmom + 255) / 256, batch);
+    // every block of the exchange kernel waits for the peers, so all of them must be co-resident
+    if ((int)(g.x * g.y) > pl->num_sms * 4)
+        return fail(Z3D_ERR_UNSUPPORTED, "z3d_decompose_allreduce: batch %d too large for the one-shot exchange (use "
+                                         "z3d_decompose_part + a library all-reduce)", batch);
+    c->epoch += 1;
+    k_reduce_allreduce_p2p<<<g, 256, 0, st>>>(partial, pl->d_src, pl->d_scale, pl->nmom, pl->npass, pl->nsplit, batch, c->peers,
+                                              c->rank, c->world, c->max_elems, c->epoch, c->d_done, c->d_err, d_moments);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 2;
+    return Z3D_OK;
+}
+
+extern "C" int z3d_comm_error(z3d_comm *c) {  // 1 after an exchange timed out (results were set to NaN)
+    if (!c) return -1;
+    int e = 0;
+    cudaSetDevice(c->device);
+    cudaMemcpy(&e, c->d_err, sizeof(int), cudaMemcpyDeviceToHost);
+    return e;
+}

@@ -615,6 +615,79 @@ __global__ void k_reduce_moments(const float *__restrict__ partial, const int *_
     moments[(size_t)b * 2 * nmom + e] = (float)(sum * scale[e >> 1]);
 }
 
+// Fused "reduce partials + all-reduce over NVLink peer memory" for the work-sharded analysis of ONE volume spread
+// over several GPUs (one process per GPU).  Every rank owns a communication buffer that all ranks have mapped
+// (CUDA IPC): [2 slots][max_elems] floats of data followed by [2 slots][MAX_RANKS] epoch flags.
+//   1. each thread reduces this rank's per-CTA partials for its elements (same arithmetic as k_reduce_moments) and
+//      writes them into the LOCAL buffer, slot = epoch & 1;
+//   2. the last block to finish publishes `epoch` into flag[slot][rank] of EVERY rank's buffer (system-scope release);
+//   3. all blocks wait until all ranks' epochs arrived in the local flags (acquire), then
+//   4. every thread sums its elements over the ranks in rank order through peer loads (L1-bypassing) and writes the
+//      final moments: one-shot all-gather + ordered sum, bit-identical on all ranks, no NCCL call on the data path.
+// Two slots make back-to-back calls safe: a rank can be at most one call ahead of the slowest reader.
+constexpr int MAX_RANKS = 16;
+struct PeerBufs {
+    float *data[MAX_RANKS];            // base of each rank's buffer (own included), device-accessible from this GPU
+};
+__device__ __forceinline__ unsigned *comm_flags(float *base, size_t max_elems) {
+    return reinterpret_cast<unsigned *>(base + 2 * max_elems);
+}
+__global__ void k_reduce_allreduce_p2p(const float *__restrict__ partial, const int *__restrict__ src,
+                                       const double *__restrict__ scale, int nmom, int npass, int nsplit, int batch,
+                                       PeerBufs peers, int rank, int world, size_t max_elems, unsigned epoch,
+                                       unsigned *done_counter, int *error_flag, float *__restrict__ moments) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const int slot = epoch & 1;
+    const bool live = e < 2 * nmom && b < batch;
+    const size_t idx = (size_t)b * 2 * nmom + e;
+    if (live) {
+        const int s = src[e];
+        const int pass = s / SLOT_WORDS, off = s % SLOT_WORDS;
+        const float *p = partial + (((size_t)b * npass + pass) * nsplit) * SLOT_WORDS + off;
+        double sum = 0.0;
+        for (int sp = 0; sp < nsplit; ++sp) sum += (double)p[(size_t)sp * SLOT_WORDS];
+        peers.data[rank][(size_t)slot * max_elems + idx] = (float)(sum * scale[e >> 1]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool ok;
+    if (threadIdx.x == 0) {
+        ok = true;
+        const unsigned nblocks = gridDim.x * gridDim.y;
+        if (atomicAdd(done_counter, 1u) == nblocks - 1) {  // last block of this rank: publish
+            *done_counter = 0;
+            __threadfence_system();
+            for (int r = 0; r < world; ++r) {
+                unsigned *f = comm_flags(peers.data[r], max_elems) + slot * MAX_RANKS + rank;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+            }
+        }
+        const unsigned *mine = comm_flags(peers.data[rank], max_elems) + slot * MAX_RANKS;
+        const long long t0 = clock64();
+        for (int r = 0; r < world; ++r) {
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + r) : "memory");
+                if (v != epoch && clock64() - t0 > 4000000000LL) {  // ~2 s: a peer never arrived - fail, do not hang
+                    ok = false;
+                    atomicExch(error_flag, 1);
+                    break;
+                }
+            } while (v != epoch);
+        }
+    }
+    __syncthreads();
+    if (live) {
+        float acc = 0.0f;
+        if (ok)
+            for (int r = 0; r < world; ++r) acc += __ldcv(peers.data[r] + (size_t)slot * max_elems + idx);
+        else
+            acc = __int_as_float(0x7fc00000);  // NaN marks the failed exchange
+        moments[idx] = acc;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Synthesis
 // ---------------------------------------------------------------------------------------------

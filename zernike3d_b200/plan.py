@@ -109,6 +109,19 @@ class Plan:
                                              self._stream(stream)))
         return out[0] if single else out
 
+    def decompose_allreduce(self, vol: torch.Tensor, comm: "PeerComm", out: torch.Tensor | None = None, stream=None):
+        """Work-sharded analysis of replicated volume(s) fused with a one-shot all-reduce over NVLink peer memory
+        (``z3d_decompose_allreduce``): every rank returns the full, bit-identical moments."""
+        single = vol.dim() == 3
+        v = (vol.unsqueeze(0) if single else vol).contiguous()
+        B = v.shape[0]
+        if out is None:
+            out = torch.empty((B, self.num_moments), dtype=torch.complex64, device=v.device)
+        ws = self._workspace(B)
+        _lib.check(self._L.z3d_decompose_allreduce(self._h, comm._c, _ptr(v), B, _ptr(out), _ptr(ws), ws.numel(),
+                                                   self._stream(stream)))
+        return out[0] if single else out
+
     def reconstruct(self, moments: torch.Tensor, pairs=None, out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
         """complex64 CUDA ``[B, num_moments]`` -> float32 ``[B, N, N, N]`` (planes outside ``pairs`` untouched)."""
         single = moments.dim() == 1
@@ -158,6 +171,38 @@ class Plan:
         _lib.check(self._L.z3d_reconstruct_host(self._h, ctypes.c_void_p(m.ctypes.data), B,
                                                 ctypes.c_void_p(o.ctypes.data)))
         return out[0] if single else out
+
+
+class PeerComm:
+    """Peer-mapped communication buffers of the fused analysis + all-reduce path: one per rank, exchanged as CUDA IPC
+    handles through ``torch.distributed`` (control plane only; the data path is the kernel's own NVLink loads)."""
+
+    def __init__(self, plan: Plan, batch_max: int = 1, group=None):
+        import torch.distributed as dist
+
+        self._L = _lib.lib()
+        self._c = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(self._L.z3d_comm_create(plan._h, int(batch_max), ctypes.byref(self._c), handle))
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        _lib.check(self._L.z3d_comm_connect(self._c, self.rank, self.world, b"".join(handles)))
+        dist.barrier(group)
+
+    def error(self) -> int:
+        return int(self._L.z3d_comm_error(self._c))
+
+    def close(self):
+        c, self._c = self._c, None
+        if c:
+            self._L.z3d_comm_destroy(c)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def launch_count() -> int:
