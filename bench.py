@@ -271,8 +271,11 @@ def run_gpu_arm(args):
         peaks = measured_peaks()
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_max * 1e6 / 1e12     # 74.45 TFLOP/s at 1965 MHz
-        k_ms = float(np.mean(kernel_ms))
-        W = algorithmic_flops(nmom, DIM) * BATCH
+        # z3d_decompose runs the batch in groups of a few volumes (one k_decompose launch each, so that the per-CTA
+        # partial sums stay in L2); last_kernel_ms() is the sum over the launches of one call
+        n_launch = max(1, int(launches) // (2 * args.steps))          # k_decompose launches per step
+        k_ms = float(np.mean(kernel_ms)) / n_launch                   # average duration of one launch
+        W = algorithmic_flops(nmom, DIM) * BATCH / n_launch           # algorithmic flops of one launch
         achieved = W / (k_ms * 1e-3) / 1e12
         fma_live = [fma_peak_tflops(local, v, 4096) for v in (0, 1)]
         traffic = None
@@ -296,13 +299,14 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "kernel": "z3d::k_decompose", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak, "traffic": traffic,
-                         "kernel_ms": k_ms, "algorithmic_flops_per_launch": W,
+                         "kernel_ms": k_ms, "algorithmic_flops_per_launch": W, "launches_per_step": n_launch,
+                         "volumes_per_launch": BATCH // n_launch, "algorithmic_bytes_per_launch": (BATCH // n_launch) * (DIM ** 3 * 4 + nmom * 8),
                          "peak_source": f"FP32 FMA: 148 SMs x 128 lanes x 2 x sm_max_mhz ({sm_max:.0f} MHz, MEASURED_PEAKS.json); "
                                         "MEASURED_PEAKS.json has no FP32 figure, the live FMA micro-benchmark is `fma_microbench_tflops`",
                          "fma_microbench_tflops": {"ffma": fma_live[0], "ffma2": fma_live[1]},
                          "note": "achieved = 4*N_mom*N^3 flops per volume / k_decompose time; mirror folding executes 1/8 of these, "
                                  "so frac may exceed 1 (executed-pipe utilisation is in profiles/)",
-                         "hbm_frac": (BATCH * (DIM ** 3 * 4 + nmom * 8)) / (k_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6553.0))},
+                         "hbm_frac": ((BATCH // n_launch) * (DIM ** 3 * 4 + nmom * 8)) / (k_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6553.0))},
             "cpu_baseline": cpu,
             "sharded_single_volume": {"ms": sharded_ms, "decompositions_per_s": 1e3 / sharded_ms, "gpus": world,
                                       "how": "one 128^3 volume replicated, the kernel's work list split evenly over the ranks, "

@@ -78,7 +78,11 @@ struct z3d_plan {
     int stage_batch = 0;
     // optional per-kernel timing (bench.py roofline): events around the dominant kernel of the last call
     bool profiling = false;
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;       // synthesis kernel / fused path
+    static constexpr int MAX_TIMED = 64;
+    cudaEvent_t ev_t0[MAX_TIMED] = {}, ev_t1[MAX_TIMED] = {};  // one pair per analysis-kernel launch of the last call
+    int n_timed = 0;
+    bool last_was_decompose = false;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -429,6 +433,10 @@ extern "C" int z3d_plan_destroy(z3d_plan *pl) {
     }
     if (pl->ev_k0) cudaEventDestroy(pl->ev_k0);
     if (pl->ev_k1) cudaEventDestroy(pl->ev_k1);
+    for (int i = 0; i < z3d_plan::MAX_TIMED; ++i) {
+        if (pl->ev_t0[i]) cudaEventDestroy(pl->ev_t0[i]);
+        if (pl->ev_t1[i]) cudaEventDestroy(pl->ev_t1[i]);
+    }
     if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
     if (pl->s_comp) cudaStreamDestroy(pl->s_comp);
     delete pl;
@@ -443,8 +451,15 @@ extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
     return Z3D_OK;
 }
 
+// The per-CTA partial sums of the analysis kernel are 24 MB per volume at order 50.  A batch is processed in groups of
+// a few volumes (kernel + reduction per group, same scratch) so that the partials never leave the 126 MB L2: the
+// launch's DRAM traffic is then the volumes themselves, and the scratch stays small for any batch.
+static int decompose_group(const z3d_plan *pl) {
+    const size_t per_vol = (size_t)pl->npass * pl->nsplit * SLOT_WORDS * sizeof(float);
+    return (int)std::max<size_t>(1, ((size_t)64 << 20) / per_vol);
+}
 static size_t ws_decompose(const z3d_plan *pl, int batch) {
-    return (size_t)batch * pl->npass * pl->nsplit * SLOT_WORDS * sizeof(float);
+    return (size_t)std::min(batch, decompose_group(pl)) * pl->npass * pl->nsplit * SLOT_WORDS * sizeof(float);
 }
 static size_t ws_reconstruct(const z3d_plan *pl, int batch) {
     const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
@@ -487,17 +502,28 @@ static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int
     CUDA_TRY(cudaSetDevice(pl->device));
     cudaStream_t st = (cudaStream_t)stream;
     float *partial = (float *)d_ws;
-    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
-    if (pl->npass == 2)
-        k_decompose<1><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, half_lo, half_hi, part, nparts, partial);
-    else
-        k_decompose<0><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, half_lo, half_hi, part, nparts, partial);
-    CUDA_TRY(cudaGetLastError());
-    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k1, st));
-    dim3 g((2 * pl->nmom + 255) / 256, batch);
-    k_reduce_moments<<<g, 256, 0, st>>>(partial, pl->d_src, pl->d_scale, pl->nmom, pl->npass, pl->nsplit, batch, d_moments);
-    CUDA_TRY(cudaGetLastError());
-    g_launches += 2;
+    const int grp = decompose_group(pl);
+    const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
+    z3d_plan *mpl = const_cast<z3d_plan *>(pl);  // timing bookkeeping only
+    mpl->n_timed = 0;
+    mpl->last_was_decompose = true;
+    for (int b0 = 0; b0 < batch; b0 += grp) {
+        const int nb = std::min(grp, batch - b0);
+        const float *vol = d_vol + (size_t)b0 * N3;
+        const bool timed = pl->profiling && mpl->n_timed < z3d_plan::MAX_TIMED;
+        if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t0[mpl->n_timed], st));
+        if (pl->npass == 2)
+            k_decompose<1><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, vol, nb, half_lo, half_hi, part, nparts, partial);
+        else
+            k_decompose<0><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, vol, nb, half_lo, half_hi, part, nparts, partial);
+        CUDA_TRY(cudaGetLastError());
+        if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t1[mpl->n_timed++], st));
+        dim3 g((2 * pl->nmom + 255) / 256, nb);
+        k_reduce_moments<<<g, 256, 0, st>>>(partial, pl->d_src, pl->d_scale, pl->nmom, pl->npass, pl->nsplit, nb,
+                                            d_moments + (size_t)b0 * 2 * pl->nmom);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 2;
+    }
     return Z3D_OK;
 }
 
@@ -516,6 +542,7 @@ extern "C" int z3d_reconstruct(const z3d_plan *pl, const float *d_moments, int b
     dim3 g((pl->npass * SLOT_WORDS + 255) / 256, batch);
     k_prepare_tiles<<<g, 256, 0, st>>>(d_moments, pl->d_omap, pl->d_ofac, pl->nmom, pl->npass, batch, otiles);
     CUDA_TRY(cudaGetLastError());
+    const_cast<z3d_plan *>(pl)->last_was_decompose = false;
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
     if (pl->npass == 2)
         k_reconstruct<1><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, otiles, batch, half_lo, half_hi, pvol);
@@ -536,6 +563,10 @@ extern "C" int z3d_profile_enable(z3d_plan *pl, int on) {
     if (on && !pl->ev_k0) {
         CUDA_TRY(cudaEventCreate(&pl->ev_k0));
         CUDA_TRY(cudaEventCreate(&pl->ev_k1));
+        for (int i = 0; i < z3d_plan::MAX_TIMED; ++i) {
+            CUDA_TRY(cudaEventCreate(&pl->ev_t0[i]));
+            CUDA_TRY(cudaEventCreate(&pl->ev_t1[i]));
+        }
     }
     pl->profiling = on != 0;
     return Z3D_OK;
@@ -543,6 +574,17 @@ extern "C" int z3d_profile_enable(z3d_plan *pl, int on) {
 
 extern "C" int z3d_profile_last_ms(z3d_plan *pl, float *ms) {
     if (!pl || !ms || !pl->ev_k0) return fail(Z3D_ERR_INVALID, "z3d_profile_last_ms: profiling was not enabled");
+    if (pl->last_was_decompose) {  // sum over the analysis-kernel launches of the last call (one per volume group)
+        float tot = 0.f;
+        for (int i = 0; i < pl->n_timed; ++i) {
+            float t = 0.f;
+            CUDA_TRY(cudaEventSynchronize(pl->ev_t1[i]));
+            CUDA_TRY(cudaEventElapsedTime(&t, pl->ev_t0[i], pl->ev_t1[i]));
+            tot += t;
+        }
+        *ms = tot;
+        return Z3D_OK;
+    }
     CUDA_TRY(cudaEventSynchronize(pl->ev_k1));
     CUDA_TRY(cudaEventElapsedTime(ms, pl->ev_k0, pl->ev_k1));
     return Z3D_OK;
@@ -756,6 +798,7 @@ extern "C" int z3d_decompose_allreduce(const z3d_plan *pl, z3d_comm *c, const fl
     CUDA_TRY(cudaSetDevice(pl->device));
     cudaStream_t st = (cudaStream_t)stream;
     float *partial = (float *)d_ws;
+    const_cast<z3d_plan *>(pl)->last_was_decompose = false;
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
     if (pl->npass == 2)
         k_decompose<1><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, 0, pl->H, c->rank, c->world, partial);

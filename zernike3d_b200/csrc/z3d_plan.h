@@ -34,7 +34,7 @@ constexpr int PS = 1476;         // smem words per voxel for the a*P panel (== 4
 constexpr int GD_MAX = 1536;     // float2 entries of the per-pass Legendre coefficient table in smem
 constexpr int RK_MAX = 640;      // float4 entries of the per-pass radial coefficient table in smem
 constexpr int MAXTASK = 8;       // generation tasks per warp
-constexpr int FLUSH_ITEMS = 4;    // row-group items between flushes of the register tiles (two-level summation)
+constexpr int FLUSH_ITEMS = 8;    // row-group items between flushes of the register tiles (two-level summation)
 constexpr int CTAS_PER_SM = 2;
 constexpr int SLOT_WORDS = NT * TS * TW;  // accumulator words one CTA owns
 
