@@ -46,7 +46,6 @@ inline int num_radial(int order) {
     for (int n = 0; n <= order; ++n) c += n / 2 + 1;
     return c;
 }
-inline int pad4(int x) { return (x + 3) & ~3; }
 
 template <class T>
 int upload(const std::vector<T> &h, T **d, std::vector<void *> &owned) {

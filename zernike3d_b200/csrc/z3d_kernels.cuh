@@ -438,24 +438,15 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 k_decompose(const DevPlan P, const float *__restrict__ vol, int batch, int half_lo, int half_hi, int part, int nparts,
             float *__restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int L = P.order, N = P.dim, H = P.H;
+    const int N = P.dim, H = P.H;
     const SmemMap mp = smem_map(N, H);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pass = blockIdx.x % P.npass, split = blockIdx.x / P.npass;
-    const int par = pass & 1;
     const Ctx c = make_ctx(smem);
     load_tables(P, c, pass);
     float *rows = reinterpret_cast<float *>(smem + mp.rows);
     float *F = reinterpret_cast<float *>(smem + mp.F);
     const int ntile = P.ntiles[pass];
-#ifndef Z3D_NO_STAGGER
-    // the two CTAs of an SM have identical phase lengths; without an offset they
-    // generate and contract in lockstep and never overlap.  Delay the odd pass by about half a chunk period once.
-    if (blockIdx.x >= (gridDim.x >> 1)) {  // CTA b and b + grid/2 share an SM (round-robin block placement)
-        const long long t0 = clock64();
-        while (clock64() - t0 < 3500) {}
-    }
-#endif
 
     const float *r0p[TS], *r1p[TS], *p0p[TS], *p1p[TS];
 #pragma unroll
@@ -735,7 +726,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 k_reconstruct(const DevPlan P, const float *__restrict__ otiles, int batch, int half_lo, int half_hi,
               float *__restrict__ pvol) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int L = P.order, N = P.dim, H = P.H;
+    const int N = P.dim, H = P.H;
     const SmemMap mp = smem_map(N, H);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pass = blockIdx.x % P.npass, split = blockIdx.x / P.npass;
