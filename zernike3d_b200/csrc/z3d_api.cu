@@ -1,12 +1,14 @@
 // zernike3d_b200 - host planner and C ABI (see include/zernike3d_b200.h for the contract).
 #include "../../include/zernike3d_b200.h"
 #include "z3d_kernels.cuh"
+#include "z3d_batched.cuh"
 
 #include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -61,6 +63,12 @@ struct z3d_plan {
     int order = 0, dim = 0, device = 0, H = 0, nmom = 0, nrad = 0, npass = 0, nsplit = 0, num_sms = 0;
     int smem_bytes = 0, useful_acc = 0, padded_acc = 0;
     DevPlan dev{};
+    // batched analysis kernel (tiles of BNV volumes); absent when the order does not fit its fixed layout
+    bool batched = false;
+    int batched_min = 24;        // smallest (remaining) batch that is routed to the batched kernel
+    DevPlanB devb{};
+    int2 *d_rowmap = nullptr;
+    int b_smem = 0;
     // reduce / prepare tables
     int *d_src = nullptr;        // [2*nmom]  pass*SLOT_WORDS + word
     double *d_scale = nullptr;   // [nmom]    coeff(n) * kappa_lm
@@ -118,6 +126,7 @@ struct HostPlan {
     std::vector<int> goff;      // [npass][L+1]
     std::vector<float4> rk;     // [npass][RK_MAX]
     std::vector<double> kappa;  // [(L+1)*(L+1)] kappa[l*(L+1)+m]
+    std::vector<double> beta;   // [(L+1)*(L+4)]  beta[m*(L+4)+l] of the monic Legendre recurrence, 0 outside m+2..L
     std::vector<int> src, omap;
     int useful = 0, padded = 0;
 };
@@ -164,7 +173,8 @@ int build_host_plan(int L, HostPlan &hp) {
     // ---- coefficient tables (float64 on the host, like the reference's Python scalars)
     // Legendre: C1, C2 of zm:2017-2024, C3 of zm:2013; kappa_mm = P_mm / sin^m, kappa_lm = kappa_{l-1,m} C1/2
     hp.kappa.assign((size_t)S * S, 0.0);
-    std::vector<double> beta((size_t)S * (S + 3), 0.0);  // beta[m*(S+3) + l], zero for l <= m+1 and l > L
+    hp.beta.assign((size_t)S * (S + 3), 0.0);  // beta[m*(S+3) + l], zero for l <= m+1 and l > L
+    std::vector<double> &beta = hp.beta;
     std::vector<double> C1((size_t)S * S, 0.0), C2((size_t)S * S, 0.0);
     for (int l = 1; l <= L; ++l)
         for (int m = 0; m < l; ++m) {
@@ -300,6 +310,145 @@ int build_host_plan(int L, HostPlan &hp) {
     return Z3D_OK;
 }
 
+
+// ---- planner of the batched analysis kernel (z3d_batched.cuh) ------------------------------------------------------
+struct HostPlanB {
+    bool ok = false;
+    int ngroups = 0, nsplit = 0;
+    std::vector<int2> rowtab, rowmap;
+    std::vector<int> blk_mpz, mpz, nmpz, mlo, mhi, goff, qoff, rbase, gen_tasks;
+    std::vector<float4> gd, rk;
+};
+
+// Returns ok = false (no error) when the order does not fit the fixed shared-memory layout: callers then use the
+// per-volume kernel for batches as well.
+void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
+    const int S = L + 1;
+    if (num_radial(L) + 8 > BR_MAX) return;
+    // rows per (m, pz) in (m, pz) order, padded to blocks of 8
+    struct Row { int n, l, m; };
+    std::vector<Row> rows;           // padded row list, n = -1 for padding
+    std::vector<int> blk_code;       // m | pz << 16 per block
+    for (int m = 0; m <= L; ++m)
+        for (int pz = 0; pz < 2; ++pz) {
+            int cnt = 0;
+            for (int l = m + pz; l <= L; l += 2)
+                for (int n = l; n <= L; n += 2, ++cnt) rows.push_back({n, l, m});
+            if (cnt == 0) continue;
+            for (; cnt % 8; ++cnt) rows.push_back({-1, 0, m});
+            for (int b = (int)blk_code.size(); b < (int)rows.size() / 8; ++b) blk_code.push_back(m | (pz << 16));
+        }
+    const int nblk = (int)blk_code.size();
+    const int ngroups = (nblk + BBLK_MAX - 3) / (BBLK_MAX - 2);  // <= 78 blocks: 624 threads + spare for balance
+    if (ngroups > num_sms) return;
+    const int per = (nblk + ngroups - 1) / ngroups;
+    hb.ngroups = ngroups;
+    hb.nsplit = std::max(1, num_sms / ngroups);
+    hb.rowtab.assign((size_t)ngroups * BROWS_MAX, make_int2(0, 0));
+    hb.blk_mpz.assign((size_t)ngroups * BBLK_MAX, 0);
+    hb.mpz.assign((size_t)ngroups * BMPZ_MAX, -1);
+    hb.nmpz.assign(ngroups, 0);
+    hb.mlo.assign(ngroups, 0);
+    hb.mhi.assign(ngroups, 0);
+    hb.goff.assign((size_t)ngroups * S, 0);
+    hb.qoff.assign((size_t)ngroups * S, 0);
+    hb.gd.assign((size_t)ngroups * BGD_MAX, make_float4(0.f, 0.f, 0.f, 0.f));
+    hb.gen_tasks.assign((size_t)ngroups * BNWARP * BMAXTASK, 0);
+    hb.rowmap.assign(num_moments(L), make_int2(-1, -1));
+    // radial table, l-major over ALL l (index in rk == index in the R panel)
+    hb.rbase.assign(S, 0);
+    hb.rk.assign(BR_MAX, make_float4(0.f, 0.f, 0.f, 0.f));
+    {
+        int pos = 0;
+        for (int l = 0; l <= L; ++l) {
+            hb.rbase[l] = pos;
+            for (int n = l; n <= L; n += 2) {
+                float4 K = make_float4(0.f, 0.f, 1.f, 0.f);
+                if (n > l) {
+                    const double k0 = (double)(n - l) * (n + l + 1) * (2 * n - 3);
+                    const double k1 = (double)(2 * n - 1) * (2 * n + 1) * (2 * n - 3);
+                    const double k2 = 0.5 * (double)(-2 * n + 1) * (double)((2 * l + 1) * (2 * l + 1)) - k1 / 2.0;
+                    const double k3 = -1.0 * (double)(n - l - 2) * (n + l - 1) * (2 * n + 1);
+                    K = make_float4((float)(k1 / k0), (float)(k2 / k0), (float)(k3 / k0), 0.f);
+                }
+                hb.rk[pos++] = K;
+            }
+        }
+    }
+    std::vector<int> mubase((size_t)S * S, -1);
+    {
+        int mu = 0;
+        for (int n = 0; n <= L; ++n)
+            for (int l = n & 1; l <= n; l += 2) {
+                mubase[(size_t)n * S + l] = mu;
+                mu += l + 1;
+            }
+    }
+    for (int g = 0; g < ngroups; ++g) {
+        const int b0 = g * per, b1 = std::min(nblk, b0 + per);
+        if (b0 >= b1) return;  // cannot happen for ngroups = ceil(nblk / cap)
+        const int mlo = blk_code[b0] & 0xffff, mhi = blk_code[b1 - 1] & 0xffff;
+        hb.mlo[g] = mlo;
+        hb.mhi[g] = mhi;
+        // Q panel and coefficient-table offsets of the group's m
+        int qpos = 0, gpos = 0;
+        for (int m = mlo; m <= mhi; ++m) {
+            hb.qoff[(size_t)g * S + m] = qpos;
+            qpos += 2 * ((L - m) / 2 + 1);
+            hb.goff[(size_t)g * S + m] = gpos;
+            const double *bm = &hp.beta[(size_t)m * (S + 3)];
+            auto B = [&](int l) { return (l >= 0 && l < S + 3) ? bm[l] : 0.0; };
+            const int cnt = (L - m) / 2 + 4;
+            if (gpos + cnt > BGD_MAX) return;
+            for (int i = 0; i < cnt; ++i) {
+                const int le = m + 2 * i, lo = le + 1;
+                hb.gd[(size_t)g * BGD_MAX + gpos + i] =
+                    make_float4((float)(B(le + 2) + B(le + 1)), (float)(-(B(le + 1) * B(le))),
+                                (float)(B(lo + 2) + B(lo + 1)), (float)(-(B(lo + 1) * B(lo))));
+            }
+            gpos += cnt;
+        }
+        if (qpos > BQ_MAX) return;
+        // a panels and rows
+        int nm = 0, last = -1;
+        for (int b = b0; b < b1; ++b) {
+            if (blk_code[b] != last) {
+                if (nm >= BMPZ_MAX) return;
+                hb.mpz[(size_t)g * BMPZ_MAX + nm++] = blk_code[b];
+                last = blk_code[b];
+            }
+            hb.blk_mpz[(size_t)g * BBLK_MAX + (b - b0)] = nm - 1;
+            for (int i = 0; i < 8; ++i) {
+                const Row &r = rows[(size_t)b * 8 + i];
+                if (r.n < 0) continue;
+                const int row = (b - b0) * 8 + i;
+                hb.rowtab[(size_t)g * BROWS_MAX + row] =
+                    make_int2(hb.rbase[r.l] + (r.n - r.l) / 2, hb.qoff[(size_t)g * S + r.m] + (r.l - r.m));
+                hb.rowmap[mubase[(size_t)r.n * S + r.l] + r.m] = make_int2(g, row);
+            }
+        }
+        hb.nmpz[g] = nm;
+        // generation tasks: one group of 4 chains (x 8 voxels) per warp-task, longest first over the 20 warps
+        struct Task { int code; int cost; };
+        std::vector<Task> tasks;
+        for (int m0 = mlo; m0 <= mhi; m0 += 4) tasks.push_back({(1 << 16) | m0, ((L - m0) / 2 + 1) * 24 + 80});
+        for (int l0 = mlo & ~3; l0 <= L; l0 += 4) tasks.push_back({(2 << 16) | l0, ((L - l0) / 2 + 1) * 16 + 60});
+        std::sort(tasks.begin(), tasks.end(), [](const Task &a, const Task &b) { return a.cost > b.cost; });
+        int load[BNWARP] = {0}, cnt[BNWARP] = {0};
+        for (const Task &tk : tasks) {
+            int w = 0;
+            for (int q = 1; q < BNWARP; ++q)
+                if (load[q] < load[w]) w = q;
+            if (cnt[w] >= BMAXTASK) return;
+            hb.gen_tasks[((size_t)g * BNWARP + w) * BMAXTASK + cnt[w]++] = tk.code;
+            load[w] += tk.cost;
+        }
+    }
+    for (const int2 &r : hb.rowmap)
+        if (r.x < 0) return;
+    hb.ok = true;
+}
+
 template <int NPH>
 int set_kernel_attrs_t(int smem) {
     CUDA_TRY(cudaFuncSetAttribute(k_decompose<NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -311,7 +460,14 @@ int set_kernel_attrs_t(int smem) {
 
 int set_kernel_attrs(int smem) {
     int rc = set_kernel_attrs_t<1>(smem);
-    return rc ? rc : set_kernel_attrs_t<0>(smem);
+    if (rc) return rc;
+#ifdef Z3D_DEBUG_TIMING
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, smem - 2048));  // static s_dbg
+#else
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+#endif
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    return set_kernel_attrs_t<0>(smem);
 }
 
 }  // namespace
@@ -406,10 +562,30 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
     UP(hp.gen_tasks, d_gen) UP(hp.tiles, d_tiles)
     UP(hp.src, pl->d_src) UP(scale, pl->d_scale) UP(hp.omap, pl->d_omap) UP(ofac, pl->d_ofac)
     UP(nl_base, pl->d_nl_base) UP(nl_l, pl->d_nl_l)
-#undef UP
     d.side = d_side; d.gd = d_gd; d.goff = d_goff; d.rk = d_rk; d.rbase = d_rbase; d.roffw = d_roffw; d.poffw = d_poffw;
     d.ownl = d_ownl; d.nown = d_nown; d.ntiles = d_ntiles; d.tiles = d_tiles; d.gen_tasks = d_gen;
 
+    {
+        HostPlanB hb;
+        build_batched_plan(order, prop.multiProcessorCount, hp, hb);
+        pl->b_smem = batched_smem_bytes(pl->H);
+        // dim >= 14: the staged 8-voxel segments (direct and z-mirrored) must lie inside a row
+        if (hb.ok && dim >= 14 && (size_t)pl->b_smem <= prop.sharedMemPerBlockOptin) {
+            DevPlanB &b = pl->devb;
+            b.order = order; b.dim = dim; b.H = pl->H; b.ngroups = hb.ngroups; b.nsplit = hb.nsplit; b.side = d_side;
+            int2 *d_rowtab; int *d_bm, *d_mpz, *d_nmpz, *d_mlo, *d_mhi, *d_bgoff, *d_qoff, *d_brbase, *d_bgen;
+            float4 *d_bgd, *d_brk;
+            UP(hb.rowtab, d_rowtab) UP(hb.blk_mpz, d_bm) UP(hb.mpz, d_mpz) UP(hb.nmpz, d_nmpz) UP(hb.mlo, d_mlo)
+            UP(hb.mhi, d_mhi) UP(hb.goff, d_bgoff) UP(hb.qoff, d_qoff) UP(hb.rbase, d_brbase) UP(hb.gen_tasks, d_bgen)
+            UP(hb.gd, d_bgd) UP(hb.rk, d_brk) UP(hb.rowmap, pl->d_rowmap)
+            b.rowtab = d_rowtab; b.blk_mpz = d_bm; b.mpz = d_mpz; b.nmpz = d_nmpz; b.mlo = d_mlo; b.mhi = d_mhi;
+            b.goff = d_bgoff; b.qoff = d_qoff; b.rbase = d_brbase; b.gen_tasks = d_bgen; b.gd = d_bgd; b.rk = d_brk;
+            pl->batched = true;
+        }
+    }
+#undef UP
+
+    if (const char *e = getenv("Z3D_BATCHED_MIN")) pl->batched_min = std::max(1, atoi(e));  // tuning / tests
     rc = set_kernel_attrs((int)prop.sharedMemPerBlockOptin);  // per-function attribute: plans of any size coexist
     if (rc) {
         z3d_plan_destroy(pl);
@@ -444,9 +620,10 @@ extern "C" int z3d_plan_destroy(z3d_plan *pl) {
 
 extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
     if (!pl || !info) return fail(Z3D_ERR_INVALID, "z3d_plan_info: NULL argument");
-    const int v[12] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
-                       KC, pl->num_sms, pl->useful_acc, pl->padded_acc};
-    for (int i = 0; i < n && i < 12; ++i) info[i] = v[i];
+    const int v[16] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
+                       KC, pl->num_sms, pl->useful_acc, pl->padded_acc,
+                       pl->batched ? pl->batched_min : 0, pl->devb.ngroups, pl->devb.nsplit, BNV};
+    for (int i = 0; i < n && i < 16; ++i) info[i] = v[i];
     return Z3D_OK;
 }
 
@@ -458,7 +635,10 @@ static int decompose_group(const z3d_plan *pl) {
     return (int)std::max<size_t>(1, ((size_t)64 << 20) / per_vol);
 }
 static size_t ws_decompose(const z3d_plan *pl, int batch) {
-    return (size_t)std::min(batch, decompose_group(pl)) * pl->npass * pl->nsplit * SLOT_WORDS * sizeof(float);
+    size_t w = (size_t)std::min(batch, decompose_group(pl)) * pl->npass * pl->nsplit * SLOT_WORDS * sizeof(float);
+    if (pl->batched && batch >= pl->batched_min)
+        w = std::max(w, (size_t)pl->devb.ngroups * pl->devb.nsplit * BSLOT_WORDS * sizeof(float));
+    return w;
 }
 static size_t ws_reconstruct(const z3d_plan *pl, int batch) {
     const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
@@ -506,7 +686,24 @@ static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int
     z3d_plan *mpl = const_cast<z3d_plan *>(pl);  // timing bookkeeping only
     mpl->n_timed = 0;
     mpl->last_was_decompose = true;
-    for (int b0 = 0; b0 < batch; b0 += grp) {
+    int done = 0;
+    // batches: tiles of up to BNV volumes through the batched kernel (whole-volume calls only); what is left below
+    // the threshold goes through the per-volume kernel
+    while (pl->batched && half_lo == 0 && half_hi == pl->H && batch - done >= pl->batched_min) {
+        const int nb = std::min(BNV, batch - done);
+        const float *vol = d_vol + (size_t)done * N3;
+        const bool timed = pl->profiling && mpl->n_timed < z3d_plan::MAX_TIMED;
+        if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t0[mpl->n_timed], st));
+        k_decompose_batched<<<pl->devb.ngroups * pl->devb.nsplit, BNT, pl->b_smem, st>>>(pl->devb, vol, nb, part, nparts, partial);
+        CUDA_TRY(cudaGetLastError());
+        if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t1[mpl->n_timed++], st));
+        k_reduce_batched<<<(pl->nmom * BCOL + 255) / 256, 256, 0, st>>>(partial, pl->d_rowmap, pl->d_scale, pl->nmom,
+                                                                       pl->devb.nsplit, nb, d_moments + (size_t)done * 2 * pl->nmom);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 2;
+        done += nb;
+    }
+    for (int b0 = done; b0 < batch; b0 += grp) {
         const int nb = std::min(grp, batch - b0);
         const float *vol = d_vol + (size_t)b0 * N3;
         const bool timed = pl->profiling && mpl->n_timed < z3d_plan::MAX_TIMED;
