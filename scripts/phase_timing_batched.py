@@ -15,9 +15,9 @@ for _ in range(2): P.decompose(v)
 L.z3d_debug_dump(buf, 1)
 P.decompose(v); ms = P.last_kernel_ms()
 L.z3d_debug_dump(buf, 1)
-names = ["wait top barrier", "X: T and a panels", "wait barrier 2", "Y: fold+recur", "Y: contraction", "-", "-", "-"]
+names = ["wait barrier B", "geo + wait MMA", "flush", "T and a panels", "wait barrier A", "issue MMA + stage", "fold", "recurrences + trig"]
 info = P.info()
-nw = info["batched_row_groups"] * info["batched_splits"] * 20
+nw = info["batched_row_groups"] * info["batched_splits"] * 32
 tot = sum(buf[i] for i in range(8))
 print(f"kernel {ms:.3f} ms = {ms*1.965e6:.0f} clk @1965MHz; warps {nw}")
 for i, n in enumerate(names):

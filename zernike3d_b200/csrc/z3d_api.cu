@@ -65,7 +65,7 @@ struct z3d_plan {
     DevPlan dev{};
     // batched analysis kernel (tiles of BNV volumes); absent when the order does not fit its fixed layout
     bool batched = false;
-    int batched_min = 24;        // smallest (remaining) batch that is routed to the batched kernel
+    int batched_min = 8;         // smallest (remaining) batch that is routed to the batched kernel
     DevPlanB devb{};
     int2 *d_rowmap = nullptr;
     int b_smem = 0;
@@ -311,12 +311,12 @@ int build_host_plan(int L, HostPlan &hp) {
 }
 
 
-// ---- planner of the batched analysis kernel (z3d_batched.cuh) ------------------------------------------------------
+// ---- planner of the batched (tensor-core) analysis kernel (z3d_batched.cuh) -----------------------------------------
 struct HostPlanB {
     bool ok = false;
     int ngroups = 0, nsplit = 0;
     std::vector<int2> rowtab, rowmap;
-    std::vector<int> blk_mpz, mpz, nmpz, mlo, mhi, goff, qoff, rbase, gen_tasks;
+    std::vector<int> tile_mpz, mpz, nmpz, ntile, mlo, mhi, goff, qoff, rbase, gen_tasks;
     std::vector<float4> gd, rk;
 };
 
@@ -324,30 +324,30 @@ struct HostPlanB {
 // per-volume kernel for batches as well.
 void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
     const int S = L + 1;
-    if (num_radial(L) + 8 > BR_MAX) return;
-    // rows per (m, pz) in (m, pz) order, padded to blocks of 8
+    if (num_radial(L) + 9 > BR_MAX) return;  // 8 prefetch entries + the zero slot
+    // rows of every (m, pz), in (m, pz) order, padded to tiles of BTM
     struct Row { int n, l, m; };
     std::vector<Row> rows;           // padded row list, n = -1 for padding
-    std::vector<int> blk_code;       // m | pz << 16 per block
+    std::vector<int> tile_code;      // m | pz << 16 per tile
     for (int m = 0; m <= L; ++m)
         for (int pz = 0; pz < 2; ++pz) {
             int cnt = 0;
             for (int l = m + pz; l <= L; l += 2)
                 for (int n = l; n <= L; n += 2, ++cnt) rows.push_back({n, l, m});
             if (cnt == 0) continue;
-            for (; cnt % 8; ++cnt) rows.push_back({-1, 0, m});
-            for (int b = (int)blk_code.size(); b < (int)rows.size() / 8; ++b) blk_code.push_back(m | (pz << 16));
+            for (; cnt % BTM; ++cnt) rows.push_back({-1, 0, m});
+            for (int t = (int)tile_code.size(); t < (int)rows.size() / BTM; ++t) tile_code.push_back(m | (pz << 16));
         }
-    const int nblk = (int)blk_code.size();
-    const int ngroups = (nblk + BBLK_MAX - 3) / (BBLK_MAX - 2);  // <= 78 blocks: 624 threads + spare for balance
+    const int ntiles = (int)tile_code.size();
+    const int ngroups = (ntiles + BTILES - 1) / BTILES;
     if (ngroups > num_sms) return;
-    const int per = (nblk + ngroups - 1) / ngroups;
     hb.ngroups = ngroups;
     hb.nsplit = std::max(1, num_sms / ngroups);
-    hb.rowtab.assign((size_t)ngroups * BROWS_MAX, make_int2(0, 0));
-    hb.blk_mpz.assign((size_t)ngroups * BBLK_MAX, 0);
+    hb.rowtab.assign((size_t)ngroups * BROWS_MAX, make_int2(BR_MAX - 1, 0));  // padding rows: T = 0 * Q
+    hb.tile_mpz.assign((size_t)ngroups * BTILES, 0);
     hb.mpz.assign((size_t)ngroups * BMPZ_MAX, -1);
     hb.nmpz.assign(ngroups, 0);
+    hb.ntile.assign(ngroups, 0);
     hb.mlo.assign(ngroups, 0);
     hb.mhi.assign(ngroups, 0);
     hb.goff.assign((size_t)ngroups * S, 0);
@@ -363,8 +363,8 @@ void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
         for (int l = 0; l <= L; ++l) {
             hb.rbase[l] = pos;
             for (int n = l; n <= L; n += 2) {
-                float4 K = make_float4(0.f, 0.f, 1.f, 0.f);
-                if (n > l) {
+                float4 K = make_float4(0.f, 0.f, 1.f, 0.f);  // n == l: R = 1 * seed (R_ll = r^l, zm:1983-1984)
+                if (n > l) {  // K1, K2, K3 of zm:1992-1998
                     const double k0 = (double)(n - l) * (n + l + 1) * (2 * n - 3);
                     const double k1 = (double)(2 * n - 1) * (2 * n + 1) * (2 * n - 3);
                     const double k2 = 0.5 * (double)(-2 * n + 1) * (double)((2 * l + 1) * (2 * l + 1)) - k1 / 2.0;
@@ -385,11 +385,11 @@ void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
             }
     }
     for (int g = 0; g < ngroups; ++g) {
-        const int b0 = g * per, b1 = std::min(nblk, b0 + per);
-        if (b0 >= b1) return;  // cannot happen for ngroups = ceil(nblk / cap)
-        const int mlo = blk_code[b0] & 0xffff, mhi = blk_code[b1 - 1] & 0xffff;
+        const int t0 = g * BTILES, t1 = std::min(ntiles, t0 + BTILES);
+        const int mlo = tile_code[t0] & 0xffff, mhi = tile_code[t1 - 1] & 0xffff;
         hb.mlo[g] = mlo;
         hb.mhi[g] = mhi;
+        hb.ntile[g] = t1 - t0;
         // Q panel and coefficient-table offsets of the group's m
         int qpos = 0, gpos = 0;
         for (int m = mlo; m <= mhi; ++m) {
@@ -411,30 +411,31 @@ void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
         if (qpos > BQ_MAX) return;
         // a panels and rows
         int nm = 0, last = -1;
-        for (int b = b0; b < b1; ++b) {
-            if (blk_code[b] != last) {
-                if (nm >= BMPZ_MAX) return;
-                hb.mpz[(size_t)g * BMPZ_MAX + nm++] = blk_code[b];
-                last = blk_code[b];
+        for (int t = t0; t < t1; ++t) {
+            if (tile_code[t] != last) {
+                hb.mpz[(size_t)g * BMPZ_MAX + nm++] = tile_code[t];
+                last = tile_code[t];
             }
-            hb.blk_mpz[(size_t)g * BBLK_MAX + (b - b0)] = nm - 1;
-            for (int i = 0; i < 8; ++i) {
-                const Row &r = rows[(size_t)b * 8 + i];
+            hb.tile_mpz[(size_t)g * BTILES + (t - t0)] = nm - 1;
+            for (int i = 0; i < BTM; ++i) {
+                const Row &r = rows[(size_t)t * BTM + i];
                 if (r.n < 0) continue;
-                const int row = (b - b0) * 8 + i;
+                const int row = (t - t0) * BTM + i;
                 hb.rowtab[(size_t)g * BROWS_MAX + row] =
                     make_int2(hb.rbase[r.l] + (r.n - r.l) / 2, hb.qoff[(size_t)g * S + r.m] + (r.l - r.m));
                 hb.rowmap[mubase[(size_t)r.n * S + r.l] + r.m] = make_int2(g, row);
             }
         }
         hb.nmpz[g] = nm;
-        // generation tasks: one group of 4 chains (x 8 voxels) per warp-task, longest first over the 20 warps
+        // generation tasks: one group of 4 chains (x 8 voxels) per warp-task, longest first over the warps
         struct Task { int code; int cost; };
         std::vector<Task> tasks;
         for (int m0 = mlo; m0 <= mhi; m0 += 4) tasks.push_back({(1 << 16) | m0, ((L - m0) / 2 + 1) * 24 + 80});
         for (int l0 = mlo & ~3; l0 <= L; l0 += 4) tasks.push_back({(2 << 16) | l0, ((L - l0) / 2 + 1) * 16 + 60});
         std::sort(tasks.begin(), tasks.end(), [](const Task &a, const Task &b) { return a.cost > b.cost; });
+        // warp 0 issues the MMAs and warps 0-15 stage and fold the voxels before their tasks: the others go first
         int load[BNWARP] = {0}, cnt[BNWARP] = {0};
+        for (int w = 0; w < BNWARP; ++w) load[w] = (w == 0) ? 2000 : (w < 16 ? 200 : 0);
         for (const Task &tk : tasks) {
             int w = 0;
             for (int q = 1; q < BNWARP; ++q)
@@ -573,12 +574,12 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
         if (hb.ok && dim >= 14 && (size_t)pl->b_smem <= prop.sharedMemPerBlockOptin) {
             DevPlanB &b = pl->devb;
             b.order = order; b.dim = dim; b.H = pl->H; b.ngroups = hb.ngroups; b.nsplit = hb.nsplit; b.side = d_side;
-            int2 *d_rowtab; int *d_bm, *d_mpz, *d_nmpz, *d_mlo, *d_mhi, *d_bgoff, *d_qoff, *d_brbase, *d_bgen;
+            int2 *d_rowtab; int *d_bm, *d_mpz, *d_nmpz, *d_ntile, *d_mlo, *d_mhi, *d_bgoff, *d_qoff, *d_brbase, *d_bgen;
             float4 *d_bgd, *d_brk;
-            UP(hb.rowtab, d_rowtab) UP(hb.blk_mpz, d_bm) UP(hb.mpz, d_mpz) UP(hb.nmpz, d_nmpz) UP(hb.mlo, d_mlo)
-            UP(hb.mhi, d_mhi) UP(hb.goff, d_bgoff) UP(hb.qoff, d_qoff) UP(hb.rbase, d_brbase) UP(hb.gen_tasks, d_bgen)
-            UP(hb.gd, d_bgd) UP(hb.rk, d_brk) UP(hb.rowmap, pl->d_rowmap)
-            b.rowtab = d_rowtab; b.blk_mpz = d_bm; b.mpz = d_mpz; b.nmpz = d_nmpz; b.mlo = d_mlo; b.mhi = d_mhi;
+            UP(hb.rowtab, d_rowtab) UP(hb.tile_mpz, d_bm) UP(hb.mpz, d_mpz) UP(hb.nmpz, d_nmpz) UP(hb.ntile, d_ntile)
+            UP(hb.mlo, d_mlo) UP(hb.mhi, d_mhi) UP(hb.goff, d_bgoff) UP(hb.qoff, d_qoff) UP(hb.rbase, d_brbase)
+            UP(hb.gen_tasks, d_bgen) UP(hb.gd, d_bgd) UP(hb.rk, d_brk) UP(hb.rowmap, pl->d_rowmap)
+            b.rowtab = d_rowtab; b.tile_mpz = d_bm; b.mpz = d_mpz; b.nmpz = d_nmpz; b.ntile = d_ntile; b.mlo = d_mlo; b.mhi = d_mhi;
             b.goff = d_bgoff; b.qoff = d_qoff; b.rbase = d_brbase; b.gen_tasks = d_bgen; b.gd = d_bgd; b.rk = d_brk;
             pl->batched = true;
         }
