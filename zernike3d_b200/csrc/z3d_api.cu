@@ -69,6 +69,10 @@ struct z3d_plan {
     DevPlanB devb{};
     int2 *d_rowmap = nullptr;
     int b_smem = 0;
+    long long b_chunks = 0;      // chunks of the whole volume: row-group items x chunks per row
+    BasisArgs basis{};           // inputs of k_build_basis; the tables themselves are built on first use
+    bool basis_ready = false;
+    float *d_Rt = nullptr, *d_Qt = nullptr, *d_trig = nullptr;
     // reduce / prepare tables
     int *d_src = nullptr;        // [2*nmom]  pass*SLOT_WORDS + word
     double *d_scale = nullptr;   // [nmom]    coeff(n) * kappa_lm
@@ -311,20 +315,62 @@ int build_host_plan(int L, HostPlan &hp) {
 }
 
 
-// ---- planner of the batched (tensor-core) analysis kernel (z3d_batched.cuh) -----------------------------------------
+// ---- planner of the batched (tensor-core) analysis path (z3d_batched.cuh) -------------------------------------------
 struct HostPlanB {
     bool ok = false;
-    int ngroups = 0, nsplit = 0;
+    int ngroups = 0, nsplit = 0, nrad = 0, nq = 0;
     std::vector<int2> rowtab, rowmap;
-    std::vector<int> tile_mpz, mpz, nmpz, ntile, mlo, mhi, goff, qoff, rbase, gen_tasks;
+    std::vector<int> tile_mpz, mpz, nmpz, ntile, qlo, qlen;
+    // inputs of k_build_basis
+    std::vector<int> rbase, goff, qoff;
     std::vector<float4> gd, rk;
 };
 
-// Returns ok = false (no error) when the order does not fit the fixed shared-memory layout: callers then use the
-// per-volume kernel for batches as well.
+// Returns ok = false (no error) when the order does not fit the kernel's fixed layout: callers then use the per-volume
+// kernel for batches as well.
 void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
     const int S = L + 1;
-    if (num_radial(L) + 9 > BR_MAX) return;  // 8 prefetch entries + the zero slot
+    hb.nrad = num_radial(L);
+    // radial table, l-major over ALL l (index in rk == index in the R table)
+    hb.rbase.assign(S, 0);
+    hb.rk.assign(hb.nrad + 8, make_float4(0.f, 0.f, 0.f, 0.f));
+    {
+        int pos = 0;
+        for (int l = 0; l <= L; ++l) {
+            hb.rbase[l] = pos;
+            for (int n = l; n <= L; n += 2) {
+                float4 K = make_float4(0.f, 0.f, 1.f, 0.f);  // n == l: R = 1 * seed (R_ll = r^l, zm:1983-1984)
+                if (n > l) {  // K1, K2, K3 of zm:1992-1998
+                    const double k0 = (double)(n - l) * (n + l + 1) * (2 * n - 3);
+                    const double k1 = (double)(2 * n - 1) * (2 * n + 1) * (2 * n - 3);
+                    const double k2 = 0.5 * (double)(-2 * n + 1) * (double)((2 * l + 1) * (2 * l + 1)) - k1 / 2.0;
+                    const double k3 = -1.0 * (double)(n - l - 2) * (n + l - 1) * (2 * n + 1);
+                    K = make_float4((float)(k1 / k0), (float)(k2 / k0), (float)(k3 / k0), 0.f);
+                }
+                hb.rk[pos++] = K;
+            }
+        }
+    }
+    // Legendre coefficients and Q table offsets of every m: pairs (E_i, O_i) = levels (m + 2i, m + 2i + 1)
+    hb.goff.assign(S, 0);
+    hb.qoff.assign(S, 0);
+    {
+        int qpos = 0;
+        for (int m = 0; m <= L; ++m) {
+            hb.qoff[m] = qpos;
+            qpos += 2 * ((L - m) / 2 + 1);
+            hb.goff[m] = (int)hb.gd.size();
+            const double *bm = &hp.beta[(size_t)m * (S + 3)];
+            auto B = [&](int l) { return (l >= 0 && l < S + 3) ? bm[l] : 0.0; };
+            for (int i = 0; i < (L - m) / 2 + 2; ++i) {
+                const int le = m + 2 * i, lo = le + 1;
+                hb.gd.push_back(make_float4((float)(B(le + 2) + B(le + 1)), (float)(-(B(le + 1) * B(le))),
+                                            (float)(B(lo + 2) + B(lo + 1)), (float)(-(B(lo + 1) * B(lo)))));
+            }
+        }
+        hb.nq = qpos;
+    }
+    if (hb.nrad + 4 > 65535 || hb.nq > 65535) return;
     // rows of every (m, pz), in (m, pz) order, padded to tiles of BTM
     struct Row { int n, l, m; };
     std::vector<Row> rows;           // padded row list, n = -1 for padding
@@ -343,38 +389,14 @@ void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
     if (ngroups > num_sms) return;
     hb.ngroups = ngroups;
     hb.nsplit = std::max(1, num_sms / ngroups);
-    hb.rowtab.assign((size_t)ngroups * BROWS_MAX, make_int2(BR_MAX - 1, 0));  // padding rows: T = 0 * Q
+    hb.rowtab.assign((size_t)ngroups * BROWS_MAX, make_int2(hb.nrad, 0));  // padding rows: the zero R entry
     hb.tile_mpz.assign((size_t)ngroups * BTILES, 0);
     hb.mpz.assign((size_t)ngroups * BMPZ_MAX, -1);
     hb.nmpz.assign(ngroups, 0);
     hb.ntile.assign(ngroups, 0);
-    hb.mlo.assign(ngroups, 0);
-    hb.mhi.assign(ngroups, 0);
-    hb.goff.assign((size_t)ngroups * S, 0);
-    hb.qoff.assign((size_t)ngroups * S, 0);
-    hb.gd.assign((size_t)ngroups * BGD_MAX, make_float4(0.f, 0.f, 0.f, 0.f));
-    hb.gen_tasks.assign((size_t)ngroups * BNWARP * BMAXTASK, 0);
+    hb.qlo.assign(ngroups, 0);
+    hb.qlen.assign(ngroups, 0);
     hb.rowmap.assign(num_moments(L), make_int2(-1, -1));
-    // radial table, l-major over ALL l (index in rk == index in the R panel)
-    hb.rbase.assign(S, 0);
-    hb.rk.assign(BR_MAX, make_float4(0.f, 0.f, 0.f, 0.f));
-    {
-        int pos = 0;
-        for (int l = 0; l <= L; ++l) {
-            hb.rbase[l] = pos;
-            for (int n = l; n <= L; n += 2) {
-                float4 K = make_float4(0.f, 0.f, 1.f, 0.f);  // n == l: R = 1 * seed (R_ll = r^l, zm:1983-1984)
-                if (n > l) {  // K1, K2, K3 of zm:1992-1998
-                    const double k0 = (double)(n - l) * (n + l + 1) * (2 * n - 3);
-                    const double k1 = (double)(2 * n - 1) * (2 * n + 1) * (2 * n - 3);
-                    const double k2 = 0.5 * (double)(-2 * n + 1) * (double)((2 * l + 1) * (2 * l + 1)) - k1 / 2.0;
-                    const double k3 = -1.0 * (double)(n - l - 2) * (n + l - 1) * (2 * n + 1);
-                    K = make_float4((float)(k1 / k0), (float)(k2 / k0), (float)(k3 / k0), 0.f);
-                }
-                hb.rk[pos++] = K;
-            }
-        }
-    }
     std::vector<int> mubase((size_t)S * S, -1);
     {
         int mu = 0;
@@ -387,29 +409,10 @@ void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
     for (int g = 0; g < ngroups; ++g) {
         const int t0 = g * BTILES, t1 = std::min(ntiles, t0 + BTILES);
         const int mlo = tile_code[t0] & 0xffff, mhi = tile_code[t1 - 1] & 0xffff;
-        hb.mlo[g] = mlo;
-        hb.mhi[g] = mhi;
         hb.ntile[g] = t1 - t0;
-        // Q panel and coefficient-table offsets of the group's m
-        int qpos = 0, gpos = 0;
-        for (int m = mlo; m <= mhi; ++m) {
-            hb.qoff[(size_t)g * S + m] = qpos;
-            qpos += 2 * ((L - m) / 2 + 1);
-            hb.goff[(size_t)g * S + m] = gpos;
-            const double *bm = &hp.beta[(size_t)m * (S + 3)];
-            auto B = [&](int l) { return (l >= 0 && l < S + 3) ? bm[l] : 0.0; };
-            const int cnt = (L - m) / 2 + 4;
-            if (gpos + cnt > BGD_MAX) return;
-            for (int i = 0; i < cnt; ++i) {
-                const int le = m + 2 * i, lo = le + 1;
-                hb.gd[(size_t)g * BGD_MAX + gpos + i] =
-                    make_float4((float)(B(le + 2) + B(le + 1)), (float)(-(B(le + 1) * B(le))),
-                                (float)(B(lo + 2) + B(lo + 1)), (float)(-(B(lo + 1) * B(lo))));
-            }
-            gpos += cnt;
-        }
-        if (qpos > BQ_MAX) return;
-        // a panels and rows
+        hb.qlo[g] = hb.qoff[mlo];
+        hb.qlen[g] = hb.qoff[mhi] + 2 * ((L - mhi) / 2 + 1) - hb.qoff[mlo];
+        if (hb.qlen[g] > BQ_MAX) return;
         int nm = 0, last = -1;
         for (int t = t0; t < t1; ++t) {
             if (tile_code[t] != last) {
@@ -422,28 +425,11 @@ void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
                 if (r.n < 0) continue;
                 const int row = (t - t0) * BTM + i;
                 hb.rowtab[(size_t)g * BROWS_MAX + row] =
-                    make_int2(hb.rbase[r.l] + (r.n - r.l) / 2, hb.qoff[(size_t)g * S + r.m] + (r.l - r.m));
+                    make_int2(hb.rbase[r.l] + (r.n - r.l) / 2, hb.qoff[r.m] + (r.l - r.m) - hb.qlo[g]);
                 hb.rowmap[mubase[(size_t)r.n * S + r.l] + r.m] = make_int2(g, row);
             }
         }
         hb.nmpz[g] = nm;
-        // generation tasks: one group of 4 chains (x 8 voxels) per warp-task, longest first over the warps
-        struct Task { int code; int cost; };
-        std::vector<Task> tasks;
-        for (int m0 = mlo; m0 <= mhi; m0 += 4) tasks.push_back({(1 << 16) | m0, ((L - m0) / 2 + 1) * 24 + 80});
-        for (int l0 = mlo & ~3; l0 <= L; l0 += 4) tasks.push_back({(2 << 16) | l0, ((L - l0) / 2 + 1) * 16 + 60});
-        std::sort(tasks.begin(), tasks.end(), [](const Task &a, const Task &b) { return a.cost > b.cost; });
-        // warp 0 issues the MMAs and warps 0-15 stage and fold the voxels before their tasks: the others go first
-        int load[BNWARP] = {0}, cnt[BNWARP] = {0};
-        for (int w = 0; w < BNWARP; ++w) load[w] = (w == 0) ? 2000 : (w < 16 ? 200 : 0);
-        for (const Task &tk : tasks) {
-            int w = 0;
-            for (int q = 1; q < BNWARP; ++q)
-                if (load[q] < load[w]) w = q;
-            if (cnt[w] >= BMAXTASK) return;
-            hb.gen_tasks[((size_t)g * BNWARP + w) * BMAXTASK + cnt[w]++] = tk.code;
-            load[w] += tk.cost;
-        }
     }
     for (const int2 &r : hb.rowmap)
         if (r.x < 0) return;
@@ -569,18 +555,23 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
     {
         HostPlanB hb;
         build_batched_plan(order, prop.multiProcessorCount, hp, hb);
-        pl->b_smem = batched_smem_bytes(pl->H);
-        // dim >= 14: the staged 8-voxel segments (direct and z-mirrored) must lie inside a row
+        pl->b_smem = batched_smem_bytes(hb.nrad);
+        // dim >= 14 keeps every 8-voxel chunk and its z-mirror inside a row (k_fold_tile reads both)
         if (hb.ok && dim >= 14 && (size_t)pl->b_smem <= prop.sharedMemPerBlockOptin) {
             DevPlanB &b = pl->devb;
-            b.order = order; b.dim = dim; b.H = pl->H; b.ngroups = hb.ngroups; b.nsplit = hb.nsplit; b.side = d_side;
-            int2 *d_rowtab; int *d_bm, *d_mpz, *d_nmpz, *d_ntile, *d_mlo, *d_mhi, *d_bgoff, *d_qoff, *d_brbase, *d_bgen;
+            b.order = order; b.dim = dim; b.H = pl->H; b.ngroups = hb.ngroups; b.nsplit = hb.nsplit;
+            b.nrad = hb.nrad; b.nq = hb.nq;
+            int2 *d_rowtab; int *d_bm, *d_mpz, *d_nmpz, *d_ntile, *d_qlo, *d_qlen, *d_bgoff, *d_qoff, *d_brbase;
             float4 *d_bgd, *d_brk;
             UP(hb.rowtab, d_rowtab) UP(hb.tile_mpz, d_bm) UP(hb.mpz, d_mpz) UP(hb.nmpz, d_nmpz) UP(hb.ntile, d_ntile)
-            UP(hb.mlo, d_mlo) UP(hb.mhi, d_mhi) UP(hb.goff, d_bgoff) UP(hb.qoff, d_qoff) UP(hb.rbase, d_brbase)
-            UP(hb.gen_tasks, d_bgen) UP(hb.gd, d_bgd) UP(hb.rk, d_brk) UP(hb.rowmap, pl->d_rowmap)
-            b.rowtab = d_rowtab; b.tile_mpz = d_bm; b.mpz = d_mpz; b.nmpz = d_nmpz; b.ntile = d_ntile; b.mlo = d_mlo; b.mhi = d_mhi;
-            b.goff = d_bgoff; b.qoff = d_qoff; b.rbase = d_brbase; b.gen_tasks = d_bgen; b.gd = d_bgd; b.rk = d_brk;
+            UP(hb.qlo, d_qlo) UP(hb.qlen, d_qlen) UP(hb.goff, d_bgoff) UP(hb.qoff, d_qoff) UP(hb.rbase, d_brbase)
+            UP(hb.gd, d_bgd) UP(hb.rk, d_brk) UP(hb.rowmap, pl->d_rowmap)
+            b.rowtab = d_rowtab; b.tile_mpz = d_bm; b.mpz = d_mpz; b.nmpz = d_nmpz; b.ntile = d_ntile;
+            b.qlo = d_qlo; b.qlen = d_qlen;
+            BasisArgs &a = pl->basis;
+            a.order = order; a.dim = dim; a.H = pl->H; a.nrad = hb.nrad; a.nq = hb.nq; a.side = d_side;
+            a.rk = d_brk; a.rbase = d_brbase; a.gd = d_bgd; a.goff = d_bgoff; a.qoff = d_qoff;
+            pl->b_chunks = (long long)analysis_items(0, pl->H, pl->H) * ((pl->H + KC - 1) / KC);
             pl->batched = true;
         }
     }
@@ -600,6 +591,9 @@ extern "C" int z3d_plan_destroy(z3d_plan *pl) {
     if (!pl) return Z3D_OK;
     cudaSetDevice(pl->device);
     for (void *p : pl->owned) cudaFree(p);
+    if (pl->d_Rt) cudaFree(pl->d_Rt);
+    if (pl->d_Qt) cudaFree(pl->d_Qt);
+    if (pl->d_trig) cudaFree(pl->d_trig);
     for (int i = 0; i < 2; ++i) {
         if (pl->d_stage_vol[i]) cudaFree(pl->d_stage_vol[i]);
         if (pl->d_stage_mom[i]) cudaFree(pl->d_stage_mom[i]);
@@ -637,8 +631,8 @@ static int decompose_group(const z3d_plan *pl) {
 }
 static size_t ws_decompose(const z3d_plan *pl, int batch) {
     size_t w = (size_t)std::min(batch, decompose_group(pl)) * pl->npass * pl->nsplit * SLOT_WORDS * sizeof(float);
-    if (pl->batched && batch >= pl->batched_min)
-        w = std::max(w, (size_t)pl->devb.ngroups * pl->devb.nsplit * BSLOT_WORDS * sizeof(float));
+    if (pl->batched && batch >= pl->batched_min)  // per-CTA partial sums + the folds of one tile of volumes
+        w = std::max(w, (size_t)pl->devb.ngroups * pl->devb.nsplit * BSLOT_WORDS * sizeof(float) + (size_t)pl->b_chunks * BF_BYTES);
     return w;
 }
 static size_t ws_reconstruct(const z3d_plan *pl, int batch) {
@@ -672,6 +666,34 @@ extern "C" int z3d_decompose_part(const z3d_plan *pl, const float *d_vol, int ba
     return decompose_impl(pl, d_vol, batch, 0, pl->H, part, nparts, d_moments, d_ws, ws_bytes, stream);
 }
 
+// Basis tables of the batched path (what is left of CalculatePolynomials, zm:2237-2323): built on the first batched
+// call, on that call's stream.  When device memory is short the plan silently keeps to the per-volume kernel.
+static int ensure_basis(z3d_plan *pl, cudaStream_t st) {
+    if (pl->basis_ready || !pl->batched) return Z3D_OK;
+    const size_t items = (size_t)analysis_items(0, pl->H, pl->H);
+    const size_t rb = (size_t)pl->b_chunks * pl->basis.nrad * KC * sizeof(float), qb = (size_t)pl->b_chunks * pl->basis.nq * KC * sizeof(float);
+    const size_t tb = items * 4 * (LMAX + 1) * sizeof(float);
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    if (rb + qb + tb > free_b / 2 || cudaMalloc((void **)&pl->d_Rt, rb) != cudaSuccess ||
+        cudaMalloc((void **)&pl->d_Qt, qb) != cudaSuccess || cudaMalloc((void **)&pl->d_trig, tb) != cudaSuccess) {
+        cudaGetLastError();
+        if (pl->d_Rt) cudaFree(pl->d_Rt);
+        if (pl->d_Qt) cudaFree(pl->d_Qt);
+        pl->d_Rt = pl->d_Qt = pl->d_trig = nullptr;
+        pl->batched = false;
+        return Z3D_OK;
+    }
+    pl->basis.Rt = pl->d_Rt; pl->basis.Qt = pl->d_Qt; pl->basis.trig = pl->d_trig;
+    pl->devb.Rt = pl->d_Rt; pl->devb.Qt = pl->d_Qt; pl->devb.trig = pl->d_trig;
+    CUDA_TRY(cudaMemsetAsync(pl->d_trig, 0, tb, st));
+    k_build_basis<<<(unsigned)pl->b_chunks, 1024, 0, st>>>(pl->basis);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    pl->basis_ready = true;
+    return Z3D_OK;
+}
+
 static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int half_lo, int half_hi, int part, int nparts,
                           float *d_moments, void *d_ws, size_t ws_bytes, void *stream) {
     int rc = check_range(pl, batch, half_lo, half_hi, "z3d_decompose");
@@ -690,18 +712,25 @@ static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int
     int done = 0;
     // batches: tiles of up to BNV volumes through the batched kernel (whole-volume calls only); what is left below
     // the threshold goes through the per-volume kernel
+    if (pl->batched && half_lo == 0 && half_hi == pl->H && batch >= pl->batched_min) {
+        rc = ensure_basis(mpl, st);
+        if (rc) return rc;
+    }
     while (pl->batched && half_lo == 0 && half_hi == pl->H && batch - done >= pl->batched_min) {
         const int nb = std::min(BNV, batch - done);
         const float *vol = d_vol + (size_t)done * N3;
+        float *folds = partial + (size_t)pl->devb.ngroups * pl->devb.nsplit * BSLOT_WORDS;
+        k_fold_tile<<<(unsigned)pl->b_chunks, 2 * BNV * KC, 0, st>>>(vol, nb, pl->dim, pl->H, folds);
+        CUDA_TRY(cudaGetLastError());
         const bool timed = pl->profiling && mpl->n_timed < z3d_plan::MAX_TIMED;
         if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t0[mpl->n_timed], st));
-        k_decompose_batched<<<pl->devb.ngroups * pl->devb.nsplit, BNT, pl->b_smem, st>>>(pl->devb, vol, nb, part, nparts, partial);
+        k_decompose_batched<<<pl->devb.ngroups * pl->devb.nsplit, BNT, pl->b_smem, st>>>(pl->devb, folds, part, nparts, partial);
         CUDA_TRY(cudaGetLastError());
         if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t1[mpl->n_timed++], st));
         k_reduce_batched<<<(pl->nmom * BCOL + 255) / 256, 256, 0, st>>>(partial, pl->d_rowmap, pl->d_scale, pl->nmom,
                                                                        pl->devb.nsplit, nb, d_moments + (size_t)done * 2 * pl->nmom);
         CUDA_TRY(cudaGetLastError());
-        g_launches += 2;
+        g_launches += 3;
         done += nb;
     }
     for (int b0 = done; b0 < batch; b0 += grp) {
