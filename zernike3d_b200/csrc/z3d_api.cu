@@ -555,12 +555,13 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
     {
         HostPlanB hb;
         build_batched_plan(order, prop.multiProcessorCount, hp, hb);
-        pl->b_smem = batched_smem_bytes(hb.nrad);
+        const bool adouble = (size_t)batched_smem_bytes(hb.nrad, true) <= prop.sharedMemPerBlockOptin;
+        pl->b_smem = batched_smem_bytes(hb.nrad, adouble);
         // dim >= 14 keeps every 8-voxel chunk and its z-mirror inside a row (k_fold_tile reads both)
         if (hb.ok && dim >= 14 && (size_t)pl->b_smem <= prop.sharedMemPerBlockOptin) {
             DevPlanB &b = pl->devb;
             b.order = order; b.dim = dim; b.H = pl->H; b.ngroups = hb.ngroups; b.nsplit = hb.nsplit;
-            b.nrad = hb.nrad; b.nq = hb.nq;
+            b.nrad = hb.nrad; b.nq = hb.nq; b.adouble = adouble;
             int2 *d_rowtab; int *d_bm, *d_mpz, *d_nmpz, *d_ntile, *d_qlo, *d_qlen, *d_bgoff, *d_qoff, *d_brbase;
             float4 *d_bgd, *d_brk;
             UP(hb.rowtab, d_rowtab) UP(hb.tile_mpz, d_bm) UP(hb.mpz, d_mpz) UP(hb.nmpz, d_nmpz) UP(hb.ntile, d_ntile)

@@ -43,22 +43,25 @@ constexpr int BF_BYTES = 16 * BNV * KC * 4;       // folds of one chunk: [set 2]
 
 constexpr int BOFF_THI = 0;                                      // T panels, TF32 high part   [2 k-halves][BROWS_MAX][4]
 constexpr int BOFF_TLO = BOFF_THI + 2 * BROWS_MAX * 16;          //           float32 remainder
-constexpr int BOFF_AHI = BOFF_TLO + 2 * BROWS_MAX * 16;          // a panels  [BMPZ_MAX][2 k-halves][BCOL][4]
-constexpr int BOFF_ALO = BOFF_AHI + BMPZ_MAX * 2 * BCOL * 16;
-constexpr int BOFF_ROWTAB = BOFF_ALO + BMPZ_MAX * 2 * BCOL * 16; // (R index, Q index in the slice) per row [BROWS_MAX] ushort2
+constexpr int BOFF_ROWTAB = BOFF_TLO + 2 * BROWS_MAX * 16;       // (R index, Q index in the slice) per row [BROWS_MAX] ushort2
 constexpr int BOFF_TABS = BOFF_ROWTAB + BROWS_MAX * 4;           // mpz, tile_mpz [2][BTILES]
 constexpr int BOFF_MBAR = BOFF_TABS + 2 * BTILES * 4;            // mbarriers: full[2], mma; tensor-memory base address
-constexpr int BOFF_STAGE = (BOFF_MBAR + 32 + 127) / 128 * 128;                     // 2 x [F | R (nrad + 1 entries) | Q slice]
-static_assert(BOFF_TLO % 128 == 0 && BOFF_AHI % 128 == 0 && BOFF_ALO % 128 == 0 && BOFF_MBAR % 8 == 0 && BOFF_STAGE % 128 == 0,
-              "smem alignment");
-// stage: F, then R with one extra all-zero entry (padding rows point at it), then the Q slice
+constexpr int BOFF_A = (BOFF_MBAR + 32 + 127) / 128 * 128;       // a panels [1 or 2 buffers][hi | lo][BMPZ_MAX][2 k-halves][BCOL][4],
+                                                                 // then 2 copy stages [F | R (nrad + 4 entries) | Q slice]
+constexpr int BA_WORDS = BMPZ_MAX * 2 * BCOL * 4;                // one a panel set (hi or lo)
+static_assert(BOFF_TLO % 128 == 0 && BOFF_MBAR % 8 == 0 && BOFF_A % 128 == 0 && (BA_WORDS * 4) % 128 == 0, "smem alignment");
+// stage: F, then R with extra all-zero entries (padding rows point at the first), then the Q slice
 __host__ __device__ inline int batched_stage_bytes(int nrad) { return BF_BYTES + (nrad + 4) * 32 + BQ_MAX * 32; }
-__host__ __device__ inline int batched_smem_bytes(int nrad) { return BOFF_STAGE + 2 * batched_stage_bytes(nrad); }
+__host__ __device__ inline int batched_smem_bytes(int nrad, bool adouble) {
+    return BOFF_A + 2 * BA_WORDS * 4 * (adouble ? 2 : 1) + 2 * batched_stage_bytes(nrad);
+}
 
 struct DevPlanB {
     int order, dim, H;
     int ngroups, nsplit;
     int nrad, nq;            // entries per chunk of the R and Q tables
+    int adouble;             // 1: two a-panel buffers fit in shared memory (the a panels of a chunk are then produced while the
+                             //    previous chunk's MMAs run)
     const int2 *rowtab;      // [ngroups][BROWS_MAX]   (R index, Q index relative to the group's slice); padding -> zero entry
     const int *tile_mpz;     // [ngroups][BTILES]      a-panel index of each tile
     const int *mpz;          // [ngroups][BMPZ_MAX]    m | pz << 16 of each a panel, -1 padded
@@ -272,9 +275,9 @@ struct CtxB {
     const ushort2 *rowtab;
     const int *mpz, *tile_mpz;
 };
-__device__ __forceinline__ void products(const CtxB &c, const float *stage, int nrad, int qlo, int nmpz, const float *__restrict__ trig) {
+__device__ __forceinline__ void t_products(const CtxB &c, const float *stage, int nrad, int qlo) {
     const int tid = threadIdx.x;
-    const float *Fs = stage, *Rs = stage + BF_BYTES / 4, *Qs = Rs + (nrad + 4) * KC;
+    const float *Rs = stage + BF_BYTES / 4, *Qs = Rs + (nrad + 4) * KC;
 #pragma unroll
     for (int h = 0; h < BROWS_MAX / BNT; ++h) {
         const int row = tid + h * BNT;
@@ -293,6 +296,10 @@ __device__ __forceinline__ void products(const CtxB &c, const float *stage, int 
         *reinterpret_cast<float4 *>(c.Tlo + row * 4) = l0;
         *reinterpret_cast<float4 *>(c.Tlo + (BROWS_MAX + row) * 4) = l1;
     }
+}
+__device__ __forceinline__ void a_products(const CtxB &c, const float *stage, int nmpz, const float *__restrict__ trig) {
+    const int tid = threadIdx.x;
+    const float *Fs = stage;
     for (int it = tid; it < nmpz * (2 * BNV); it += BNT) {  // (panel, re / im, volume)
         const int b = it & (BNV - 1), reim = (it >> 5) & 1, j = it >> 6;
         const int code = c.mpz[j], m = code & 0xffff, pz = code >> 16;
@@ -369,8 +376,6 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
     CtxB c;
     c.Thi = reinterpret_cast<float *>(smem + BOFF_THI);
     c.Tlo = reinterpret_cast<float *>(smem + BOFF_TLO);
-    c.Ahi = reinterpret_cast<float *>(smem + BOFF_AHI);
-    c.Alo = reinterpret_cast<float *>(smem + BOFF_ALO);
     ushort2 *rowtab = reinterpret_cast<ushort2 *>(smem + BOFF_ROWTAB);
     int *mpz = reinterpret_cast<int *>(smem + BOFF_TABS), *tile_mpz = mpz + BTILES;
     c.rowtab = rowtab;
@@ -379,7 +384,9 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + BOFF_MBAR);
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + BOFF_MBAR + 24);
     const int stage_bytes = batched_stage_bytes(nrad);
-    unsigned char *stage0 = smem + BOFF_STAGE;
+    const int adouble = P.adouble;
+    float *abase = reinterpret_cast<float *>(smem + BOFF_A);
+    unsigned char *stage0 = smem + BOFF_A + 2 * BA_WORDS * 4 * (adouble ? 2 : 1);
     // ---- tables of this row group -> smem; zero the panels and the stages (padding rows read the zero R entry)
     for (int i = tid; i < BTILES; i += BNT) {
         mpz[i] = P.mpz[grp * BMPZ_MAX + i];
@@ -390,7 +397,7 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
         rowtab[i] = make_ushort2((unsigned short)rq.x, (unsigned short)rq.y);
     }
     for (int i = tid; i < BOFF_ROWTAB / 4; i += BNT) reinterpret_cast<float *>(smem)[i] = 0.0f;
-    for (int i = tid; i < 2 * stage_bytes / 4; i += BNT) reinterpret_cast<float *>(stage0)[i] = 0.0f;
+    for (int i = tid; i < (int)(stage0 + 2 * stage_bytes - smem - BOFF_A) / 4; i += BNT) abase[i] = 0.0f;
     const int nmpz = P.nmpz[grp], ntile = P.ntile[grp], qlo = P.qlo[grp], qlen = P.qlen[grp];
     const unsigned full0 = smem_u32(bars), mbar = smem_u32(bars + 2);
     if (tid == 0) {
@@ -436,6 +443,10 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
         const int s = t & 1;
         const float *stage = reinterpret_cast<const float *>(stage0 + (size_t)s * stage_bytes);
         mbar_wait(full0 + 8 * s, (t >> 1) & 1);  // this chunk's F, R, Q have landed
+        c.Ahi = abase + (adouble ? (int)(t & 1) * 2 * BA_WORDS : 0);
+        c.Alo = c.Ahi + BA_WORDS;
+        const float *trig = P.trig + (size_t)(cc / CPR) * 4 * (LMAX + 1);
+        if (adouble) a_products(c, stage, nmpz, trig);  // into the other buffer, while the previous chunk's MMAs run
         if (t) {  // the previous chunk's MMAs have retired: the operand panels are free, the accumulators current
             mbar_wait(mbar, (t - 1) & 1);
             tc_fence_after();
@@ -446,7 +457,8 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
             since_flush = 0;
             tc_fence_before();
         }
-        products(c, stage, nrad, qlo, nmpz, P.trig + (size_t)(cc / CPR) * 4 * (LMAX + 1));
+        if (!adouble) a_products(c, stage, nmpz, trig);
+        t_products(c, stage, nrad, qlo);
         fence_async_smem();  // generic-proxy panel writes -> visible to the tensor core's async-proxy reads
         __syncthreads();     // panels complete; everybody is done reading stage s
         if (tid == 0) {
