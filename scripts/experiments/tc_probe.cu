@@ -121,7 +121,66 @@ __global__ void __launch_bounds__(128, 1) probe(const float *A, const float *B, 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tbase));
 }
 
+
+// timing: `tiles` x 3 MMAs (M=128, N=ncol, K=8) issued back to back by one thread, clocks from first issue to mbarrier completion
+__global__ void __launch_bounds__(128, 1) mma_time(int tiles, int ncol, int reps, long long *clk) {
+    extern __shared__ __align__(128) float sm[];
+    float *sA = sm, *sB = sm + 2 * 8 * 2 * 128 * 4;   // A: up to 8 tiles hi/lo ... reuse same data
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 2 * 8 * 2 * 128 * 4 + 2 * 8 * 2 * 256 * 4; i += 128) sm[i] = 1.0f;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tbase = tmem_base;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (((uint32_t)ncol >> 3) << 17) | ((128u >> 4) << 24);
+    long long best = 1ll << 60;
+    for (int r = 0; r < reps; ++r) {
+        long long t0 = 0;
+        if (tid == 0) {
+            t0 = clock64();
+            for (int t = 0; t < tiles; ++t) {
+                const uint64_t dA = make_desc(smem_u32(sA + t * 128 * 4), 8 * 128 * 16, 128);
+                const uint64_t dA2 = make_desc(smem_u32(sA + 8 * 2 * 128 * 4 + t * 128 * 4), 8 * 128 * 16, 128);
+                const uint64_t dB = make_desc(smem_u32(sB), ncol * 16, 128), dB2 = make_desc(smem_u32(sB + 8 * 2 * 256 * 4), ncol * 16, 128);
+                const uint32_t d = tbase + (t * ncol) % 512;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(dA2), "l"(dB), "r"(idesc), "r"(0u) : "memory");
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(dA), "l"(dB2), "r"(idesc), "r"(1u) : "memory");
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(dA), "l"(dB), "r"(idesc), "r"(1u) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+        }
+        mbar_wait(smem_u32(&mbar), r & 1);
+        if (tid == 0) { long long dt = clock64() - t0; if (dt < best) best = dt; }
+        __syncthreads();
+    }
+    if (tid == 0) *clk = best;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
+}
+
 int main() {
+    {
+        long long *dclk; cudaMalloc(&dclk, 8);
+        const int smem = (2 * 8 * 2 * 128 * 4 + 2 * 8 * 2 * 256 * 4) * 4;
+        cudaFuncSetAttribute(mma_time, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        for (int ncol : {64, 128, 256}) for (int tiles : {1, 2, 4, 8}) {
+            mma_time<<<1, 128, smem>>>(tiles, ncol, 5, dclk);
+            cudaError_t e = cudaDeviceSynchronize(); long long c = 0; cudaMemcpy(&c, dclk, 8, cudaMemcpyDeviceToHost);
+            printf("mma_time N=%d tiles=%d (%d MMAs): %lld clk  (%s)\n", ncol, tiles, 3 * tiles, c, cudaGetErrorString(e));
+        }
+    }
     std::vector<float> A(128 * 8), B(64 * 8), D(128 * 64);
     srand(1);
     for (auto &x : A) x = (float)rand() / RAND_MAX + 0.25f;   // positive: accumulation grows monotonically (worst case for RZ)

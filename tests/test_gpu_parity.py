@@ -16,6 +16,9 @@ pytestmark = pytest.mark.gpu
 
 TOL_MOM, TOL_MAP, TOL_INV = 1e-5, 1e-5, 1e-6
 TOL_EXACT = 1.5e-6
+# batches take the tensor-core path (3xTF32 products, TMEM accumulators, basis tables): T = R*Q is rounded to float32
+# before the contraction, which costs a little against the float64 oracle (1.0e-6 at order 50, 1.4e-6 at order 60)
+TOL_EXACT_BATCHED = 2.0e-6
 
 
 @pytest.fixture(scope="module")
@@ -107,6 +110,72 @@ def test_3dva_bundle_batched(plans):
         assert rel_l2(moms[i], g["moments"][i]) < TOL_MOM
     one_by_one = np.stack([P.decompose(dev(v)).cpu().numpy() for v in vols])
     assert np.array_equal(moms, one_by_one)           # batching does not change a single bit
+
+
+BATCHED = [("d16_o10", 13), ("d15_o8", 12), ("d32_o20", 35), ("d20_o25", 45), ("c1_d64_o50", 32), ("c5_d96_o60", 16)]
+
+
+@pytest.mark.parametrize("name,count", BATCHED)
+def test_batched_tensor_core_path(plans, oracle_mod, name, count):
+    """Batches of >= info['batched_min'] volumes: k_fold_tile + basis tables + k_decompose_batched (tcgen05)."""
+    from zernike3d_b200.plan import launch_count
+
+    g = golden(name)
+    order, dim = int(g["order"]), int(g["dim"])
+    P = plans(order, dim)
+    info = P.info()
+    assert 0 < info["batched_min"] <= count and info["batched_tile_volumes"] == 32
+    seed0 = int(g["seeds"][0])
+    vols = np.stack([volume(seed0 + i, dim) for i in range(count)])
+    dv = dev(vols)
+    P.decompose(dv)                                           # first call also builds the basis tables
+    l0 = launch_count()
+    mb = P.decompose(dv)
+    tiles, tail = divmod(count, 32)
+    if tail >= info["batched_min"]:
+        tiles, tail = tiles + 1, 0
+    assert launch_count() - l0 >= 3 * tiles + (2 if tail else 0)  # fold + contraction + reduction per tile, then the tail
+    assert mb.shape == (count, P.num_moments) and mb.dtype == torch.complex64
+    assert torch.equal(torch.view_as_real(mb), torch.view_as_real(P.decompose(dv)))     # run-to-run bitwise
+    mb = mb.cpu().numpy()
+    assert np.isfinite(mb.view(np.float32)).all()
+    # volume 0 is the golden's volume: the reference's own numbers
+    assert rel_l2(mb[0], g["moments"][0]) < TOL_MOM
+    # every volume against the per-volume kernel (different summation order and arithmetic, same tables of coefficients)
+    for i in range(count):
+        one = P.decompose(dv[i]).cpu().numpy()
+        if i >= 32 * tiles:                                   # tail volumes took the per-volume kernel inside the batch
+            assert np.array_equal(mb[i], one)
+        else:
+            assert rel_l2(mb[i], one) < 2 * TOL_EXACT_BATCHED
+    # first and last volume of the first tile against the float64 oracle, moments and invariants
+    for i in ([0, min(count, 32) - 1] if dim <= 64 else []):
+        exact = oracle_mod.decompose(vols[i], order, oracle_mod.EXACT)
+        assert rel_l2(mb[i], exact) < TOL_EXACT_BATCHED
+        inv = P.invariants(dev(mb[i])).cpu().numpy()
+        assert rel_l2(inv, oracle_mod.invariants(exact, order)) < TOL_INV
+
+
+def test_batched_128_order50_headline(plans, oracle_mod):
+    """The bench configuration: 32 volumes of 128^3 at order 50 in one tile."""
+    order, dim = 50, 128
+    P = plans(order, dim)
+    g = golden("c3_d128_o50")
+    vols = np.stack([volume(int(g["seeds"][0]) + i, dim) for i in range(32)])
+    dv = dev(vols)
+    mb = P.decompose(dv).cpu().numpy()
+    assert rel_l2(mb[0], g["moments"][0]) < TOL_MOM
+    for i in (0, 31):
+        exact = oracle_mod.decompose(vols[i], order, oracle_mod.EXACT)         # ~2 s each on the host cores
+        assert rel_l2(mb[i], exact) < TOL_EXACT_BATCHED
+        inv = P.invariants(dev(mb[i])).cpu().numpy()
+        assert rel_l2(inv, oracle_mod.invariants(exact, order)) < TOL_INV
+    # work parts of a batch are additive (multi-GPU work sharding of replicated volumes), linearity in the volumes
+    parts = sum(P.decompose(dv, part=(r, 3)) for r in range(3)).cpu().numpy()
+    assert rel_l2(parts, mb) < 1e-6
+    mix = (0.5 * dv[:16] - 2.0 * dv[16:]).contiguous()
+    lin = P.decompose(torch.cat([mix, mix])).cpu().numpy()[:16]
+    assert rel_l2(lin, 0.5 * mb[:16] - 2.0 * mb[16:]) < 2e-6
 
 
 def test_slab_partials_are_additive_and_only_read_their_planes(plans):
@@ -215,6 +284,12 @@ def test_host_buffer_api_matches_device_api(plans):
     rh = P.reconstruct_host(mh)
     rd = P.reconstruct(dev(mh)).cpu().numpy()
     assert np.array_equal(rh, rd)
+    # a batch large enough for the tensor-core tiles: the host call stages 32 volumes at a time
+    P = plans(20, 32)
+    vols = np.stack([volume(s, 32) for s in range(40)])
+    mh = P.decompose_host(torch.from_numpy(vols).pin_memory())
+    md = P.decompose(dev(vols)).cpu().numpy()
+    assert np.array_equal(mh, md)
 
 
 def test_error_paths(plans):

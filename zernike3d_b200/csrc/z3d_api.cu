@@ -65,7 +65,7 @@ struct z3d_plan {
     DevPlan dev{};
     // batched analysis kernel (tiles of BNV volumes); absent when the order does not fit its fixed layout
     bool batched = false;
-    int batched_min = 8;         // smallest (remaining) batch that is routed to the batched kernel
+    int batched_min = 12;        // smallest (remaining) batch that is routed to the batched kernel
     DevPlanB devb{};
     int2 *d_rowmap = nullptr;
     int b_smem = 0;
@@ -834,8 +834,15 @@ static int ensure_staging(z3d_plan *pl) {
     if (pl->s_copy) return Z3D_OK;
     CUDA_TRY(cudaSetDevice(pl->device));
     const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
-    // group size: ~32 MiB of volume data per stage, at least 1 volume, at most 32
+    // group size: one tile of the batched kernel (32 volumes) when that path exists and a sixteenth of the free device
+    // memory holds the two stages; otherwise ~32 MiB of volume data per stage, at least 1 volume
     int gb = (int)std::min<size_t>(32, std::max<size_t>(1, ((size_t)32 << 20) / (N3 * sizeof(float))));
+    if (pl->batched) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = 2 * ((size_t)BNV * N3 * sizeof(float) + z3d_workspace_bytes(pl, BNV));
+        if (need <= free_b / 16) gb = BNV;
+    }
     pl->stage_batch = gb;
     CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_comp, cudaStreamNonBlocking));
@@ -1025,6 +1032,11 @@ extern "C" int z3d_decompose_allreduce(const z3d_plan *pl, z3d_comm *c, const fl
     CUDA_TRY(cudaSetDevice(pl->device));
     cudaStream_t st = (cudaStream_t)stream;
     float *partial = (float *)d_ws;
+    dim3 g((2 * pl->nmom + 255) / 256, batch);
+    // every block of the exchange kernel waits for the peers, so all of them must be co-resident
+    if ((int)(g.x * g.y) > pl->num_sms * 4)
+        return fail(Z3D_ERR_UNSUPPORTED, "z3d_decompose_allreduce: batch %d too large for the one-shot exchange (use "
+                                         "z3d_decompose_part + a library all-reduce)", batch);
     const_cast<z3d_plan *>(pl)->last_was_decompose = false;
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
     if (pl->npass == 2)
@@ -1033,11 +1045,6 @@ extern "C" int z3d_decompose_allreduce(const z3d_plan *pl, z3d_comm *c, const fl
         k_decompose<0><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, 0, pl->H, c->rank, c->world, partial);
     CUDA_TRY(cudaGetLastError());
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k1, st));
-    dim3 g((2 * pl->nmom + 255) / 256, batch);
-    // every block of the exchange kernel waits for the peers, so all of them must be co-resident
-    if ((int)(g.x * g.y) > pl->num_sms * 4)
-        return fail(Z3D_ERR_UNSUPPORTED, "z3d_decompose_allreduce: batch %d too large for the one-shot exchange (use "
-                                         "z3d_decompose_part + a library all-reduce)", batch);
     c->epoch += 1;
     k_reduce_allreduce_p2p<<<g, 256, 0, st>>>(partial, pl->d_src, pl->d_scale, pl->nmom, pl->npass, pl->nsplit, batch, c->peers,
                                               c->rank, c->world, c->max_elems, c->epoch, c->d_done, c->d_err, d_moments);

@@ -92,6 +92,8 @@ class ZernikeSpherical:
         import torch
 
         v = np.ascontiguousarray(np.asarray(volume), dtype=np.float32)
+        if not v.flags.writeable:  # memory-mapped MRC data: torch wants a writable source even for a copy
+            v = v.copy()
         return torch.from_numpy(v).to(f"cuda:{self.plan.device}")
 
     def Decompose(self, volume, dim, jobs):
