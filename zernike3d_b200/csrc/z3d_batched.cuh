@@ -280,27 +280,32 @@ struct CtxB {
     const ushort2 *rowtab;
     const int *mpz, *tile_mpz;
 };
-__device__ __forceinline__ void t_products(const CtxB &c, const float *stage, int nrad, int qlo) {
-    const int tid = threadIdx.x;
+// T row = R * Q of this thread's row: loads, products and the TF32 split (registers only) ...
+struct TRow {
+    float4 h0, h1, l0, l1;
+};
+__device__ __forceinline__ TRow t_compute(const CtxB &c, const float *stage, int nrad, int qlo) {
+    static_assert(BROWS_MAX == BNT, "one row per thread");
     const float *Rs = stage + BF_BYTES / 4, *Qs = Rs + (nrad + 4) * KC;
-#pragma unroll
-    for (int h = 0; h < BROWS_MAX / BNT; ++h) {
-        const int row = tid + h * BNT;
-        const ushort2 rq = c.rowtab[row];
-        const float *rp = Rs + rq.x * KC, *qp = Qs + rq.y * KC;
-        const int sr = ((rq.x >> 2) & 1) << 2, sq = (((rq.y + qlo) >> 2) & 1) << 2;  // the tables' k-half swizzle
-        const float4 r0 = *reinterpret_cast<const float4 *>(rp + sr), r1 = *reinterpret_cast<const float4 *>(rp + (4 ^ sr));
-        const float4 q0 = *reinterpret_cast<const float4 *>(qp + sq), q1 = *reinterpret_cast<const float4 *>(qp + (4 ^ sq));
-        float4 h0, l0, h1, l1;
-        split_tf32(r0.x * q0.x, h0.x, l0.x); split_tf32(r0.y * q0.y, h0.y, l0.y);
-        split_tf32(r0.z * q0.z, h0.z, l0.z); split_tf32(r0.w * q0.w, h0.w, l0.w);
-        split_tf32(r1.x * q1.x, h1.x, l1.x); split_tf32(r1.y * q1.y, h1.y, l1.y);
-        split_tf32(r1.z * q1.z, h1.z, l1.z); split_tf32(r1.w * q1.w, h1.w, l1.w);
-        *reinterpret_cast<float4 *>(c.Thi + row * 4) = h0;
-        *reinterpret_cast<float4 *>(c.Thi + (BROWS_MAX + row) * 4) = h1;
-        *reinterpret_cast<float4 *>(c.Tlo + row * 4) = l0;
-        *reinterpret_cast<float4 *>(c.Tlo + (BROWS_MAX + row) * 4) = l1;
-    }
+    const ushort2 rq = c.rowtab[threadIdx.x];
+    const float *rp = Rs + rq.x * KC, *qp = Qs + rq.y * KC;
+    const int sr = ((rq.x >> 2) & 1) << 2, sq = (((rq.y + qlo) >> 2) & 1) << 2;  // the tables' k-half swizzle
+    const float4 r0 = *reinterpret_cast<const float4 *>(rp + sr), r1 = *reinterpret_cast<const float4 *>(rp + (4 ^ sr));
+    const float4 q0 = *reinterpret_cast<const float4 *>(qp + sq), q1 = *reinterpret_cast<const float4 *>(qp + (4 ^ sq));
+    TRow t;
+    split_tf32(r0.x * q0.x, t.h0.x, t.l0.x); split_tf32(r0.y * q0.y, t.h0.y, t.l0.y);
+    split_tf32(r0.z * q0.z, t.h0.z, t.l0.z); split_tf32(r0.w * q0.w, t.h0.w, t.l0.w);
+    split_tf32(r1.x * q1.x, t.h1.x, t.l1.x); split_tf32(r1.y * q1.y, t.h1.y, t.l1.y);
+    split_tf32(r1.z * q1.z, t.h1.z, t.l1.z); split_tf32(r1.w * q1.w, t.h1.w, t.l1.w);
+    return t;
+}
+// ... and its four 16-byte stores into the operand panels, once the previous chunk's MMAs have released them
+__device__ __forceinline__ void t_store(const CtxB &c, const TRow &t) {
+    const int row = threadIdx.x;
+    *reinterpret_cast<float4 *>(c.Thi + row * 4) = t.h0;
+    *reinterpret_cast<float4 *>(c.Thi + (BROWS_MAX + row) * 4) = t.h1;
+    *reinterpret_cast<float4 *>(c.Tlo + row * 4) = t.l0;
+    *reinterpret_cast<float4 *>(c.Tlo + (BROWS_MAX + row) * 4) = t.l1;
 }
 __device__ __forceinline__ void a_products(const CtxB &c, const float *stage, int nmpz, const float *__restrict__ trig) {
     const int tid = threadIdx.x;
@@ -452,7 +457,10 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
         c.Ahi = abase + (adouble ? (int)(t & 1) * 2 * BA_WORDS : 0);
         c.Alo = c.Ahi + BA_WORDS;
         const float *trig = P.trig + (size_t)(cc / CPR) * 4 * (LMAX + 1);
-        if (adouble) a_products(c, stage, nmpz, trig);  // into the other buffer, while the previous chunk's MMAs run
+        // everything that does not touch the panels the previous chunk's MMAs are still reading comes first: the a panels
+        // (other buffer) and the T products, which stay in registers until the MMAs have retired
+        if (adouble) a_products(c, stage, nmpz, trig);
+        const TRow trow = t_compute(c, stage, nrad, qlo);
         if (t) {  // the previous chunk's MMAs have retired: the operand panels are free, the accumulators current
             mbar_wait(mbar, (t - 1) & 1);
             tc_fence_after();
@@ -464,7 +472,7 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
             tc_fence_before();
         }
         if (!adouble) a_products(c, stage, nmpz, trig);
-        t_products(c, stage, nrad, qlo);
+        t_store(c, trow);
         fence_async_smem();  // generic-proxy panel writes -> visible to the tensor core's async-proxy reads
         __syncthreads();     // panels complete; everybody is done reading stage s
         if (tid == 0) {
