@@ -160,6 +160,7 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device - zernike3d_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
     def barrier():
