@@ -30,6 +30,7 @@ namespace z3d {
 
 constexpr int BNT = 1024;           // threads per CTA of the contraction kernel (32 producer warps, accumulators in TMEM)
 constexpr int BNWARP = BNT / 32;
+constexpr int BNPROD = BNT - 32;     // producer threads: the last warp only issues the MMAs and the bulk copies
 constexpr int BNV = 32;             // volumes per batch tile
 constexpr int BCOL = 2 * BNV;       // GEMM columns: [re | im][volume]
 constexpr int BTM = 128;            // rows of an MMA tile (UMMA M)
@@ -284,10 +285,9 @@ struct CtxB {
 struct TRow {
     float4 h0, h1, l0, l1;
 };
-__device__ __forceinline__ TRow t_compute(const CtxB &c, const float *stage, int nrad, int qlo) {
-    static_assert(BROWS_MAX == BNT, "one row per thread");
+__device__ __forceinline__ TRow t_compute(const CtxB &c, const float *stage, int nrad, int qlo, int row) {
     const float *Rs = stage + BF_BYTES / 4, *Qs = Rs + (nrad + 4) * KC;
-    const ushort2 rq = c.rowtab[threadIdx.x];
+    const ushort2 rq = c.rowtab[row];
     const float *rp = Rs + rq.x * KC, *qp = Qs + rq.y * KC;
     const int sr = ((rq.x >> 2) & 1) << 2, sq = (((rq.y + qlo) >> 2) & 1) << 2;  // the tables' k-half swizzle
     const float4 r0 = *reinterpret_cast<const float4 *>(rp + sr), r1 = *reinterpret_cast<const float4 *>(rp + (4 ^ sr));
@@ -300,8 +300,7 @@ __device__ __forceinline__ TRow t_compute(const CtxB &c, const float *stage, int
     return t;
 }
 // ... and its four 16-byte stores into the operand panels, once the previous chunk's MMAs have released them
-__device__ __forceinline__ void t_store(const CtxB &c, const TRow &t) {
-    const int row = threadIdx.x;
+__device__ __forceinline__ void t_store(const CtxB &c, const TRow &t, int row) {
     *reinterpret_cast<float4 *>(c.Thi + row * 4) = t.h0;
     *reinterpret_cast<float4 *>(c.Thi + (BROWS_MAX + row) * 4) = t.h1;
     *reinterpret_cast<float4 *>(c.Tlo + row * 4) = t.l0;
@@ -310,7 +309,7 @@ __device__ __forceinline__ void t_store(const CtxB &c, const TRow &t) {
 __device__ __forceinline__ void a_products(const CtxB &c, const float *stage, int nmpz, const float *__restrict__ trig) {
     const int tid = threadIdx.x;
     const float *Fs = stage;
-    for (int it = tid; it < nmpz * (2 * BNV); it += BNT) {  // (panel, re / im, volume)
+    for (int it = tid; it < nmpz * (2 * BNV); it += BNPROD) {  // (panel, re / im, volume); producer threads only
         const int b = it & (BNV - 1), reim = (it >> 5) & 1, j = it >> 6;
         const int code = c.mpz[j], m = code & 0xffff, pz = code >> 16;
         const int comb = (reim << 2) | (((m & 1) ^ reim) << 1) | pz;
@@ -443,7 +442,7 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
         bulk_copy(st + BF_BYTES, P.Rt + (size_t)cc * nrad * KC, rbytes, bar);
         bulk_copy(st + BF_BYTES + (nrad + 4) * 32, P.Qt + ((size_t)cc * P.nq + qlo) * KC, qbytes, bar);
     };
-    if (tid == 0) {
+    if (tid == BNPROD) {
         if (cbeg < cend) issue_copies(cbeg, 0);
         if (cbeg + 1 < cend) issue_copies(cbeg + 1, 1);
     }
@@ -458,9 +457,15 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
         c.Alo = c.Ahi + BA_WORDS;
         const float *trig = P.trig + (size_t)(cc / CPR) * 4 * (LMAX + 1);
         // everything that does not touch the panels the previous chunk's MMAs are still reading comes first: the a panels
-        // (other buffer) and the T products, which stay in registers until the MMAs have retired
-        if (adouble) a_products(c, stage, nmpz, trig);
-        const TRow trow = t_compute(c, stage, nrad, qlo);
+        // (other buffer) and the T products, which stay in registers until the MMAs have retired.  Warps 0-30 produce
+        // (one row per thread, warp 0 also the last 32 rows); warp 31 only issues, so that the ~24 MMA issues and 3 copy
+        // descriptors per chunk do not delay a producer warp the whole block would then wait for at the barrier.
+        const bool producer = tid < BNPROD, two_rows = tid < BROWS_MAX - BNPROD;
+        TRow trow;
+        if (producer) {
+            if (adouble) a_products(c, stage, nmpz, trig);
+            trow = t_compute(c, stage, nrad, qlo, tid);
+        }
         if (t) {  // the previous chunk's MMAs have retired: the operand panels are free, the accumulators current
             mbar_wait(mbar, (t - 1) & 1);
             tc_fence_after();
@@ -471,11 +476,14 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
             since_flush = 0;
             tc_fence_before();
         }
-        if (!adouble) a_products(c, stage, nmpz, trig);
-        t_store(c, trow);
+        if (producer) {
+            if (!adouble) a_products(c, stage, nmpz, trig);
+            t_store(c, trow, tid);
+            if (two_rows) t_store(c, t_compute(c, stage, nrad, qlo, BNPROD + tid), BNPROD + tid);
+        }
         fence_async_smem();  // generic-proxy panel writes -> visible to the tensor core's async-proxy reads
         __syncthreads();     // panels complete; everybody is done reading stage s
-        if (tid == 0) {
+        if (tid == BNPROD) {
             tc_fence_after();
             issue_mma(c, tmem, ntile, since_flush > 0, mbar);
             if (cc + 2 < cend) issue_copies(cc + 2, s);
