@@ -11,8 +11,9 @@
 // split into a TF32-exact high part and a float32 remainder and three products are issued per tile (lo.hi, hi.lo, hi.hi:
 // "3xTF32", relative product error 2^-21).  The tensor core adds into the accumulator with truncation (measured with
 // scripts/experiments/tc_probe.cu: about -3e-8 relative per accumulating instruction), so every BFLUSH_CHUNKS chunks the
-// accumulators are read back (tcgen05.ld) and added, round-to-nearest, into the CTA's float32 partial buffer (L2
-// resident) and the next product overwrites instead of accumulating.
+// accumulators are read back (tcgen05.ld), scaled by the inverse of the expected truncation loss and added,
+// round-to-nearest, into the CTA's float32 partial buffer (L2 resident); the next product overwrites instead of
+// accumulating.
 //
 // Three kernels:
 //   k_build_basis  (once per plan - this is what is left of the reference's CalculatePolynomials, zm:2237-2323): the
@@ -21,14 +22,14 @@
 //   k_fold_tile    (per tile of volumes): the 16 mirror / transpose images of every chunk -> F[chunk][16][volume][8];
 //   k_decompose_batched: a CTA owns a row group of <= 8 tiles of 128 rows (all 512 tensor-memory columns) and one split
 //                  of the chunk list.  Per chunk one thread issues three bulk copies (cp.async.bulk + mbarrier: F, R and
-//                  the row group's slice of Q) two chunks ahead; all warps turn them into the T and a operand panels
-//                  (K-major core-matrix layout of the shared-memory descriptors); one thread issues the MMAs.
+//                  the row group's slice of Q) two chunks ahead; 31 producer warps turn them into the T and a operand
+//                  panels (K-major core-matrix layout of the shared-memory descriptors); the same thread issues the MMAs.
 #pragma once
 #include "z3d_kernels.cuh"
 
 namespace z3d {
 
-constexpr int BNT = 1024;           // threads per CTA of the contraction kernel (32 producer warps, accumulators in TMEM)
+constexpr int BNT = 1024;           // threads per CTA of the contraction kernel (31 producer warps + 1 issuing warp; accumulators in TMEM)
 constexpr int BNWARP = BNT / 32;
 constexpr int BNPROD = BNT - 32;     // producer threads: the last warp only issues the MMAs and the bulk copies
 constexpr int BNV = 32;             // volumes per batch tile
