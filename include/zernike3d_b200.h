@@ -115,6 +115,13 @@ int z3d_reconstruct(const z3d_plan *plan, const float *d_moments /* [batch][num_
  * zm:62-76): d_invariants [batch][num_radial] float32 in sorted (n, l) order. */
 int z3d_invariants(const z3d_plan *plan, const float *d_moments, int batch, float *d_invariants, void *stream);
 
+/* 3DVA latent scaling on the device (replaces Moments.apply_scaling, zm:78-95, for many latent coordinates at once):
+ *   out[p][mu] = dims[0][mu] + sum_k latents[p][k] * dims[k + 1][mu],   p < npoints, k < ncomp
+ * d_dims [ncomp + 1][num_moments] complex64 (base map, then components: the .npz's arr_0..arr_K), d_latents [npoints][ncomp]
+ * float32 (rows of the .npz's `latents`), d_out [npoints][num_moments] complex64 - ready for z3d_reconstruct. */
+int z3d_scale_moments(const z3d_plan *plan, const float *d_dims, int ncomp, const float *d_latents, int npoints,
+                      float *d_out, void *stream);
+
 /* Host-buffer convenience calls: the same operations for callers that hold numpy / C arrays, the way
  * zm's Decompose(volume, ...) receives `mrc.data` and Reconstruct() returns a host map.  They stage
  * through pinned memory owned by the plan, overlap H2D copies with compute in chunks of volumes, and

@@ -178,6 +178,44 @@ def test_batched_128_order50_headline(plans, oracle_mod):
     assert rel_l2(lin, 0.5 * mb[:16] - 2.0 * mb[16:]) < 2e-6
 
 
+def test_latent_scaling_on_device_matches_apply_scaling(plans, tmp_path):
+    """z3d_scale_moments (+ ZernikeSpherical.ReconstructLatents) against Moments.apply_scaling (zm:78-95)."""
+    import argparse
+
+    from zernike3d_b200.moments import Moments
+    from zernike3d_b200.spherical import ZernikeSpherical
+
+    g = golden("3dva_d24_o12")
+    order, dim = int(g["order"]), int(g["dim"])
+    P = plans(order, dim)
+    dims, lat = np.asarray(g["moments"], np.complex64), np.asarray(g["latents"], np.float32)
+    got = P.scale_moments(dev(dims), dev(lat[:40])).cpu().numpy()
+    want = dims[0][None] + lat[:40] @ dims[1:]
+    assert got.shape == (40, P.num_moments) and rel_l2(got, want) < 1e-6
+    M = Moments(quiet=True)
+    for v in dims:
+        M.from_array(v)
+        M.add_dimension()
+    M.latents = lat
+    M.stats(quiet=True)
+    for z in (0, 7, 39):
+        assert rel_l2(got[z], M.apply_scaling(z_ind=z)) < 1e-6
+    with pytest.raises(ValueError):
+        P.scale_moments(dev(dims[:, :5]), dev(lat))
+    # maps at several latent coordinates, scaling and synthesis on the device
+    args = argparse.Namespace(order=order, output=str(tmp_path / "traj.mrc"), apix=None, gpu_id=0, z_ind=None, scales=None)
+    Z = ZernikeSpherical(args)
+    Z.dim, Z.moments = dim, M
+    jobs = Z.CalculatePolynomials()
+    maps = Z.ReconstructLatents(z_indices=[0, 7, 39], batch=2, write=False)
+    for i, z in enumerate((0, 7, 39)):
+        one = P.reconstruct(dev(M.apply_scaling(z_ind=z))).cpu().numpy()
+        assert rel_l2(maps[i], one) < 1e-6
+    names = Z.ReconstructLatents(latents=lat[:2])
+    assert [n.rsplit("_", 1)[1] for n in names] == ["p0.mrc", "p1.mrc"] and all(__import__("os").path.exists(n) for n in names)
+    assert len(jobs) == P.num_moments
+
+
 def test_slab_partials_are_additive_and_only_read_their_planes(plans):
     order, dim = 20, 32
     P = plans(order, dim)

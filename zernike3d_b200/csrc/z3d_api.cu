@@ -827,6 +827,20 @@ extern "C" int z3d_invariants(const z3d_plan *pl, const float *d_moments, int ba
     return Z3D_OK;
 }
 
+extern "C" int z3d_scale_moments(const z3d_plan *pl, const float *d_dims, int ncomp, const float *d_latents, int npoints,
+                                 float *d_out, void *stream) {
+    if (!pl || !d_dims || !d_out || ncomp < 0 || npoints < 1 || (ncomp > 0 && !d_latents))
+        return fail(Z3D_ERR_INVALID, "z3d_scale_moments: bad arguments");
+    if (npoints > 65535) return fail(Z3D_ERR_INVALID, "z3d_scale_moments: at most 65535 latent coordinates per call");
+    CUDA_TRY(cudaSetDevice(pl->device));
+    const int nelem = 2 * pl->nmom;
+    dim3 g((nelem + 255) / 256, npoints);
+    k_scale_moments<<<g, 256, 0, (cudaStream_t)stream>>>(d_dims, ncomp, d_latents, npoints, nelem, d_out);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    return Z3D_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-buffer calls: double-buffered groups of volumes, H2D on one stream, compute + D2H on another
 // ------------------------------------------------------------------------------------------------

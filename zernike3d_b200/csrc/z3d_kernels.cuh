@@ -888,6 +888,16 @@ __global__ void k_invariants(const float *__restrict__ moments, const int *__res
 }
 
 // FP32 FMA throughput probes for the roofline denominator
+// 3DVA latent scaling: out[p][e] = dims[0][e] + sum_k lat[p][k] * dims[k+1][e] over the 2 * nmom float components (zm:78-95)
+__global__ void k_scale_moments(const float *__restrict__ dims, int ncomp, const float *__restrict__ lat, int npoints, int nelem,
+                                float *__restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (e >= nelem || p >= npoints) return;
+    float acc = dims[e];
+    for (int k = 0; k < ncomp; ++k) acc = fmaf(__ldg(lat + (size_t)p * ncomp + k), dims[(size_t)(k + 1) * nelem + e], acc);
+    out[(size_t)p * nelem + e] = acc;
+}
+
 __global__ void k_fma_peak(int iters, float *out, int variant) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
     float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;

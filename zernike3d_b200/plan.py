@@ -139,6 +139,21 @@ class Plan:
                                            self._stream(stream)))
         return out[0] if single else out
 
+    def scale_moments(self, dims: torch.Tensor, latents: torch.Tensor, stream=None) -> torch.Tensor:
+        """3DVA latent scaling on the device (``Moments.apply_scaling``, zm:78-95, for many coordinates at once):
+        ``dims`` complex64 CUDA ``[K + 1, num_moments]`` (base map, components), ``latents`` float32 CUDA ``[P, K]`` ->
+        complex64 ``[P, num_moments]`` = base + latents @ components, ready for :meth:`reconstruct`."""
+        if dims.dtype != torch.complex64 or not dims.is_cuda or dims.dim() != 2 or dims.shape[1] != self.num_moments:
+            raise ValueError(f"expected complex64 CUDA [K+1,{self.num_moments}], got {dims.dtype} {tuple(dims.shape)}")
+        K = dims.shape[0] - 1
+        lat = latents.reshape(-1, K) if K else latents.reshape(latents.shape[0], 0)
+        if lat.dtype != torch.float32 or not lat.is_cuda:
+            raise ValueError("latents must be a float32 CUDA tensor [P, K]")
+        dims, lat = dims.contiguous(), lat.contiguous()
+        out = torch.empty((lat.shape[0], self.num_moments), dtype=torch.complex64, device=dims.device)
+        _lib.check(self._L.z3d_scale_moments(self._h, _ptr(dims), K, _ptr(lat), lat.shape[0], _ptr(out), self._stream(stream)))
+        return out
+
     def invariants(self, moments: torch.Tensor, stream=None) -> torch.Tensor:
         single = moments.dim() == 1
         m = (moments.unsqueeze(0) if single else moments).contiguous()

@@ -155,6 +155,45 @@ class ZernikeSpherical:
             out.append(name)
         return out
 
+    def ReconstructLatents(self, z_indices=None, latents=None, batch=8, write=True):
+        """Maps at MANY latent coordinates of a 3DVA bundle (trajectories / ensembles): the scaling
+        ``Omega = [1, z] . Omega_dims`` (zm:78-95) and the synthesis both run on the device, ``batch`` coordinates per
+        launch.  ``z_indices`` picks rows of the bundle's ``latents`` (file names ``<out>_scaled_<z>.mrc`` as zm:2708-2714
+        writes for a single ``--z_ind``); ``latents`` gives coordinates directly (``<out>_scaled_p<i>.mrc``).
+        Returns the file names (``write=True``) or the float32 maps ``[P, N, N, N]``."""
+        import torch
+
+        M = self.moments
+        dev = f"cuda:{self.plan.device}"
+        want = self.plan.num_moments
+        dims = M.as_matrix()
+        if dims.shape[1] < want:
+            raise ValueError(f"moment file holds {dims.shape[1]} moments, order {self.args.order} needs {want}")
+        dims = torch.from_numpy(np.ascontiguousarray(dims[:, :want]).astype(np.complex64)).to(dev)
+        if (z_indices is None) == (latents is None):
+            raise ValueError("give either z_indices= or latents=")
+        if z_indices is not None:
+            z_indices = [int(z) for z in z_indices]
+            coords = np.asarray(M.latents, dtype=np.float32)[z_indices]
+            tags = [str(z) for z in z_indices]
+        else:
+            coords = np.asarray(latents, dtype=np.float32).reshape(-1, dims.shape[0] - 1)
+            tags = [f"p{i}" for i in range(coords.shape[0])]
+        coords = torch.from_numpy(np.ascontiguousarray(coords)).to(dev)
+        stem = str(self.args.output).split(".")[0]
+        out = []
+        for b0 in range(0, coords.shape[0], batch):
+            moms = self.plan.scale_moments(dims, coords[b0:b0 + batch])
+            vols = self.plan.reconstruct(moms).cpu().numpy()
+            for tag, vol in zip(tags[b0:b0 + batch], vols):
+                if write:
+                    name = f"{stem}_scaled_{tag}.mrc"
+                    self.write_mrc_file(volume=vol, name=name)
+                    out.append(name)
+                else:
+                    out.append(vol)
+        return out if write else np.stack(out)
+
     def write_mrc_file(self, volume, name):
         mrc.write(name, np.array(volume, np.float32), 1 if self.args.apix is None else self.args.apix)
 
