@@ -161,7 +161,8 @@ int build_host_plan(int L, HostPlan &hp) {
     hp.L = L;
     int npass = 2;
     while (npass <= 64 && !layout_fits(L, npass)) npass += 2;
-    if (npass > 64) return fail(Z3D_ERR_UNSUPPORTED, "order %d too large for this build", L);
+    if (npass > 64)  // the Legendre coefficient table of a pass (GD_MAX entries of shared memory) holds orders up to 74
+        return fail(Z3D_ERR_UNSUPPORTED, "order %d too large for this build (orders 0..74 are supported)", L);
     hp.npass = npass;
     const int S = L + 1;
     hp.lpass.assign(S, 0);
