@@ -31,6 +31,22 @@ mom = zdist.decompose_slab_sharded(P.decompose, vols[0], P.half)
 ok &= rel(mom.cpu().numpy(), full[0].cpu().numpy()) < 5e-7
 rec = zdist.reconstruct_slab_sharded(P.reconstruct, full[0], P.half, gather=True)
 ok &= rel(rec.cpu().numpy(), P.reconstruct(full[0]).cpu().numpy()) < 1e-6
+# batches through the tensor-core tiles: work-sharded (every rank a part of every volume's chunk list, one all-reduce) and
+# volume-sharded (contiguous shares of independent volumes, gathered at the end)
+nb = 16
+bvols = torch.from_numpy(np.stack([volume(20 + i, dim) for i in range(nb)])).cuda()
+bfull = P.decompose(bvols)
+bws = zdist.decompose_work_sharded(P.decompose, bvols, deterministic=True)
+ok &= rel(bws.cpu().numpy(), bfull.cpu().numpy()) < 1e-6
+count = 2 * 14 * world
+allv = [volume(100 + i, dim) for i in range(count)]
+got, (lo, hi) = zdist.decompose_batch_sharded(P.decompose, bvols, count,
+                                              lambda a, b: torch.from_numpy(np.stack(allv[a:b])).cuda())
+ok &= tuple(got.shape) == (count, P.num_moments)
+mine = P.decompose(torch.from_numpy(np.stack(allv[lo:hi])).cuda())
+ok &= bool(torch.equal(torch.view_as_real(got[lo:hi]), torch.view_as_real(mine)))
+other = (lo + count // 2) % count                                   # a volume another rank decomposed
+ok &= rel(got[other].cpu().numpy(), P.decompose(torch.from_numpy(allv[other]).cuda()).cpu().numpy()) < 2e-6
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
