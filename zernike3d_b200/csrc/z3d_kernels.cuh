@@ -43,7 +43,7 @@ constexpr int OFF_SM = OFF_CM + (LMAX + 1) * 4;             // sin(m phi)
 constexpr int OFF_CM2 = OFF_SM + (LMAX + 1) * 4;            // cos / sin(m phi) of the transposed row group (analysis)
 constexpr int OFF_SM2 = OFF_CM2 + (LMAX + 1) * 4;
 constexpr int OFF_RED = OFF_SM2 + (LMAX + 1) * 4;           // synthesis: cross-warp reduction
-constexpr int OFF_GEO = OFF_RED + 2 * NWARP * 16 * 4;       // per-voxel geometry of one row group, 32 B each
+constexpr int OFF_GEO = OFF_RED + 4 * NWARP * 16 * 4;       // per-voxel geometry of one row group, 32 B each
 struct SmemMap {
     int F, rows, V, total;  // byte offsets of the box-size dependent arrays
 };
@@ -53,7 +53,7 @@ __host__ __device__ inline SmemMap smem_map(int N, int H) {
     int o = OFF_GEO + (H + KC) * 32;
     m.F = o;    o += 2 * align16(8 * H * 4);         // analysis: 8 mirror-folded rows of the row group and of its transpose
     m.rows = o; o += align16(4 * N * 4);             // analysis: 4 staged rows
-    m.V = o;    o += align16(4 * H * 4);             // synthesis: class sums of one row group
+    m.V = o;    o += align16(8 * H * 4);             // synthesis: class sums of one row group and of its transpose
     m.total = o;
     return m;
 }
@@ -744,7 +744,10 @@ k_reconstruct(const DevPlan P, const float *__restrict__ otiles, int batch, int 
         p0p[s] = c.Ps + t.p0; p1p[s] = c.Ps + t.p1;
     }
 
-    const int nG = (half_hi - half_lo) * H;
+    // a tile whose column halves are loaded in swapped order sees m = 2, 3 where the others see m = 0, 1: for the
+    // transposed row group that is one overall sign (see the class accumulation below)
+    const float bsign = (p0p[0] > p1p[0]) ? -1.0f : 1.0f;
+    const int nG = analysis_items(half_lo, half_hi, H);  // row groups, paired with their transposes inside the slab
     const size_t N3 = (size_t)N * N * N;
     for (int b = 0; b < batch; ++b) {
         unsigned long long om[TS][32];  // moment tiles, same pair layout as the analysis accumulators
@@ -762,8 +765,9 @@ k_reconstruct(const DevPlan P, const float *__restrict__ otiles, int batch, int 
         float *pv_out = pvol + ((size_t)pass * batch + b) * N3;
 
         for (int g = split; g < nG; g += P.nsplit) {
-            const int ip = half_lo + g / H, jp = g % H;
-            const int i2 = N - 1 - ip, j2 = N - 1 - jp;
+            int ip, jp;
+            bool paired;
+            decode_item(g, half_lo, half_hi, H, ip, jp, paired);
             const double y0 = P.side[ip], x0 = P.side[jp];
             const double rho2 = x0 * x0 + y0 * y0, rho = sqrt(rho2);
             __syncthreads();
@@ -775,13 +779,18 @@ k_reconstruct(const DevPlan P, const float *__restrict__ otiles, int batch, int 
                 generate_panels<NPH, false>(P, c, nullptr, k0, pass, warp, lane);
                 __syncthreads();
 #pragma unroll 1
-                for (int kh = 0; kh < 2; ++kh) {  // two half chunks keep the class accumulators at 16 registers
-                    unsigned long long vacc[KC];  // [k in half][column pair parity] -> classes (2jh, 2jh+1)
+                for (int kq = 0; kq < KC / 2; ++kq) {  // quarter chunks keep the class accumulators at 12 registers
+                    // Per voxel and column pair j = (re, im) of m = m0 + j, m0 = 0 (mod 4):  tt = (t_re, t_im).
+                    //   row group A (phi):         (P_re t_re, P_im t_im)                       -> E (m even) / O (m odd)
+                    //   transpose  B (pi/2 - phi): cos / sin(m phi') are a signed swap of cos / sin(m phi):
+                    //     m = 0: (+E.re, -E.im)   m = 2: (-E.re, +E.im)   m = 1: +swap(P) tt   m = 3: -swap(P) tt
+                    // so B costs two extra FFMA2 per voxel (the cross products X of the odd m) instead of a second panel.
+                    unsigned long long E0[2], E2[2], O1[2], O3[2], X1[2], X3[2];
 #pragma unroll
-                    for (int q = 0; q < KC; ++q) vacc[q] = 0ull;
+                    for (int q = 0; q < 2; ++q) E0[q] = E2[q] = O1[q] = O3[q] = X1[q] = X3[q] = 0ull;
 #pragma unroll
-                    for (int kk = 0; kk < KC / 2; ++kk) {
-                        const int k = kh * (KC / 2) + kk;
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int k = kq * 2 + kk;
 #pragma unroll
                         for (int s = 0; s < TS; ++s) {
                             const ulonglong2 ra = *reinterpret_cast<const ulonglong2 *>(r0p[s] + k * RS);
@@ -790,6 +799,7 @@ k_reconstruct(const DevPlan P, const float *__restrict__ otiles, int batch, int 
                             const ulonglong2 pb = *reinterpret_cast<const ulonglong2 *>(p1p[s] + k * PS);
                             const unsigned long long Rp[4] = {ra.x, ra.y, rb.x, rb.y};
                             const unsigned long long Pp[4] = {pa.x, pa.y, pb.x, pb.y};
+                            unsigned long long tt[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 unsigned long long tD = fmul2(Rp[0], om[s][j * 2]);
@@ -799,48 +809,64 @@ k_reconstruct(const DevPlan P, const float *__restrict__ otiles, int batch, int 
                                     ffma2(tD, Rp[i], om[s][(i * 4 + j) * 2]);
                                     ffma2(tX, Rp[i], om[s][(i * 4 + j) * 2 + 1]);
                                 }
-                                ffma2(vacc[kk * 2 + (j & 1)], Pp[j], fadd2(tD, swap2(tX)));
+                                tt[j] = fadd2(tD, swap2(tX));
                             }
+                            ffma2(E0[kk], Pp[0], tt[0]);
+                            ffma2(O1[kk], Pp[1], tt[1]);
+                            ffma2(X1[kk], swap2(Pp[1]), tt[1]);
+                            ffma2(E2[kk], Pp[2], tt[2]);
+                            ffma2(O3[kk], Pp[3], tt[3]);
+                            ffma2(X3[kk], swap2(Pp[3]), tt[3]);
                         }
                     }
-                    float v[16];  // [k in half][class column 0..3]
+                    float v[16];  // [k in quarter][A classes j0..j3 | B classes j0..j3]
 #pragma unroll
-                    for (int q = 0; q < KC; ++q) {
-                        const float2 u = unpack2(vacc[q]);
-                        v[2 * q] = u.x;
-                        v[2 * q + 1] = u.y;
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const float2 e0 = unpack2(E0[kk]), e2 = unpack2(E2[kk]), o1 = unpack2(O1[kk]), o3 = unpack2(O3[kk]);
+                        const float2 x1 = unpack2(X1[kk]), x3 = unpack2(X3[kk]);
+                        v[kk * 8 + 0] = e0.x + e2.x;
+                        v[kk * 8 + 1] = e0.y + e2.y;
+                        v[kk * 8 + 2] = o1.x + o3.x;
+                        v[kk * 8 + 3] = o1.y + o3.y;
+                        v[kk * 8 + 4] = bsign * (e0.x - e2.x);
+                        v[kk * 8 + 5] = bsign * (e2.y - e0.y);
+                        v[kk * 8 + 6] = bsign * (x1.x - x3.x);
+                        v[kk * 8 + 7] = bsign * (x1.y - x3.y);
                     }
                     const float tot = warp_transpose_reduce16(v, lane);
-                    if (lane < 16) red[(kh * NWARP + warp) * 16 + lane] = tot;
+                    if (lane < 16) red[(kq * NWARP + warp) * 16 + lane] = tot;
                 }
                 __syncthreads();
-                if (tid < 32) {
-                    const int kh = tid >> 4, q = tid & 15;
+                if (tid < 64) {
+                    const int kq = tid >> 4, q = tid & 15;
                     float s = 0.0f;
 #pragma unroll
-                    for (int w = 0; w < NWARP; ++w) s += red[(kh * NWARP + w) * 16 + q];
-                    const int k = kh * (KC / 2) + (q >> 2), j = q & 3;
-                    if (k0 + k < H) V[j * H + k0 + k] = s;
+                    for (int w = 0; w < NWARP; ++w) s += red[(kq * NWARP + w) * 16 + q];
+                    const int k = kq * 2 + (q >> 3), cls = q & 7;
+                    if (k0 + k < H) V[cls * H + k0 + k] = s;
                 }
             }
             __syncthreads();
-            // ---- unfold the 4 class sums of this pass into the 8 mirror voxels.
+            // ---- unfold the 4 class sums of this pass into the 8 mirror voxels of the row group (and of its transpose).
             // mirror class c = py*4 + px*2 + pz of class column j: j0 (m even, re) -> par, j1 (m even, im) -> 6|par,
             // j2 (m odd, re) -> 2|(par^1), j3 (m odd, im) -> 4|(par^1)
-            for (int k = tid; k < H; k += NT) {
+            for (int idx = tid; idx < (paired ? 2 : 1) * H; idx += NT) {
+                const int set = idx / H, k = idx - set * H;
                 const int k2 = N - 1 - k;
+                const int ri = set ? jp : ip, rj = set ? ip : jp, ri2 = N - 1 - ri, rj2 = N - 1 - rj;
+                const float *Vs = V + set * 4 * H;
                 float v[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] = 0.0f;
-                const float V0 = V[k], V1 = V[H + k], V2 = V[2 * H + k], V3 = V[3 * H + k];
+                const float V0 = Vs[k], V1 = Vs[H + k], V2 = Vs[2 * H + k], V3 = Vs[3 * H + k];
                 if (par == 0) { v[0] = V0; v[6] = V1; v[3] = V2; v[5] = V3; }
                 else          { v[1] = V0; v[7] = V1; v[2] = V2; v[4] = V3; }
                 wht8(v);
 #pragma unroll
                 for (int img = 0; img < 8; ++img) {
                     const bool sy = img & 4, sx = img & 2, sz = img & 1;
-                    if ((sy && i2 == ip) || (sx && j2 == jp) || (sz && k2 == k)) continue;
-                    const int ii = sy ? i2 : ip, jj = sx ? j2 : jp, kk = sz ? k2 : k;
+                    if ((sy && ri2 == ri) || (sx && rj2 == rj) || (sz && k2 == k)) continue;
+                    const int ii = sy ? ri2 : ri, jj = sx ? rj2 : rj, kk = sz ? k2 : k;
                     pv_out[((size_t)ii * N + jj) * N + kk] = v[img];
                 }
             }
