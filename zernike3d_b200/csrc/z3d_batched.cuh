@@ -11,9 +11,9 @@
 // split into a TF32-exact high part and a float32 remainder and three products are issued per tile (lo.hi, hi.lo, hi.hi:
 // "3xTF32", relative product error 2^-21).  The tensor core adds into the accumulator with truncation (measured with
 // scripts/experiments/tc_probe.cu: about -3e-8 relative per accumulating instruction), so every BFLUSH_CHUNKS chunks the
-// accumulators are read back (tcgen05.ld), scaled by the inverse of the expected truncation loss and added,
-// round-to-nearest, into the CTA's float32 partial buffer (L2 resident); the next product overwrites instead of
-// accumulating.
+// accumulators are read back (tcgen05.ld) and added, round-to-nearest, into the CTA's float32 partial buffer (L2
+// resident), the next product overwrites instead of accumulating, and the a panels are pre-scaled by the inverse of the
+// expected truncation loss their products will suffer until the read-back (BTRUNC_PER_MMA).
 //
 // Three kernels:
 //   k_build_basis  (once per plan - this is what is left of the reference's CalculatePolynomials, zm:2237-2323): the
@@ -43,9 +43,11 @@ constexpr int BSLOT_WORDS = BTILES * BCOL * BTM;  // partial sums of one CTA: [t
 constexpr int BFLUSH_CHUNKS = 32;   // accumulator read-back interval (see above)
 // Every accumulating MMA rounds the running sum toward zero: an expected relative loss of c = 3.1e-8 per instruction
 // (scripts/experiments/tc_probe.cu: -8e-8 per chunk of 3 on monotone sums; scripts/bias_check.py: a uniform shrink of
-// -4.7e-8 x chunks of the moments against the float64 oracle, the same for 5, 11 and 32 chunk intervals).  A term added
-// at step k of n is multiplied by (1 - c)^(3(n - k)), (1 - 1.5 c n) on average, so the read-back scales by the inverse.
-constexpr float BTRUNC_PER_CHUNK = 4.7e-8f;
+// -4.7e-8 x chunks of the moments against the float64 oracle, the same for 5, 11 and 32 chunk intervals).  The products
+// of chunk k of an interval of n chunks are followed by 3 (n - 1 - k) + 1 truncations, i.e. arrive at the read-back
+// multiplied by (1 - c)^(3 (n - 1 - k) + 1): the a panels of that chunk are pre-scaled by the inverse, which removes the
+// bias for any distribution of the volume's weight over the chunks (a single factor at the read-back only does on average).
+constexpr float BTRUNC_PER_MMA = 3.13e-8f;
 constexpr int BF_BYTES = 16 * BNV * KC * 4;       // folds of one chunk: [set 2][combo 8][volume][k], k halves swizzled
 
 constexpr int BOFF_THI = 0;                                      // T panels, TF32 high part   [2 k-halves][BROWS_MAX][4]
@@ -307,7 +309,7 @@ __device__ __forceinline__ void t_store(const CtxB &c, const TRow &t, int row) {
     *reinterpret_cast<float4 *>(c.Tlo + row * 4) = t.l0;
     *reinterpret_cast<float4 *>(c.Tlo + (BROWS_MAX + row) * 4) = t.l1;
 }
-__device__ __forceinline__ void a_products(const CtxB &c, const float *stage, int nmpz, const float *__restrict__ trig) {
+__device__ __forceinline__ void a_products(const CtxB &c, const float *stage, int nmpz, const float *__restrict__ trig, float comp) {
     const int tid = threadIdx.x;
     const float *Fs = stage;
     for (int it = tid; it < nmpz * (2 * BNV); it += BNPROD) {  // (panel, re / im, volume); producer threads only
@@ -315,10 +317,9 @@ __device__ __forceinline__ void a_products(const CtxB &c, const float *stage, in
         const int code = c.mpz[j], m = code & 0xffff, pz = code >> 16;
         const int comb = (reim << 2) | (((m & 1) ^ reim) << 1) | pz;
         float tA = __ldg(trig + reim * (LMAX + 1) + m), tB = __ldg(trig + (2 + reim) * (LMAX + 1) + m);
-        if (reim) {
-            tA = -tA;
-            tB = -tB;
-        }
+        const float sg = reim ? -comp : comp;  // comp: truncation pre-compensation of this chunk (see BTRUNC_PER_MMA)
+        tA *= sg;
+        tB *= sg;
         const int sw = ((b >> 2) & 1) << 2;  // k_fold_tile's k-half swizzle: 8 consecutive volumes cover all banks
         const float *fa = Fs + (comb * BNV + b) * KC, *fb = fa + 8 * BNV * KC;
 #pragma unroll
@@ -353,9 +354,8 @@ __device__ __forceinline__ void issue_mma(const CtxB &c, unsigned tmem, int ntil
 
 // accumulators -> this CTA's partial buffer [tile][column][row] (float32, round to nearest); warp w reads the lane
 // quarter w % 4 (the only one it can address) of tile w / 4
-__device__ __forceinline__ void flush_accumulators(unsigned tmem, int ntile, float *out, bool add, int chunks) {
+__device__ __forceinline__ void flush_accumulators(unsigned tmem, int ntile, float *out, bool add) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3;
-    const float comp = 1.0f + BTRUNC_PER_CHUNK * (float)chunks;  // undo the accumulator's expected truncation loss
 #pragma unroll 1
     for (int t = warp >> 2; t < ntile; t += BNWARP / 4) {
 #pragma unroll 1
@@ -365,10 +365,10 @@ __device__ __forceinline__ void flush_accumulators(unsigned tmem, int ntile, flo
             float *p = out + ((size_t)t * BCOL + 32 * half) * BTM + 32 * q + lane;
             if (add) {
 #pragma unroll
-                for (int col = 0; col < 32; ++col) p[col * BTM] = fmaf(__uint_as_float(v[col]), comp, p[col * BTM]);
+                for (int col = 0; col < 32; ++col) p[col * BTM] += __uint_as_float(v[col]);
             } else {
 #pragma unroll
-                for (int col = 0; col < 32; ++col) p[col * BTM] = __uint_as_float(v[col]) * comp;
+                for (int col = 0; col < 32; ++col) p[col * BTM] = __uint_as_float(v[col]);
             }
         }
     }
@@ -457,6 +457,10 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
         c.Ahi = abase + (adouble ? (int)(t & 1) * 2 * BA_WORDS : 0);
         c.Alo = c.Ahi + BA_WORDS;
         const float *trig = P.trig + (size_t)(cc / CPR) * 4 * (LMAX + 1);
+        // position of this chunk in its read-back interval and the interval's length (the last one may be shorter)
+        const int pos = since_flush == BFLUSH_CHUNKS ? 0 : since_flush;
+        const int ilen = (int)min((long long)BFLUSH_CHUNKS, (cend - cc) + pos);
+        const float comp = 1.0f + BTRUNC_PER_MMA * (float)(3 * (ilen - 1 - pos) + 1);
         // everything that does not touch the panels the previous chunk's MMAs are still reading comes first: the a panels
         // (other buffer) and the T products, which stay in registers until the MMAs have retired.  Warps 0-30 produce
         // (one row per thread, warp 0 also the last 32 rows); warp 31 only issues, so that the ~24 MMA issues and 3 copy
@@ -464,7 +468,7 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
         const bool producer = tid < BNPROD, two_rows = tid < BROWS_MAX - BNPROD;
         TRow trow;
         if (producer) {
-            if (adouble) a_products(c, stage, nmpz, trig);
+            if (adouble) a_products(c, stage, nmpz, trig, comp);
             trow = t_compute(c, stage, nrad, qlo, tid);
         }
         if (t) {  // the previous chunk's MMAs have retired: the operand panels are free, the accumulators current
@@ -472,13 +476,13 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
             tc_fence_after();
         }
         if (since_flush == BFLUSH_CHUNKS) {
-            flush_accumulators(tmem, ntile, out, flushed, since_flush);
+            flush_accumulators(tmem, ntile, out, flushed);
             flushed = true;
             since_flush = 0;
             tc_fence_before();
         }
         if (producer) {
-            if (!adouble) a_products(c, stage, nmpz, trig);
+            if (!adouble) a_products(c, stage, nmpz, trig, comp);
             t_store(c, trow, tid);
             if (two_rows) t_store(c, t_compute(c, stage, nrad, qlo, BNPROD + tid), BNPROD + tid);
         }
@@ -494,7 +498,7 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
     if (t) {
         mbar_wait(mbar, (t - 1) & 1);
         tc_fence_after();
-        flush_accumulators(tmem, ntile, out, flushed, since_flush);
+        flush_accumulators(tmem, ntile, out, flushed);
     } else {
         for (int i = tid; i < BSLOT_WORDS; i += BNT) out[i] = 0.0f;  // the reduction reads every split
     }
