@@ -64,8 +64,9 @@ int z3d_plan_destroy(z3d_plan *plan);
 
 /* Plan queries (host only). info[]: 0 order, 1 dim, 2 num_moments, 3 passes, 4 CTAs per launch,
  * 5 threads per CTA, 6 tiles per thread, 7 dynamic smem bytes, 8 voxels per chunk, 9 SM count,
- * 10 useful accumulators, 11 padded accumulators, 12 smallest batch routed to the batched analysis kernel
- * (0 = that kernel is unavailable for this order), 13 its row groups, 14 its voxel splits, 15 volumes per tile. */
+ * 10 useful accumulators, 11 padded accumulators, 12 smallest batch routed to the batched (tensor-core) analysis kernels
+ * (0 = unavailable for this order / box), 13 row groups of the 32-volume tile kernel, 14 of the 64-volume one,
+ * 15 smallest remaining batch that takes a 64-volume tile, 16 / 17 rounds (contraction launches per tile) of the two. */
 int z3d_plan_info(const z3d_plan *plan, int *info, int n_info);
 
 /* Bytes of device scratch z3d_decompose / z3d_reconstruct need for `batch` volumes. */

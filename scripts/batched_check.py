@@ -18,7 +18,9 @@ def timed(fn, reps=3):
     return e0.elapsed_time(e1) / reps
 
 cases = [("d16_o10", 9), ("d15_o8", 12), ("d32_o20", 32), ("d20_o25", 33), ("c1_d64_o50", 32), ("c5_d96_o60", 16), ("c3_d128_o50", 32)]
-if len(sys.argv) > 1: cases = [c for c in cases if c[0] in sys.argv[1:]]
+if len(sys.argv) > 1:  # names, optionally name:count
+    want = dict((a.split(":") + [None])[:2] for a in sys.argv[1:])
+    cases = [(n, int(want[n]) if want[n] else b) for n, b in cases if n in want]
 for name, B in cases:
     g = np.load(os.path.join(ROOT, "tests/golden", f"ref_{name}.npz"))
     order, dim = int(g["order"]), int(g["dim"])
@@ -29,7 +31,7 @@ for name, B in cases:
     mb = P.decompose(dv); torch.cuda.synchronize()          # batched route (B >= batched_min)
     ms = torch.stack([P.decompose(dv[i:i + 1])[0] for i in range(B)])   # per-volume route
     torch.cuda.synchronize()
-    line = f"{name} B={B} batched_min={info['batched_min']} groups={info['batched_row_groups']}x{info['batched_splits']}: "
+    line = f"{name} B={B} batched_min={info['batched_min']} groups={info['batched_row_groups']}/{info['batched_row_groups_wide']} wide>={info['batched_wide_min']}: "
     line += f"batched vs per-volume {rel(mb.cpu().numpy(), ms.cpu().numpy()):.2e} (worst volume {max(rel(mb[i].cpu().numpy(), ms[i].cpu().numpy()) for i in range(B)):.2e})"
     line += f" vs ref golden {rel(mb[0].cpu().numpy(), g['moments'][0]):.2e}"
     if dim <= 64:

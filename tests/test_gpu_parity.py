@@ -112,7 +112,8 @@ def test_3dva_bundle_batched(plans):
     assert np.array_equal(moms, one_by_one)           # batching does not change a single bit
 
 
-BATCHED = [("d16_o10", 13), ("d15_o8", 12), ("d32_o20", 35), ("d20_o25", 45), ("c1_d64_o50", 32), ("c5_d96_o60", 16)]
+BATCHED = [("d16_o10", 13), ("d15_o8", 12), ("d32_o20", 35), ("d20_o25", 45), ("d16_o10", 139), ("c1_d64_o50", 32),
+           ("c1_d64_o50", 50), ("c5_d96_o60", 16)]
 
 
 @pytest.mark.parametrize("name,count", BATCHED)
@@ -124,17 +125,19 @@ def test_batched_tensor_core_path(plans, oracle_mod, name, count):
     order, dim = int(g["order"]), int(g["dim"])
     P = plans(order, dim)
     info = P.info()
-    assert 0 < info["batched_min"] <= count and info["batched_tile_volumes"] == 32
+    assert 0 < info["batched_min"] <= count
     seed0 = int(g["seeds"][0])
     vols = np.stack([volume(seed0 + i, dim) for i in range(count)])
     dv = dev(vols)
     P.decompose(dv)                                           # first call also builds the basis tables
     l0 = launch_count()
     mb = P.decompose(dv)
-    tiles, tail = divmod(count, 32)
-    if tail >= info["batched_min"]:
-        tiles, tail = tiles + 1, 0
-    assert launch_count() - l0 >= 3 * tiles + (2 if tail else 0)  # fold + contraction + reduction per tile, then the tail
+    tiles, left, covered = 0, count, 0                        # the C side's tiling: 64-volume tiles while >= wide_min are left,
+    while left >= info["batched_min"]:                        # then 32-volume tiles, then the per-volume kernel
+        take = min(64 if left >= info["batched_wide_min"] else 32, left)
+        tiles, left, covered = tiles + 1, left - take, covered + take
+    tail = left
+    assert launch_count() - l0 >= 3 * tiles + (2 if tail else 0)  # fold + contraction round(s) + reduction per tile, then the tail
     assert mb.shape == (count, P.num_moments) and mb.dtype == torch.complex64
     assert torch.equal(torch.view_as_real(mb), torch.view_as_real(P.decompose(dv)))     # run-to-run bitwise
     mb = mb.cpu().numpy()
@@ -144,12 +147,12 @@ def test_batched_tensor_core_path(plans, oracle_mod, name, count):
     # every volume against the per-volume kernel (different summation order and arithmetic, same tables of coefficients)
     for i in range(count):
         one = P.decompose(dv[i]).cpu().numpy()
-        if i >= 32 * tiles:                                   # tail volumes took the per-volume kernel inside the batch
+        if i >= covered:                                      # tail volumes took the per-volume kernel inside the batch
             assert np.array_equal(mb[i], one)
         else:
             assert rel_l2(mb[i], one) < 2 * TOL_EXACT_BATCHED
     # first and last volume of the first tile against the float64 oracle, moments and invariants
-    for i in ([0, min(count, 32) - 1] if dim <= 64 else []):
+    for i in ([0, covered - 1] if dim <= 64 else []):
         exact = oracle_mod.decompose(vols[i], order, oracle_mod.EXACT)
         assert rel_l2(mb[i], exact) < TOL_EXACT_BATCHED
         inv = P.invariants(dev(mb[i])).cpu().numpy()
@@ -170,6 +173,11 @@ def test_batched_128_order50_headline(plans, oracle_mod):
         assert rel_l2(mb[i], exact) < TOL_EXACT_BATCHED
         inv = P.invariants(dev(mb[i])).cpu().numpy()
         assert rel_l2(inv, oracle_mod.invariants(exact, order)) < TOL_INV
+    # the same volumes in one 64-volume tile (N = 128 MMAs, 4-tile row groups, 3 rounds)
+    wide = P.decompose(torch.cat([dv, dv])).cpu().numpy()
+    assert rel_l2(wide[:32], mb) < 1.5e-6 and np.array_equal(wide[:32], wide[32:])
+    for i in (0, 31):
+        assert rel_l2(wide[i], oracle_mod.decompose(vols[i], order, oracle_mod.EXACT)) < TOL_EXACT_BATCHED
     # work parts of a batch are additive (multi-GPU work sharding of replicated volumes), linearity in the volumes
     parts = sum(P.decompose(dv, part=(r, 3)) for r in range(3)).cpu().numpy()
     assert rel_l2(parts, mb) < 1e-6

@@ -63,12 +63,13 @@ struct z3d_plan {
     int order = 0, dim = 0, device = 0, H = 0, nmom = 0, nrad = 0, npass = 0, nsplit = 0, num_sms = 0;
     int smem_bytes = 0, useful_acc = 0, padded_acc = 0;
     DevPlan dev{};
-    // batched analysis kernel (tiles of BNV volumes); absent when the order does not fit its fixed layout
+    // batched analysis kernels (tiles of 32 or 64 volumes); absent when the order does not fit their fixed layout
     bool batched = false;
-    int batched_min = 12;        // smallest (remaining) batch that is routed to the batched kernel
-    DevPlanB devb{};
-    int2 *d_rowmap = nullptr;
-    int b_smem = 0;
+    int batched_min = 12;        // smallest (remaining) batch that is routed to the batched kernels
+    int batched_wide = 33;       // smallest (remaining) batch that takes a 64-volume tile instead of a 32-volume one
+    DevPlanB devb[2]{};          // [0]: 32 volumes per tile (8 tiles of 128 rows per row group), [1]: 64 (4 tiles)
+    int2 *d_rowmap[2] = {nullptr, nullptr};
+    int b_smem[2] = {0, 0};
     long long b_chunks = 0;      // chunks of the whole volume: row-group items x chunks per row
     BasisArgs basis{};           // inputs of k_build_basis; the tables themselves are built on first use
     bool basis_ready = false;
@@ -319,7 +320,7 @@ int build_host_plan(int L, HostPlan &hp) {
 // ---- planner of the batched (tensor-core) analysis path (z3d_batched.cuh) -------------------------------------------
 struct HostPlanB {
     bool ok = false;
-    int ngroups = 0, nsplit = 0, nrad = 0, nq = 0;
+    int ngroups = 0, gpr = 0, nrounds = 0, nrad = 0, nq = 0;
     std::vector<int2> rowtab, rowmap;
     std::vector<int> tile_mpz, mpz, nmpz, ntile, qlo, qlen;
     // inputs of k_build_basis
@@ -329,7 +330,8 @@ struct HostPlanB {
 
 // Returns ok = false (no error) when the order does not fit the kernel's fixed layout: callers then use the per-volume
 // kernel for batches as well.
-void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
+void build_batched_plan(int L, int num_sms, int tiles_per_group, const HostPlan &hp, HostPlanB &hb) {
+    const int rows_per_group = tiles_per_group * BTM;
     const int S = L + 1;
     hb.nrad = num_radial(L);
     // radial table, l-major over ALL l (index in rk == index in the R table)
@@ -386,13 +388,28 @@ void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
             for (int t = (int)tile_code.size(); t < (int)rows.size() / BTM; ++t) tile_code.push_back(m | (pz << 16));
         }
     const int ntiles = (int)tile_code.size();
-    const int ngroups = (ntiles + BTILES - 1) / BTILES;
+    const int ngroups = (ntiles + tiles_per_group - 1) / tiles_per_group;
     if (ngroups > num_sms) return;
     hb.ngroups = ngroups;
-    hb.nsplit = std::max(1, num_sms / ngroups);
-    hb.rowtab.assign((size_t)ngroups * BROWS_MAX, make_int2(hb.nrad, 0));  // padding rows: the zero R entry
-    hb.tile_mpz.assign((size_t)ngroups * BTILES, 0);
-    hb.mpz.assign((size_t)ngroups * BMPZ_MAX, -1);
+    {   // rounds (z3d_batched.cuh, WorkRange): time ~ sum over rounds of 1 / floor(SMs / groups in the round); take the largest
+        // number of groups per round (best L2 reuse, fewest accumulator read-backs) within 6 % of the best
+        auto cost = [&](int gpr) {
+            double c = 0.0;
+            for (int g0 = 0; g0 < ngroups; g0 += gpr) c += 1.0 / (num_sms / std::min(gpr, ngroups - g0));
+            return c;
+        };
+        double best = 1e30;
+        for (int gpr = 1; gpr <= ngroups; ++gpr) best = std::min(best, cost(gpr));
+        for (int gpr = ngroups; gpr >= 1; --gpr)
+            if (cost(gpr) <= 1.06 * best) {
+                hb.gpr = gpr;
+                break;
+            }
+        hb.nrounds = (ngroups + hb.gpr - 1) / hb.gpr;
+    }
+    hb.rowtab.assign((size_t)ngroups * rows_per_group, make_int2(hb.nrad, 0));  // padding rows: the zero R entry
+    hb.tile_mpz.assign((size_t)ngroups * BTILES_MAX, 0);
+    hb.mpz.assign((size_t)ngroups * BTILES_MAX, -1);
     hb.nmpz.assign(ngroups, 0);
     hb.ntile.assign(ngroups, 0);
     hb.qlo.assign(ngroups, 0);
@@ -408,7 +425,7 @@ void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
             }
     }
     for (int g = 0; g < ngroups; ++g) {
-        const int t0 = g * BTILES, t1 = std::min(ntiles, t0 + BTILES);
+        const int t0 = g * tiles_per_group, t1 = std::min(ntiles, t0 + tiles_per_group);
         const int mlo = tile_code[t0] & 0xffff, mhi = tile_code[t1 - 1] & 0xffff;
         hb.ntile[g] = t1 - t0;
         hb.qlo[g] = hb.qoff[mlo];
@@ -417,15 +434,15 @@ void build_batched_plan(int L, int num_sms, const HostPlan &hp, HostPlanB &hb) {
         int nm = 0, last = -1;
         for (int t = t0; t < t1; ++t) {
             if (tile_code[t] != last) {
-                hb.mpz[(size_t)g * BMPZ_MAX + nm++] = tile_code[t];
+                hb.mpz[(size_t)g * BTILES_MAX + nm++] = tile_code[t];
                 last = tile_code[t];
             }
-            hb.tile_mpz[(size_t)g * BTILES + (t - t0)] = nm - 1;
+            hb.tile_mpz[(size_t)g * BTILES_MAX + (t - t0)] = nm - 1;
             for (int i = 0; i < BTM; ++i) {
                 const Row &r = rows[(size_t)t * BTM + i];
                 if (r.n < 0) continue;
                 const int row = (t - t0) * BTM + i;
-                hb.rowtab[(size_t)g * BROWS_MAX + row] =
+                hb.rowtab[(size_t)g * rows_per_group + row] =
                     make_int2(hb.rbase[r.l] + (r.n - r.l) / 2, hb.qoff[r.m] + (r.l - r.m) - hb.qlo[g]);
                 hb.rowmap[mubase[(size_t)r.n * S + r.l] + r.m] = make_int2(g, row);
             }
@@ -449,12 +466,10 @@ int set_kernel_attrs_t(int smem) {
 int set_kernel_attrs(int smem) {
     int rc = set_kernel_attrs_t<1>(smem);
     if (rc) return rc;
-#ifdef Z3D_DEBUG_TIMING
-    CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, smem - 2048));  // static s_dbg
-#else
-    CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-#endif
-    CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return set_kernel_attrs_t<0>(smem);
 }
 
@@ -553,33 +568,40 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
     d.side = d_side; d.gd = d_gd; d.goff = d_goff; d.rk = d_rk; d.rbase = d_rbase; d.roffw = d_roffw; d.poffw = d_poffw;
     d.ownl = d_ownl; d.nown = d_nown; d.ntiles = d_ntiles; d.tiles = d_tiles; d.gen_tasks = d_gen;
 
-    {
+    // dim >= 14 keeps every 8-voxel chunk and its z-mirror inside a row (k_fold_tile reads both)
+    pl->batched = dim >= 14;
+    for (int v = 0; v < 2 && pl->batched; ++v) {
         HostPlanB hb;
-        build_batched_plan(order, prop.multiProcessorCount, hp, hb);
-        const bool adouble = (size_t)batched_smem_bytes(hb.nrad, true) <= prop.sharedMemPerBlockOptin;
-        pl->b_smem = batched_smem_bytes(hb.nrad, adouble);
-        // dim >= 14 keeps every 8-voxel chunk and its z-mirror inside a row (k_fold_tile reads both)
-        if (hb.ok && dim >= 14 && (size_t)pl->b_smem <= prop.sharedMemPerBlockOptin) {
-            DevPlanB &b = pl->devb;
-            b.order = order; b.dim = dim; b.H = pl->H; b.ngroups = hb.ngroups; b.nsplit = hb.nsplit;
-            b.nrad = hb.nrad; b.nq = hb.nq; b.adouble = adouble;
-            int2 *d_rowtab; int *d_bm, *d_mpz, *d_nmpz, *d_ntile, *d_qlo, *d_qlen, *d_bgoff, *d_qoff, *d_brbase;
+        build_batched_plan(order, prop.multiProcessorCount, v ? BCfg<64>::TILES : BCfg<32>::TILES, hp, hb);
+        auto smem_of = [&](bool ad) { return v ? BCfg<64>::smem_bytes(hb.nrad, ad) : BCfg<32>::smem_bytes(hb.nrad, ad); };
+        const bool adouble = (size_t)smem_of(true) <= prop.sharedMemPerBlockOptin;
+        pl->b_smem[v] = smem_of(adouble);
+        if (!hb.ok || (size_t)pl->b_smem[v] > prop.sharedMemPerBlockOptin) {
+            pl->batched = false;
+            break;
+        }
+        DevPlanB &b = pl->devb[v];
+        b.order = order; b.dim = dim; b.H = pl->H; b.ngroups = hb.ngroups; b.gpr = hb.gpr; b.nrounds = hb.nrounds;
+        b.nrad = hb.nrad; b.nq = hb.nq; b.adouble = adouble;
+        int2 *d_rowtab; int *d_bm, *d_mpz, *d_nmpz, *d_ntile, *d_qlo, *d_qlen;
+        UP(hb.rowtab, d_rowtab) UP(hb.tile_mpz, d_bm) UP(hb.mpz, d_mpz) UP(hb.nmpz, d_nmpz) UP(hb.ntile, d_ntile)
+        UP(hb.qlo, d_qlo) UP(hb.qlen, d_qlen) UP(hb.rowmap, pl->d_rowmap[v])
+        b.rowtab = d_rowtab; b.tile_mpz = d_bm; b.mpz = d_mpz; b.nmpz = d_nmpz; b.ntile = d_ntile;
+        b.qlo = d_qlo; b.qlen = d_qlen;
+        if (v == 0) {  // inputs of k_build_basis (the same for both tile widths)
+            int *d_bgoff, *d_qoff, *d_brbase;
             float4 *d_bgd, *d_brk;
-            UP(hb.rowtab, d_rowtab) UP(hb.tile_mpz, d_bm) UP(hb.mpz, d_mpz) UP(hb.nmpz, d_nmpz) UP(hb.ntile, d_ntile)
-            UP(hb.qlo, d_qlo) UP(hb.qlen, d_qlen) UP(hb.goff, d_bgoff) UP(hb.qoff, d_qoff) UP(hb.rbase, d_brbase)
-            UP(hb.gd, d_bgd) UP(hb.rk, d_brk) UP(hb.rowmap, pl->d_rowmap)
-            b.rowtab = d_rowtab; b.tile_mpz = d_bm; b.mpz = d_mpz; b.nmpz = d_nmpz; b.ntile = d_ntile;
-            b.qlo = d_qlo; b.qlen = d_qlen;
+            UP(hb.goff, d_bgoff) UP(hb.qoff, d_qoff) UP(hb.rbase, d_brbase) UP(hb.gd, d_bgd) UP(hb.rk, d_brk)
             BasisArgs &a = pl->basis;
             a.order = order; a.dim = dim; a.H = pl->H; a.nrad = hb.nrad; a.nq = hb.nq; a.side = d_side;
             a.rk = d_brk; a.rbase = d_brbase; a.gd = d_bgd; a.goff = d_bgoff; a.qoff = d_qoff;
             pl->b_chunks = (long long)analysis_items(0, pl->H, pl->H) * ((pl->H + KC - 1) / KC);
-            pl->batched = true;
         }
     }
 #undef UP
 
     if (const char *e = getenv("Z3D_BATCHED_MIN")) pl->batched_min = std::max(1, atoi(e));  // tuning / tests
+    if (const char *e = getenv("Z3D_BATCHED_WIDE")) pl->batched_wide = std::max(1, atoi(e));
     rc = set_kernel_attrs((int)prop.sharedMemPerBlockOptin);  // per-function attribute: plans of any size coexist
     if (rc) {
         z3d_plan_destroy(pl);
@@ -617,10 +639,11 @@ extern "C" int z3d_plan_destroy(z3d_plan *pl) {
 
 extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
     if (!pl || !info) return fail(Z3D_ERR_INVALID, "z3d_plan_info: NULL argument");
-    const int v[16] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
+    const int v[18] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
                        KC, pl->num_sms, pl->useful_acc, pl->padded_acc,
-                       pl->batched ? pl->batched_min : 0, pl->devb.ngroups, pl->devb.nsplit, BNV};
-    for (int i = 0; i < n && i < 16; ++i) info[i] = v[i];
+                       pl->batched ? pl->batched_min : 0, pl->devb[0].ngroups, pl->devb[1].ngroups, pl->batched ? pl->batched_wide : 0,
+                       pl->devb[0].nrounds, pl->devb[1].nrounds};
+    for (int i = 0; i < n && i < 18; ++i) info[i] = v[i];
     return Z3D_OK;
 }
 
@@ -633,8 +656,9 @@ static int decompose_group(const z3d_plan *pl) {
 }
 static size_t ws_decompose(const z3d_plan *pl, int batch) {
     size_t w = (size_t)std::min(batch, decompose_group(pl)) * pl->npass * pl->nsplit * SLOT_WORDS * sizeof(float);
-    if (pl->batched && batch >= pl->batched_min)  // per-CTA partial sums + the folds of one tile of volumes
-        w = std::max(w, (size_t)pl->devb.ngroups * pl->devb.nsplit * BSLOT_WORDS * sizeof(float) + (size_t)pl->b_chunks * BF_BYTES);
+    if (pl->batched && batch >= pl->batched_min)  // per-(CTA, segment) partial sums + the folds of one tile of volumes
+        w = std::max(w, (size_t)pl->num_sms * std::max(pl->devb[0].nrounds, pl->devb[1].nrounds) * BSLOT_WORDS * sizeof(float) +
+                            (size_t)pl->b_chunks * (batch >= pl->batched_wide ? BCfg<64>::F_BYTES : BCfg<32>::F_BYTES));
     return w;
 }
 static size_t ws_reconstruct(const z3d_plan *pl, int batch) {
@@ -687,7 +711,9 @@ static int ensure_basis(z3d_plan *pl, cudaStream_t st) {
         return Z3D_OK;
     }
     pl->basis.Rt = pl->d_Rt; pl->basis.Qt = pl->d_Qt; pl->basis.trig = pl->d_trig;
-    pl->devb.Rt = pl->d_Rt; pl->devb.Qt = pl->d_Qt; pl->devb.trig = pl->d_trig;
+    for (int v = 0; v < 2; ++v) {
+        pl->devb[v].Rt = pl->d_Rt; pl->devb[v].Qt = pl->d_Qt; pl->devb[v].trig = pl->d_trig;
+    }
     CUDA_TRY(cudaMemsetAsync(pl->d_trig, 0, tb, st));
     k_build_basis<<<(unsigned)pl->b_chunks, 1024, 0, st>>>(pl->basis);
     CUDA_TRY(cudaGetLastError());
@@ -719,20 +745,35 @@ static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int
         if (rc) return rc;
     }
     while (pl->batched && half_lo == 0 && half_hi == pl->H && batch - done >= pl->batched_min) {
-        const int nb = std::min(BNV, batch - done);
+        // a tile of up to 64 volumes when enough are left, else of up to 32 (a tile costs the same whatever it holds)
+        const int wide = (batch - done >= pl->batched_wide) ? 1 : 0;
+        const int nb = std::min(wide ? 64 : 32, batch - done);
+        const DevPlanB &dp = pl->devb[wide];
         const float *vol = d_vol + (size_t)done * N3;
-        float *folds = partial + (size_t)pl->devb.ngroups * pl->devb.nsplit * BSLOT_WORDS;
-        k_fold_tile<<<(unsigned)pl->b_chunks, 2 * BNV * KC, 0, st>>>(vol, nb, pl->dim, pl->H, folds);
+        float *folds = partial + (size_t)pl->num_sms * std::max(pl->devb[0].nrounds, pl->devb[1].nrounds) * BSLOT_WORDS;
+        float *mom = d_moments + (size_t)done * 2 * pl->nmom;
+        if (wide) k_fold_tile<64><<<(unsigned)pl->b_chunks, 2 * 64 * KC, 0, st>>>(vol, nb, pl->dim, pl->H, folds);
+        else k_fold_tile<32><<<(unsigned)pl->b_chunks, 2 * 32 * KC, 0, st>>>(vol, nb, pl->dim, pl->H, folds);
         CUDA_TRY(cudaGetLastError());
+        // one launch per round of dp.gpr row groups: groups x floor(SMs / groups) CTAs sweep the chunk list in lock step
         const bool timed = pl->profiling && mpl->n_timed < z3d_plan::MAX_TIMED;
         if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t0[mpl->n_timed], st));
-        k_decompose_batched<<<pl->devb.ngroups * pl->devb.nsplit, BNT, pl->b_smem, st>>>(pl->devb, folds, part, nparts, partial);
-        CUDA_TRY(cudaGetLastError());
+        for (int r = 0; r < dp.nrounds; ++r) {
+            const int g0 = r * dp.gpr, gr = std::min(dp.gpr, dp.ngroups - g0), cpg = pl->num_sms / gr;
+            float *slots = partial + (size_t)r * pl->num_sms * BSLOT_WORDS;
+            if (wide) k_decompose_batched<64><<<gr * cpg, BNT, pl->b_smem[1], st>>>(dp, folds, part, nparts, g0, cpg, slots);
+            else k_decompose_batched<32><<<gr * cpg, BNT, pl->b_smem[0], st>>>(dp, folds, part, nparts, g0, cpg, slots);
+            CUDA_TRY(cudaGetLastError());
+        }
         if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t1[mpl->n_timed++], st));
-        k_reduce_batched<<<(pl->nmom * BCOL + 255) / 256, 256, 0, st>>>(partial, pl->d_rowmap, pl->d_scale, pl->nmom,
-                                                                       pl->devb.nsplit, nb, d_moments + (size_t)done * 2 * pl->nmom);
+        if (wide)
+            k_reduce_batched<64><<<(pl->nmom * 128 + 255) / 256, 256, 0, st>>>(partial, pl->d_rowmap[1], pl->d_scale, pl->nmom, dp.ngroups,
+                                                                             dp.gpr, pl->num_sms, nb, mom);
+        else
+            k_reduce_batched<32><<<(pl->nmom * 64 + 255) / 256, 256, 0, st>>>(partial, pl->d_rowmap[0], pl->d_scale, pl->nmom, dp.ngroups,
+                                                                            dp.gpr, pl->num_sms, nb, mom);
         CUDA_TRY(cudaGetLastError());
-        g_launches += 3;
+        g_launches += 2 + dp.nrounds;
         done += nb;
     }
     for (int b0 = done; b0 < batch; b0 += grp) {
@@ -849,14 +890,14 @@ static int ensure_staging(z3d_plan *pl) {
     if (pl->s_copy) return Z3D_OK;
     CUDA_TRY(cudaSetDevice(pl->device));
     const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
-    // group size: one tile of the batched kernel (32 volumes) when that path exists and a sixteenth of the free device
-    // memory holds the two stages; otherwise ~32 MiB of volume data per stage, at least 1 volume
+    // group size: one wide tile of the batched kernels (64 volumes) when that path exists and a sixteenth of the free
+    // device memory holds the two stages; otherwise ~32 MiB of volume data per stage, at least 1 volume
     int gb = (int)std::min<size_t>(32, std::max<size_t>(1, ((size_t)32 << 20) / (N3 * sizeof(float))));
     if (pl->batched) {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        const size_t need = 2 * ((size_t)BNV * N3 * sizeof(float) + z3d_workspace_bytes(pl, BNV));
-        if (need <= free_b / 16) gb = BNV;
+        const size_t need = 2 * ((size_t)64 * N3 * sizeof(float) + z3d_workspace_bytes(pl, 64));
+        if (need <= free_b / 16) gb = 64;
     }
     pl->stage_batch = gb;
     CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));

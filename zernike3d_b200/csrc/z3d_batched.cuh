@@ -31,15 +31,11 @@ namespace z3d {
 
 constexpr int BNT = 1024;           // threads per CTA of the contraction kernel (31 producer warps + 1 issuing warp; accumulators in TMEM)
 constexpr int BNWARP = BNT / 32;
-constexpr int BNPROD = BNT - 32;     // producer threads: the last warp only issues the MMAs and the bulk copies
-constexpr int BNV = 32;             // volumes per batch tile
-constexpr int BCOL = 2 * BNV;       // GEMM columns: [re | im][volume]
+constexpr int BNPROD = BNT - 32;    // producer threads: the last warp only issues the MMAs and the bulk copies
 constexpr int BTM = 128;            // rows of an MMA tile (UMMA M)
-constexpr int BTILES = 8;           // tiles per row group: 8 x 64 columns = all of tensor memory
-constexpr int BROWS_MAX = BTILES * BTM;
-constexpr int BMPZ_MAX = BTILES;    // (m, pz) combinations per row group (a tile belongs to exactly one)
+constexpr int BTILES_MAX = 8;       // tiles per row group at most (32-volume tiles)
 constexpr int BQ_MAX = 192;         // Q values per voxel in a row group's slice
-constexpr int BSLOT_WORDS = BTILES * BCOL * BTM;  // partial sums of one CTA: [tile][column][row]
+constexpr int BSLOT_WORDS = 512 * BTM;  // partial sums of one CTA: [tensor-memory column = tile * COL + col][row]
 constexpr int BFLUSH_CHUNKS = 32;   // accumulator read-back interval (see above)
 // Every accumulating MMA rounds the running sum toward zero: an expected relative loss of c = 3.1e-8 per instruction
 // (scripts/experiments/tc_probe.cu: -8e-8 per chunk of 3 on monotone sums; scripts/bias_check.py: a uniform shrink of
@@ -48,32 +44,40 @@ constexpr int BFLUSH_CHUNKS = 32;   // accumulator read-back interval (see above
 // multiplied by (1 - c)^(3 (n - 1 - k) + 1): the a panels of that chunk are pre-scaled by the inverse, which removes the
 // bias for any distribution of the volume's weight over the chunks (a single factor at the read-back only does on average).
 constexpr float BTRUNC_PER_MMA = 3.13e-8f;
-constexpr int BF_BYTES = 16 * BNV * KC * 4;       // folds of one chunk: [set 2][combo 8][volume][k], k halves swizzled
 
-constexpr int BOFF_THI = 0;                                      // T panels, TF32 high part   [2 k-halves][BROWS_MAX][4]
-constexpr int BOFF_TLO = BOFF_THI + 2 * BROWS_MAX * 16;          //           float32 remainder
-constexpr int BOFF_ROWTAB = BOFF_TLO + 2 * BROWS_MAX * 16;       // (R index, Q index in the slice) per row [BROWS_MAX] ushort2
-constexpr int BOFF_TABS = BOFF_ROWTAB + BROWS_MAX * 4;           // mpz, tile_mpz [2][BTILES]
-constexpr int BOFF_MBAR = BOFF_TABS + 2 * BTILES * 4;            // mbarriers: full[2], mma; tensor-memory base address
-constexpr int BOFF_A = (BOFF_MBAR + 32 + 127) / 128 * 128;       // a panels [1 or 2 buffers][hi | lo][BMPZ_MAX][2 k-halves][BCOL][4],
-                                                                 // then 2 copy stages [F | R (nrad + 4 entries) | Q slice]
-constexpr int BA_WORDS = BMPZ_MAX * 2 * BCOL * 4;                // one a panel set (hi or lo)
-static_assert(BOFF_TLO % 128 == 0 && BOFF_MBAR % 8 == 0 && BOFF_A % 128 == 0 && (BA_WORDS * 4) % 128 == 0, "smem alignment");
-// stage: F, then R with extra all-zero entries (padding rows point at the first), then the Q slice
-__host__ __device__ inline int batched_stage_bytes(int nrad) { return BF_BYTES + (nrad + 4) * 32 + BQ_MAX * 32; }
-__host__ __device__ inline int batched_smem_bytes(int nrad, bool adouble) {
-    return BOFF_A + 2 * BA_WORDS * 4 * (adouble ? 2 : 1) + 2 * batched_stage_bytes(nrad);
-}
+// compile-time geometry of the two tile widths: NV = 32 volumes (N = 64 MMAs, 8 tiles of 128 rows per row group) or
+// NV = 64 (N = 128 MMAs, which run at the full tensor-pipe rate and fetch the T operand once per 128 columns; 4 tiles)
+template <int NV>
+struct BCfg {
+    static constexpr int COL = 2 * NV;                 // GEMM columns: [re | im][volume]
+    static constexpr int TILES = 512 / COL;            // tiles per row group: all of tensor memory
+    static constexpr int ROWS = TILES * BTM;
+    static constexpr int F_BYTES = 16 * NV * KC * 4;   // folds of one chunk: [set 2][combo 8][volume][k], k halves swizzled
+    static constexpr int A_WORDS = TILES * 2 * COL * 4;  // one a panel set (hi or lo): [panel][2 k-halves][COL][4]
+    static constexpr int OFF_THI = 0;                              // T panels, TF32 high part [2 k-halves][ROWS][4]
+    static constexpr int OFF_TLO = OFF_THI + 2 * ROWS * 16;        //           float32 remainder
+    static constexpr int OFF_ROWTAB = OFF_TLO + 2 * ROWS * 16;     // (R index, Q index in the slice) per row [ROWS] ushort2
+    static constexpr int OFF_TABS = OFF_ROWTAB + ROWS * 4;         // mpz, tile_mpz [2][BTILES_MAX]
+    static constexpr int OFF_MBAR = OFF_TABS + 2 * BTILES_MAX * 4; // mbarriers: full[2], mma; tensor-memory base address
+    static constexpr int OFF_A = (OFF_MBAR + 32 + 127) / 128 * 128;  // a panels [1 or 2 buffers][hi | lo], then 2 copy stages
+    static_assert(OFF_TLO % 128 == 0 && OFF_MBAR % 8 == 0 && (A_WORDS * 4) % 128 == 0, "smem alignment");
+    // stage: F, then R with extra all-zero entries (padding rows point at the first), then the Q slice
+    __host__ __device__ static int stage_bytes(int nrad) { return F_BYTES + (nrad + 4) * 32 + BQ_MAX * 32; }
+    __host__ __device__ static int smem_bytes(int nrad, bool adouble) {
+        return OFF_A + 2 * A_WORDS * 4 * (adouble ? 2 : 1) + 2 * stage_bytes(nrad);
+    }
+};
 
 struct DevPlanB {
     int order, dim, H;
-    int ngroups, nsplit;
+    int ngroups;             // row groups
+    int gpr, nrounds;        // row groups per round, rounds: one launch of the contraction kernel per round (see z3d_api.cu)
     int nrad, nq;            // entries per chunk of the R and Q tables
     int adouble;             // 1: two a-panel buffers fit in shared memory (the a panels of a chunk are then produced while the
                              //    previous chunk's MMAs run)
-    const int2 *rowtab;      // [ngroups][BROWS_MAX]   (R index, Q index relative to the group's slice); padding -> zero entry
-    const int *tile_mpz;     // [ngroups][BTILES]      a-panel index of each tile
-    const int *mpz;          // [ngroups][BMPZ_MAX]    m | pz << 16 of each a panel, -1 padded
+    const int2 *rowtab;      // [ngroups][ROWS]   (R index, Q index relative to the group's slice); padding -> zero entry
+    const int *tile_mpz;     // [ngroups][BTILES_MAX]     a-panel index of each tile
+    const int *mpz;          // [ngroups][BTILES_MAX]    m | pz << 16 of each a panel, -1 padded
     const int *nmpz;         // [ngroups]
     const int *ntile;        // [ngroups]
     const int *qlo, *qlen;   // [ngroups]              the row group's slice of the Q table
@@ -93,17 +97,16 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned saddr, unsigned
     return (unsigned long long)((saddr >> 4) & 0x3fff) | ((unsigned long long)((lbo >> 4) & 0x3fff) << 16) |
            ((unsigned long long)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);  // bits 46-47: descriptor version 1
 }
-// instruction descriptor: D float32, A and B TF32, both K-major, N = 64, M = 128
-constexpr unsigned UMMA_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BCOL >> 3) << 17) | ((unsigned)(BTM >> 4) << 24);
-
-__device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long a, unsigned long long b, unsigned accumulate) {
+__device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long a, unsigned long long b, unsigned idesc,
+                                          unsigned accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a), "l"(b), "r"(UMMA_IDESC), "r"(accumulate) : "memory");
+                 ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(unsigned mbar) {  // the mbarrier completes a phase when all MMAs issued so far retire
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+#pragma unroll 1
     for (int it = 0; it < (1 << 26); ++it) {
         unsigned ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
@@ -248,14 +251,15 @@ __global__ void __launch_bounds__(1024) k_build_basis(const BasisArgs A) {
 // Folds of a tile of volumes: F[chunk][set][combo][volume][k] = 8-point Walsh-Hadamard transform of the mirror images of
 // voxel k of the chunk's row group (set 0) and of its transpose (set 1; zero on the diagonal).  One CTA per chunk.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(2 * BNV * KC) k_fold_tile(const float *__restrict__ vol, int nvol, int N, int H,
+template <int NV>
+__global__ void __launch_bounds__(2 * NV * KC) k_fold_tile(const float *__restrict__ vol, int nvol, int N, int H,
                                                             float *__restrict__ Ft) {
     const int CPR = (H + KC - 1) / KC;
     const long long chunk = blockIdx.x;
     ChunkPos p;
     chunk_pos(chunk, CPR, H, p);
     const int tid = threadIdx.x;
-    const int k = tid % KC, b = (tid / KC) % BNV, set = tid / (KC * BNV);
+    const int k = tid % KC, b = (tid / KC) % NV, set = tid / (KC * NV);
     const int kk = p.kc * KC + k, k2 = N - 1 - kk;
     const int ri = set ? p.jp : p.ip, rj = set ? p.ip : p.jp;
     const int i2 = N - 1 - ri, j2 = N - 1 - rj;
@@ -269,9 +273,9 @@ __global__ void __launch_bounds__(2 * BNV * KC) k_fold_tile(const float *__restr
         v[img] = (live && !dup) ? __ldg(vb + ((size_t)(sy ? i2 : ri) * N + (sx ? j2 : rj)) * N + (sz ? k2 : kk)) : 0.0f;
     }
     wht8(v);
-    float *dst = Ft + (size_t)chunk * (BF_BYTES / 4);
+    float *dst = Ft + (size_t)chunk * (BCfg<NV>::F_BYTES / 4);
 #pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) dst[((set * 8 + c8) * BNV + b) * KC + (k ^ (((b >> 2) & 1) << 2))] = v[c8];
+    for (int c8 = 0; c8 < 8; ++c8) dst[((set * 8 + c8) * NV + b) * KC + (k ^ (((b >> 2) & 1) << 2))] = v[c8];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -286,34 +290,67 @@ struct CtxB {
 };
 // T row = R * Q of this thread's row: loads, products and the TF32 split (registers only) ...
 struct TRow {
-    float4 h0, h1, l0, l1;
-};
+    float4 t0, t1;  // the eight float32 products; the TF32 split happens at the store: 8 live registers, not 16 (with 12
+};                  // or 16 the compiler spills them across the MMA wait, and the reload sits on the critical path)
+template <int F_BYTES>
 __device__ __forceinline__ TRow t_compute(const CtxB &c, const float *stage, int nrad, int qlo, int row) {
-    const float *Rs = stage + BF_BYTES / 4, *Qs = Rs + (nrad + 4) * KC;
+    const float *Rs = stage + F_BYTES / 4, *Qs = Rs + (nrad + 4) * KC;
     const ushort2 rq = c.rowtab[row];
     const float *rp = Rs + rq.x * KC, *qp = Qs + rq.y * KC;
     const int sr = ((rq.x >> 2) & 1) << 2, sq = (((rq.y + qlo) >> 2) & 1) << 2;  // the tables' k-half swizzle
     const float4 r0 = *reinterpret_cast<const float4 *>(rp + sr), r1 = *reinterpret_cast<const float4 *>(rp + (4 ^ sr));
     const float4 q0 = *reinterpret_cast<const float4 *>(qp + sq), q1 = *reinterpret_cast<const float4 *>(qp + (4 ^ sq));
     TRow t;
-    split_tf32(r0.x * q0.x, t.h0.x, t.l0.x); split_tf32(r0.y * q0.y, t.h0.y, t.l0.y);
-    split_tf32(r0.z * q0.z, t.h0.z, t.l0.z); split_tf32(r0.w * q0.w, t.h0.w, t.l0.w);
-    split_tf32(r1.x * q1.x, t.h1.x, t.l1.x); split_tf32(r1.y * q1.y, t.h1.y, t.l1.y);
-    split_tf32(r1.z * q1.z, t.h1.z, t.l1.z); split_tf32(r1.w * q1.w, t.h1.w, t.l1.w);
+    t.t0 = make_float4(r0.x * q0.x, r0.y * q0.y, r0.z * q0.z, r0.w * q0.w);
+    t.t1 = make_float4(r1.x * q1.x, r1.y * q1.y, r1.z * q1.z, r1.w * q1.w);
     return t;
 }
-// ... and its four 16-byte stores into the operand panels, once the previous chunk's MMAs have released them
-__device__ __forceinline__ void t_store(const CtxB &c, const TRow &t, int row) {
-    *reinterpret_cast<float4 *>(c.Thi + row * 4) = t.h0;
-    *reinterpret_cast<float4 *>(c.Thi + (BROWS_MAX + row) * 4) = t.h1;
-    *reinterpret_cast<float4 *>(c.Tlo + row * 4) = t.l0;
-    *reinterpret_cast<float4 *>(c.Tlo + (BROWS_MAX + row) * 4) = t.l1;
+__device__ __forceinline__ void split4(const float4 &x, float4 &hi, float4 &lo) {
+    split_tf32(x.x, hi.x, lo.x);
+    split_tf32(x.y, hi.y, lo.y);
+    split_tf32(x.z, hi.z, lo.z);
+    split_tf32(x.w, hi.w, lo.w);
 }
+// ... and its split and four 16-byte stores into the operand panels, once the previous chunk's MMAs have released them
+template <int ROWS>
+__device__ __forceinline__ void t_store(const CtxB &c, const TRow &t, int row) {
+    float4 hi, lo;
+    split4(t.t0, hi, lo);
+    *reinterpret_cast<float4 *>(c.Thi + row * 4) = hi;
+    *reinterpret_cast<float4 *>(c.Tlo + row * 4) = lo;
+    split4(t.t1, hi, lo);
+    *reinterpret_cast<float4 *>(c.Thi + (ROWS + row) * 4) = hi;
+    *reinterpret_cast<float4 *>(c.Tlo + (ROWS + row) * 4) = lo;
+}
+// the same for one k half (4 voxels) of a row: the 64-volume kernel has two threads per row
+struct THalf {
+    float4 t;
+};
+template <int F_BYTES>
+__device__ __forceinline__ THalf t_compute_half(const CtxB &c, const float *stage, int nrad, int qlo, int row, int kh) {
+    const float *Rs = stage + F_BYTES / 4, *Qs = Rs + (nrad + 4) * KC;
+    const ushort2 rq = c.rowtab[row];
+    const int sr = ((rq.x >> 2) & 1) << 2, sq = (((rq.y + qlo) >> 2) & 1) << 2;  // the tables' k-half swizzle
+    const float4 r = *reinterpret_cast<const float4 *>(Rs + rq.x * KC + ((4 * kh) ^ sr));
+    const float4 q = *reinterpret_cast<const float4 *>(Qs + rq.y * KC + ((4 * kh) ^ sq));
+    THalf t;
+    t.t = make_float4(r.x * q.x, r.y * q.y, r.z * q.z, r.w * q.w);
+    return t;
+}
+template <int ROWS>
+__device__ __forceinline__ void t_store_half(const CtxB &c, const THalf &t, int row, int kh) {
+    float4 hi, lo;
+    split4(t.t, hi, lo);
+    *reinterpret_cast<float4 *>(c.Thi + (kh * ROWS + row) * 4) = hi;
+    *reinterpret_cast<float4 *>(c.Tlo + (kh * ROWS + row) * 4) = lo;
+}
+template <int NV>
 __device__ __forceinline__ void a_products(const CtxB &c, const float *stage, int nmpz, const float *__restrict__ trig, float comp) {
+    constexpr int BNV = NV, BCOL = 2 * NV;
     const int tid = threadIdx.x;
     const float *Fs = stage;
-    for (int it = tid; it < nmpz * (2 * BNV); it += BNPROD) {  // (panel, re / im, volume); producer threads only
-        const int b = it & (BNV - 1), reim = (it >> 5) & 1, j = it >> 6;
+    for (int it = tid; it < nmpz * BCOL; it += BNPROD) {  // (panel, re / im, volume); producer threads only
+        const int b = it % NV, reim = (it / NV) & 1, j = it / BCOL;
         const int code = c.mpz[j], m = code & 0xffff, pz = code >> 16;
         const int comb = (reim << 2) | (((m & 1) ^ reim) << 1) | pz;
         float tA = __ldg(trig + reim * (LMAX + 1) + m), tB = __ldg(trig + (2 + reim) * (LMAX + 1) + m);
@@ -339,30 +376,34 @@ __device__ __forceinline__ void a_products(const CtxB &c, const float *stage, in
 
 // one thread: the three TF32 products of every tile of the chunk, then a commit that completes the mbarrier phase when
 // they (and their shared-memory reads) have retired
+template <int NV>
 __device__ __forceinline__ void issue_mma(const CtxB &c, unsigned tmem, int ntile, bool accumulate, unsigned mbar) {
+    constexpr int BCOL = BCfg<NV>::COL, BROWS_MAX = BCfg<NV>::ROWS;
+    // instruction descriptor: D float32, A and B TF32, both K-major, N = COL, M = 128
+    constexpr unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BCOL >> 3) << 17) | ((unsigned)(BTM >> 4) << 24);
     const unsigned long long dThi = umma_desc(smem_u32(c.Thi), BROWS_MAX * 16, 128), dTlo = umma_desc(smem_u32(c.Tlo), BROWS_MAX * 16, 128);
     const unsigned long long dAhi = umma_desc(smem_u32(c.Ahi), BCOL * 16, 128), dAlo = umma_desc(smem_u32(c.Alo), BCOL * 16, 128);
     for (int t = 0; t < ntile; ++t) {
         const unsigned long long ta = (unsigned long long)(t * BTM * 16 >> 4), aa = (unsigned long long)(c.tile_mpz[t] * 2 * BCOL * 16 >> 4);
         const unsigned d = tmem + t * BCOL;
-        umma_tf32(d, dTlo + ta, dAhi + aa, accumulate ? 1u : 0u);  // small terms first
-        umma_tf32(d, dThi + ta, dAlo + aa, 1u);
-        umma_tf32(d, dThi + ta, dAhi + aa, 1u);
+        umma_tf32(d, dTlo + ta, dAhi + aa, idesc, accumulate ? 1u : 0u);  // small terms first
+        umma_tf32(d, dThi + ta, dAlo + aa, idesc, 1u);
+        umma_tf32(d, dThi + ta, dAhi + aa, idesc, 1u);
     }
     umma_commit(mbar);
 }
 
-// accumulators -> this CTA's partial buffer [tile][column][row] (float32, round to nearest); warp w reads the lane
-// quarter w % 4 (the only one it can address) of tile w / 4
-__device__ __forceinline__ void flush_accumulators(unsigned tmem, int ntile, float *out, bool add) {
+// accumulators -> this CTA's partial buffer [tensor-memory column][row] (float32, round to nearest); warp w reads the lane
+// quarter w % 4 (the only one it can address) of the 64 columns 64 (w / 4) .. 64 (w / 4) + 63
+__device__ __forceinline__ void flush_accumulators(unsigned tmem, int ncols, float *out, bool add) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3;
 #pragma unroll 1
-    for (int t = warp >> 2; t < ntile; t += BNWARP / 4) {
+    for (int c64 = 64 * (warp >> 2); c64 < ncols; c64 += 64 * (BNWARP / 4)) {
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             unsigned v[32];
-            tmem_ld32(tmem + ((unsigned)(32 * q) << 16) + t * BCOL + 32 * half, v);
-            float *p = out + ((size_t)t * BCOL + 32 * half) * BTM + 32 * q + lane;
+            tmem_ld32(tmem + ((unsigned)(32 * q) << 16) + c64 + 32 * half, v);
+            float *p = out + ((size_t)c64 + 32 * half) * BTM + 32 * q + lane;
             if (add) {
 #pragma unroll
                 for (int col = 0; col < 32; ++col) p[col * BTM] += __uint_as_float(v[col]);
@@ -374,37 +415,46 @@ __device__ __forceinline__ void flush_accumulators(unsigned tmem, int ntile, flo
     }
 }
 
-// partial layout: [ngroups][nsplit][BSLOT_WORDS]
+// partial layout: [round][CTA of the round][BSLOT_WORDS]
 //
 // Per chunk t (stage s = t & 1):  wait full[s] (bulk copies of chunk t)  |  wait for the MMAs of chunk t-1 (panels free)
 //   | products  |  barrier  |  one thread: MMAs of chunk t (asynchronous) + the bulk copies of chunk t+2 into stage s.
+// One launch per ROUND of row groups: CTAs [0, groups x cpg) - group g0 + blockIdx / cpg, split blockIdx % cpg of the
+// launch's chunk range.  All CTAs of a launch sweep the chunk list in lock step, so the R / Q / F data of a chunk is
+// fetched from DRAM once per round and served to the round's row groups from L2 (see z3d_api.cu for the choice of rounds).
+template <int NV>
 __global__ void __launch_bounds__(BNT, 1)
-k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, int nparts, float *__restrict__ partial) {
+k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, int nparts, int g0, int cpg,
+                    float *__restrict__ partial /* slots of this round */) {
+    using G = BCfg<NV>;
+    constexpr int BROWS_MAX = G::ROWS, BF_BYTES = G::F_BYTES, BA_WORDS = G::A_WORDS;
+    constexpr int BOFF_THI = G::OFF_THI, BOFF_TLO = G::OFF_TLO, BOFF_ROWTAB = G::OFF_ROWTAB, BOFF_TABS = G::OFF_TABS;
+    constexpr int BOFF_MBAR = G::OFF_MBAR, BOFF_A = G::OFF_A;
     extern __shared__ __align__(16) unsigned char smem[];
     const int H = P.H, nrad = P.nrad;
     const int tid = threadIdx.x;
-    const int grp = blockIdx.x % P.ngroups, split = blockIdx.x / P.ngroups;
+    const int grp = g0 + blockIdx.x / cpg, split = blockIdx.x % cpg;
     CtxB c;
     c.Thi = reinterpret_cast<float *>(smem + BOFF_THI);
     c.Tlo = reinterpret_cast<float *>(smem + BOFF_TLO);
     ushort2 *rowtab = reinterpret_cast<ushort2 *>(smem + BOFF_ROWTAB);
-    int *mpz = reinterpret_cast<int *>(smem + BOFF_TABS), *tile_mpz = mpz + BTILES;
+    int *mpz = reinterpret_cast<int *>(smem + BOFF_TABS), *tile_mpz = mpz + BTILES_MAX;
     c.rowtab = rowtab;
     c.mpz = mpz;
     c.tile_mpz = tile_mpz;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + BOFF_MBAR);
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + BOFF_MBAR + 24);
-    const int stage_bytes = batched_stage_bytes(nrad);
+    const int stage_bytes = G::stage_bytes(nrad);
     const int adouble = P.adouble;
     float *abase = reinterpret_cast<float *>(smem + BOFF_A);
     unsigned char *stage0 = smem + BOFF_A + 2 * BA_WORDS * 4 * (adouble ? 2 : 1);
     // ---- tables of this row group -> smem; zero the panels and the stages (padding rows read the zero R entry)
-    for (int i = tid; i < BTILES; i += BNT) {
-        mpz[i] = P.mpz[grp * BMPZ_MAX + i];
-        tile_mpz[i] = P.tile_mpz[grp * BTILES + i];
+    for (int i = tid; i < BTILES_MAX; i += BNT) {
+        mpz[i] = P.mpz[grp * BTILES_MAX + i];
+        tile_mpz[i] = P.tile_mpz[grp * BTILES_MAX + i];
     }
     for (int i = tid; i < BROWS_MAX; i += BNT) {
-        const int2 rq = P.rowtab[grp * BROWS_MAX + i];
+        const int2 rq = P.rowtab[(size_t)grp * BROWS_MAX + i];
         rowtab[i] = make_ushort2((unsigned short)rq.x, (unsigned short)rq.y);
     }
     for (int i = tid; i < BOFF_ROWTAB / 4; i += BNT) reinterpret_cast<float *>(smem)[i] = 0.0f;
@@ -430,8 +480,8 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
     const int CPR = (H + KC - 1) / KC;
     const long long total = (long long)analysis_items(0, H, H) * CPR;
     const long long gbeg = total * part / nparts, glen = total * (part + 1) / nparts - gbeg;
-    const long long cbeg = gbeg + glen * split / P.nsplit, cend = gbeg + glen * (split + 1) / P.nsplit;
-    float *out = partial + ((size_t)(grp * P.nsplit + split)) * BSLOT_WORDS;
+    const long long cbeg = gbeg + glen * split / cpg, cend = gbeg + glen * (split + 1) / cpg;
+    float *out = partial + (size_t)blockIdx.x * BSLOT_WORDS;
     const unsigned rbytes = (unsigned)nrad * 32u, qbytes = (unsigned)qlen * 32u;
 
     // one thread: F, R and the Q slice of chunk cc -> stage s, completion on full[s]
@@ -465,32 +515,45 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
         // (other buffer) and the T products, which stay in registers until the MMAs have retired.  Warps 0-30 produce
         // (one row per thread, warp 0 also the last 32 rows); warp 31 only issues, so that the ~24 MMA issues and 3 copy
         // descriptors per chunk do not delay a producer warp the whole block would then wait for at the barrier.
-        const bool producer = tid < BNPROD, two_rows = tid < BROWS_MAX - BNPROD;
+        // 64-volume tiles have 512 rows: two threads per row, lanes 0-15 of a warp the first k half of 16 consecutive rows,
+        // lanes 16-31 the second (conflict-free loads and stores); warp 0 also does the 16 rows of the issuing warp.
+        const bool producer = tid < BNPROD, two_rows = tid < BNT - BNPROD;
+        const int hrow = (tid >> 5) * 16 + (tid & 15), hkh = (tid >> 4) & 1;
         TRow trow;
+        THalf thalf;
         if (producer) {
-            if (adouble) a_products(c, stage, nmpz, trig, comp);
-            trow = t_compute(c, stage, nrad, qlo, tid);
+            if (adouble) a_products<NV>(c, stage, nmpz, trig, comp);
+            if constexpr (NV == 32) trow = t_compute<BF_BYTES>(c, stage, nrad, qlo, tid);
+            else thalf = t_compute_half<BF_BYTES>(c, stage, nrad, qlo, hrow, hkh);
         }
         if (t) {  // the previous chunk's MMAs have retired: the operand panels are free, the accumulators current
             mbar_wait(mbar, (t - 1) & 1);
             tc_fence_after();
         }
         if (since_flush == BFLUSH_CHUNKS) {
-            flush_accumulators(tmem, ntile, out, flushed);
+            flush_accumulators(tmem, ntile * G::COL, out, flushed);
             flushed = true;
             since_flush = 0;
             tc_fence_before();
         }
         if (producer) {
-            if (!adouble) a_products(c, stage, nmpz, trig, comp);
-            t_store(c, trow, tid);
-            if (two_rows) t_store(c, t_compute(c, stage, nrad, qlo, BNPROD + tid), BNPROD + tid);
+            if (!adouble) a_products<NV>(c, stage, nmpz, trig, comp);
+            if constexpr (NV == 32) {
+                t_store<BROWS_MAX>(c, trow, tid);
+                if (two_rows) t_store<BROWS_MAX>(c, t_compute<BF_BYTES>(c, stage, nrad, qlo, BNPROD + tid), BNPROD + tid);
+            } else {
+                t_store_half<BROWS_MAX>(c, thalf, hrow, hkh);
+                if (two_rows) {
+                    const int v = BNPROD + tid, row = (v >> 5) * 16 + (v & 15), kh = (v >> 4) & 1;
+                    t_store_half<BROWS_MAX>(c, t_compute_half<BF_BYTES>(c, stage, nrad, qlo, row, kh), row, kh);
+                }
+            }
         }
         fence_async_smem();  // generic-proxy panel writes -> visible to the tensor core's async-proxy reads
         __syncthreads();     // panels complete; everybody is done reading stage s
         if (tid == BNPROD) {
             tc_fence_after();
-            issue_mma(c, tmem, ntile, since_flush > 0, mbar);
+            issue_mma<NV>(c, tmem, ntile, since_flush > 0, mbar);
             if (cc + 2 < cend) issue_copies(cc + 2, s);
         }
         ++since_flush;
@@ -498,7 +561,7 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
     if (t) {
         mbar_wait(mbar, (t - 1) & 1);
         tc_fence_after();
-        flush_accumulators(tmem, ntile, out, flushed);
+        flush_accumulators(tmem, ntile * G::COL, out, flushed);
     } else {
         for (int i = tid; i < BSLOT_WORDS; i += BNT) out[i] = 0.0f;  // the reduction reads every split
     }
@@ -508,18 +571,23 @@ k_decompose_batched(const DevPlanB P, const float *__restrict__ Ft, int part, in
 }
 
 // moments[b][mu][reim] = scale[mu] * sum over splits of the owning accumulator (fixed order, float64)
+template <int NV>
 __global__ void k_reduce_batched(const float *__restrict__ partial, const int2 *__restrict__ rowmap /* [nmom] (group, row) */,
-                                 const double *__restrict__ scale, int nmom, int nsplit, int nvol,
+                                 const double *__restrict__ scale, int nmom, int ngroups, int gpr, int nctas, int nvol,
                                  float *__restrict__ moments) {
+    constexpr int BNV = NV, BCOL = 2 * NV;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over nmom * BCOL
     if (idx >= nmom * BCOL) return;
     const int mu = idx / BCOL, col = idx % BCOL;
     const int reim = col / BNV, b = col % BNV;
     if (b >= nvol) return;
     const int2 gr = rowmap[mu];
-    const float *p = partial + (size_t)gr.x * nsplit * BSLOT_WORDS + ((size_t)(gr.y / BTM) * BCOL + col) * BTM + gr.y % BTM;
+    // slots are [round][CTA of the round's launch]: nctas per round, the group's CTAs are contiguous in split order
+    const int round = gr.x / gpr, first = round * gpr, grn = min(gpr, ngroups - first), cpg = nctas / grn;
+    const float *p = partial + ((size_t)round * nctas + (size_t)(gr.x - first) * cpg) * BSLOT_WORDS +
+                     ((size_t)(gr.y / BTM) * BCOL + col) * BTM + gr.y % BTM;
     double sum = 0.0;
-    for (int s = 0; s < nsplit; ++s) sum += (double)p[(size_t)s * BSLOT_WORDS];
+    for (int s = 0; s < cpg; ++s) sum += (double)p[(size_t)s * BSLOT_WORDS];
     moments[((size_t)b * nmom + mu) * 2 + reim] = (float)(sum * scale[mu]);
 }
 

@@ -22,7 +22,8 @@ def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
 class Plan:
     INFO_KEYS = ("order", "dim", "num_moments", "passes", "ctas", "threads", "tiles_per_thread", "smem_bytes",
                  "voxels_per_chunk", "sms", "useful_accumulators", "padded_accumulators",
-                 "batched_min", "batched_row_groups", "batched_splits", "batched_tile_volumes")
+                 "batched_min", "batched_row_groups", "batched_row_groups_wide", "batched_wide_min", "batched_rounds",
+                 "batched_rounds_wide")
 
     def __init__(self, order: int, dim: int, device: int | None = None):
         if not torch.cuda.is_available():
@@ -48,8 +49,8 @@ class Plan:
 
     # ------------------------------------------------------------------ helpers
     def info(self) -> dict:
-        arr = (ctypes.c_int * 16)()
-        _lib.check(self._L.z3d_plan_info(self._h, arr, 16))
+        arr = (ctypes.c_int * 18)()
+        _lib.check(self._L.z3d_plan_info(self._h, arr, 18))
         return dict(zip(self.INFO_KEYS, list(arr)))
 
     def workspace_bytes(self, batch: int) -> int:
