@@ -2,6 +2,7 @@
 #include "../../include/zernike3d_b200.h"
 #include "z3d_kernels.cuh"
 #include "z3d_batched.cuh"
+#include "z3d_stream.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -74,6 +75,13 @@ struct z3d_plan {
     BasisArgs basis{};           // inputs of k_build_basis; the tables themselves are built on first use
     bool basis_ready = false;
     float *d_Rt = nullptr, *d_Qt = nullptr, *d_trig = nullptr;
+    // streamed-T variant of the batched path (z3d_stream.cuh): preferred whenever its T table fits in device memory
+    bool stream = false, stream_ready = false;
+    DevPlanS devs{};
+    int s_smem = 0, s_ncols_all = 0;
+    int4 *d_colsrc = nullptr;
+    int2 *d_colmap = nullptr;
+    float *d_Tt = nullptr;
     // reduce / prepare tables
     int *d_src = nullptr;        // [2*nmom]  pass*SLOT_WORDS + word
     double *d_scale = nullptr;   // [nmom]    coeff(n) * kappa_lm
@@ -454,6 +462,165 @@ void build_batched_plan(int L, int num_sms, int tiles_per_group, const HostPlan 
     hb.ok = true;
 }
 
+// ---- planner of the streamed-T variant (z3d_stream.cuh) -------------------------------------------------------------
+struct HostPlanS {
+    bool ok = false;
+    int nsets = 0, nsplits = 0, ncols_all = 0, t_bytes_max = 0;
+    long long trec = 0;
+    std::vector<StreamTabs> tabs;
+    std::vector<int4> colsrc;
+    std::vector<int2> colmap;
+};
+
+// Column sets: the moment rows of every (m, pz), padded to 16, are laid end to end in kind order ((m parity, pz), then
+// m) and cut into sets of equal estimated shared-memory traffic per chunk (64 + 96 B per column for the T block and the
+// tensor core's reads of it, ~28 KB per a panel), subject to <= 512 columns (tensor memory), <= S_PANELS panels, <= 2
+// kinds.  sets x splits <= SMs; the number of splits is the one with the smallest estimated time.
+void build_stream_plan(int L, int num_sms, const HostPlanB &hb, HostPlanS &hs, int force_splits) {
+    const int S = L + 1;
+    struct Row { int n, l, m; };
+    struct Group { int kind, m, pz; std::vector<Row> rows; };
+    std::vector<Group> groups;
+    for (int mp = 0; mp < 2; ++mp)
+        for (int pz = 0; pz < 2; ++pz)
+            for (int m = mp; m <= L; m += 2) {
+                Group g{(mp << 1) | pz, m, pz, {}};
+                for (int l = m + pz; l <= L; l += 2)
+                    for (int n = l; n <= L; n += 2) g.rows.push_back({n, l, m});
+                if (!g.rows.empty()) groups.push_back(std::move(g));
+            }
+    struct Piece { int group, first, cols; };
+    typedef std::vector<std::vector<Piece>> Sets;
+    const double CA = 160.0, CB = 28000.0, CK = 16384.0;
+    auto set_cost = [&](const std::vector<Piece> &st) {
+        double c = 0.0;
+        int k0 = -1, nk = 0;
+        for (const Piece &p : st) {
+            c += CB + CA * p.cols;
+            if (groups[p.group].kind != k0) { k0 = groups[p.group].kind; ++nk; }
+        }
+        return c + CK * nk;
+    };
+    auto pack = [&](double cap) {
+        Sets sets;
+        std::vector<Piece> cur;
+        double cost = 0.0;
+        int cols = 0, segs = 0, k_first = -1, k_last = -1;
+        auto close = [&]() {
+            if (!cur.empty()) sets.push_back(cur);
+            cur.clear(); cost = 0.0; cols = 0; segs = 0; k_first = k_last = -1;
+        };
+        for (int gi = 0; gi < (int)groups.size(); ++gi) {
+            const int kind = groups[gi].kind;
+            int rem = ((int)groups[gi].rows.size() + 15) / 16 * 16, first = 0;
+            while (rem > 0) {
+                const bool newkind = !cur.empty() && kind != k_last;
+                const double kc = (cur.empty() || newkind) ? CK : 0.0;
+                int room = std::min(512 - cols, (int)((cap - cost - CB - kc) / CA) / 16 * 16);
+                if ((int)cur.size() >= S_PANELS || segs + 1 > S_SEGS || room < 16 || (newkind && k_first != k_last)) {
+                    if (cur.empty()) room = 16; else { close(); continue; }
+                }
+                int take = std::min(rem, room);
+                if (take > 256 && segs + 2 > S_SEGS) take = 256;
+                if (cur.empty()) k_first = kind;
+                k_last = kind;
+                cur.push_back({gi, first, take});
+                cost += CB + kc + CA * take;
+                cols += take;
+                segs += take > 256 ? 2 : 1;
+                first += take;
+                rem -= take;
+            }
+        }
+        close();
+        return sets;
+    };
+    Sets best;
+    double best_t = 1e300;
+    int best_splits = 0;
+    for (int ns = 1; ns <= 12; ++ns) {
+        if (force_splits > 0 && ns != force_splits) continue;
+        const int target = num_sms / ns;
+        if (target < 1) break;
+        double lo = CB, hi = 4e6;
+        if ((int)pack(hi).size() > target) continue;
+        for (int it = 0; it < 40; ++it) {
+            const double mid = 0.5 * (lo + hi);
+            if ((int)pack(mid).size() > target) lo = mid; else hi = mid;
+        }
+        Sets st = pack(hi);
+        double mx = 0.0;
+        for (auto &x : st) mx = std::max(mx, set_cost(x));
+        const double t = (mx + 20000.0) / ns;  // + per-chunk synchronisation overhead
+        if (t < best_t) { best_t = t; best = st; best_splits = ns; }
+    }
+    if (best.empty()) return;
+    hs.nsets = (int)best.size();
+    hs.nsplits = best_splits;
+    hs.tabs.assign(hs.nsets, StreamTabs{});
+    hs.colmap.assign(num_moments(L), make_int2(-1, -1));
+    std::vector<int> mubase((size_t)S * S, -1);
+    {
+        int mu = 0;
+        for (int n = 0; n <= L; ++n)
+            for (int l = n & 1; l <= n; l += 2) {
+                mubase[(size_t)n * S + l] = mu;
+                mu += l + 1;
+            }
+    }
+    long long toff = 0;
+    for (int si = 0; si < hs.nsets; ++si) {
+        StreamTabs &T = hs.tabs[si];
+        int cols = 0;
+        for (const Piece &p : best[si]) cols += p.cols;
+        T.ncols = cols;
+        T.toff = toff;
+        T.kind[0] = T.kind[1] = 0;
+        int off = 0;
+        for (const Piece &p : best[si]) {
+            const Group &g = groups[p.group];
+            int slot = -1;
+            for (int q = 0; q < T.nkind; ++q)
+                if (T.kind[q] == g.kind) slot = q;
+            if (slot < 0) {
+                if (T.nkind >= S_KINDS) return;
+                slot = T.nkind;
+                T.kind[T.nkind++] = g.kind;
+            }
+            if (T.npanel >= S_PANELS) return;
+            const int j = T.npanel++;
+            T.panel_code[j] = g.m | (g.pz << 16) | (slot << 24);
+            for (int c0 = 0; c0 < p.cols; c0 += 256) {
+                if (T.nseg >= S_SEGS) return;
+                T.seg_cols[T.nseg] = std::min(256, p.cols - c0);
+                T.seg_off[T.nseg] = off + c0;
+                T.seg_panel[T.nseg] = j;
+                ++T.nseg;
+            }
+            for (int c = 0; c < p.cols; ++c) {
+                const int ri = p.first + c;
+                int4 cs = make_int4(-1, 0, (int)(toff + (long long)(off + c) * 4), cols);
+                if (ri < (int)g.rows.size()) {
+                    const Row &r = g.rows[ri];
+                    cs.x = hb.rbase[r.l] + (r.n - r.l) / 2;
+                    cs.y = hb.qoff[r.m] + (r.l - r.m);
+                    hs.colmap[mubase[(size_t)r.n * S + r.l] + r.m] = make_int2(si, off + c);
+                }
+                hs.colsrc.push_back(cs);
+            }
+            off += p.cols;
+        }
+        if (cols > 512 || toff + 16LL * cols > 0x7fffffffLL) return;
+        hs.t_bytes_max = std::max(hs.t_bytes_max, cols * 64);
+        toff += 16LL * cols;
+    }
+    hs.trec = toff;
+    hs.ncols_all = (int)hs.colsrc.size();
+    for (const int2 &r : hs.colmap)
+        if (r.x < 0) return;
+    hs.ok = true;
+}
+
 template <int NPH>
 int set_kernel_attrs_t(int smem) {
     CUDA_TRY(cudaFuncSetAttribute(k_decompose<NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -470,6 +637,8 @@ int set_kernel_attrs(int smem) {
     CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_stream, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return set_kernel_attrs_t<0>(smem);
 }
 
@@ -570,6 +739,7 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
 
     // dim >= 14 keeps every 8-voxel chunk and its z-mirror inside a row (k_fold_tile reads both)
     pl->batched = dim >= 14;
+    HostPlanB hb0;
     for (int v = 0; v < 2 && pl->batched; ++v) {
         HostPlanB hb;
         build_batched_plan(order, prop.multiProcessorCount, v ? BCfg<64>::TILES : BCfg<32>::TILES, hp, hb);
@@ -596,6 +766,31 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
             a.order = order; a.dim = dim; a.H = pl->H; a.nrad = hb.nrad; a.nq = hb.nq; a.side = d_side;
             a.rk = d_brk; a.rbase = d_brbase; a.gd = d_bgd; a.goff = d_bgoff; a.qoff = d_qoff;
             pl->b_chunks = (long long)analysis_items(0, pl->H, pl->H) * ((pl->H + KC - 1) / KC);
+            hb0 = hb;
+        }
+    }
+    if (pl->batched) {  // streamed-T variant: tables only; the T table itself is built on first use (ensure_stream)
+        HostPlanS hs;
+        int force = 0;
+        if (const char *e = getenv("Z3D_STREAM_SPLITS")) force = atoi(e);
+        const char *off = getenv("Z3D_STREAM");
+        if (!(off && atoi(off) == 0)) build_stream_plan(order, prop.multiProcessorCount, hb0, hs, force);
+        if (hs.ok) {
+            DevPlanS &d2 = pl->devs;
+            d2.order = order; d2.dim = dim; d2.H = pl->H; d2.nsets = hs.nsets; d2.nsplits = hs.nsplits;
+            d2.t_bytes_max = hs.t_bytes_max;
+            d2.stage_bytes = hs.t_bytes_max + S_KINDS * S_FK_BYTES;
+            d2.nstages = std::min(S_MAX_STAGES, ((int)prop.sharedMemPerBlockOptin - S_OFF_A - S_A_TOTAL) / d2.stage_bytes);
+            if (const char *e = getenv("Z3D_STREAM_STAGES")) d2.nstages = std::min(d2.nstages, std::max(2, atoi(e)));
+            d2.trec = hs.trec;
+            if (d2.nstages >= 2) {
+                StreamTabs *d_tabs;
+                UP(hs.tabs, d_tabs) UP(hs.colsrc, pl->d_colsrc) UP(hs.colmap, pl->d_colmap)
+                d2.tabs = d_tabs;
+                pl->s_smem = S_OFF_A + S_A_TOTAL + d2.nstages * d2.stage_bytes;
+                pl->s_ncols_all = hs.ncols_all;
+                pl->stream = true;
+            }
         }
     }
 #undef UP
@@ -618,6 +813,7 @@ extern "C" int z3d_plan_destroy(z3d_plan *pl) {
     if (pl->d_Rt) cudaFree(pl->d_Rt);
     if (pl->d_Qt) cudaFree(pl->d_Qt);
     if (pl->d_trig) cudaFree(pl->d_trig);
+    if (pl->d_Tt) cudaFree(pl->d_Tt);
     for (int i = 0; i < 2; ++i) {
         if (pl->d_stage_vol[i]) cudaFree(pl->d_stage_vol[i]);
         if (pl->d_stage_mom[i]) cudaFree(pl->d_stage_mom[i]);
@@ -658,7 +854,7 @@ static size_t ws_decompose(const z3d_plan *pl, int batch) {
     size_t w = (size_t)std::min(batch, decompose_group(pl)) * pl->npass * pl->nsplit * SLOT_WORDS * sizeof(float);
     if (pl->batched && batch >= pl->batched_min)  // per-(CTA, segment) partial sums + the folds of one tile of volumes
         w = std::max(w, (size_t)pl->num_sms * std::max(pl->devb[0].nrounds, pl->devb[1].nrounds) * BSLOT_WORDS * sizeof(float) +
-                            (size_t)pl->b_chunks * (batch >= pl->batched_wide ? BCfg<64>::F_BYTES : BCfg<32>::F_BYTES));
+                            (size_t)pl->b_chunks * ((pl->stream || batch >= pl->batched_wide) ? BCfg<64>::F_BYTES : BCfg<32>::F_BYTES));
     return w;
 }
 static size_t ws_reconstruct(const z3d_plan *pl, int batch) {
@@ -722,6 +918,31 @@ static int ensure_basis(z3d_plan *pl, cudaStream_t st) {
     return Z3D_OK;
 }
 
+// T table of the streamed variant (13.7 GB at 128^3 / order 50): built from the R / Q tables on the first batched call when it
+// fits in 45 % of the free device memory; otherwise the plan keeps to k_decompose_batched (R / Q tables, products in-kernel).
+static int ensure_stream(z3d_plan *pl, cudaStream_t st) {
+    if (pl->stream_ready || !pl->stream || !pl->batched || !pl->basis_ready) return Z3D_OK;
+    const size_t bytes = (size_t)pl->b_chunks * (size_t)pl->devs.trec * sizeof(float);
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    size_t limit = (size_t)(0.45 * (double)free_b);
+    if (const char *e = getenv("Z3D_STREAM_MAX_GB")) limit = std::min(limit, (size_t)(atof(e) * 1e9));
+    if (bytes > limit || cudaMalloc((void **)&pl->d_Tt, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        pl->d_Tt = nullptr;
+        pl->stream = false;
+        return Z3D_OK;
+    }
+    pl->devs.Tt = pl->d_Tt;
+    pl->devs.trig = pl->d_trig;
+    k_build_T<<<(unsigned)pl->b_chunks, 1024, 0, st>>>(pl->d_Rt, pl->d_Qt, pl->basis.nrad, pl->basis.nq, pl->d_colsrc,
+                                                        pl->s_ncols_all, pl->devs.trec, pl->d_Tt);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    pl->stream_ready = true;
+    return Z3D_OK;
+}
+
 static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int half_lo, int half_hi, int part, int nparts,
                           float *d_moments, void *d_ws, size_t ws_bytes, void *stream) {
     int rc = check_range(pl, batch, half_lo, half_hi, "z3d_decompose");
@@ -743,6 +964,27 @@ static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int
     if (pl->batched && half_lo == 0 && half_hi == pl->H && batch >= pl->batched_min) {
         rc = ensure_basis(mpl, st);
         if (rc) return rc;
+        rc = ensure_stream(mpl, st);
+        if (rc) return rc;
+    }
+    while (pl->batched && pl->stream_ready && half_lo == 0 && half_hi == pl->H && batch - done >= pl->batched_min) {
+        // streamed-T variant: tiles of up to 64 volumes (a tile costs the same whatever it holds)
+        const int nb = std::min(SNV, batch - done);
+        const DevPlanS &dp = pl->devs;
+        const float *vol = d_vol + (size_t)done * N3;
+        float *folds = partial + (size_t)pl->num_sms * std::max(pl->devb[0].nrounds, pl->devb[1].nrounds) * BSLOT_WORDS;
+        float *mom = d_moments + (size_t)done * 2 * pl->nmom;
+        k_fold_tile_kind<<<(unsigned)pl->b_chunks, 2 * SNV * KC, 0, st>>>(vol, nb, pl->dim, pl->H, folds);
+        CUDA_TRY(cudaGetLastError());
+        const bool timed = pl->profiling && mpl->n_timed < z3d_plan::MAX_TIMED;
+        if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t0[mpl->n_timed], st));
+        k_decompose_stream<<<dp.nsets * dp.nsplits, SNT, pl->s_smem, st>>>(dp, folds, part, nparts, partial);
+        CUDA_TRY(cudaGetLastError());
+        if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t1[mpl->n_timed++], st));
+        k_reduce_stream<<<(pl->nmom * SM_ROWS + 255) / 256, 256, 0, st>>>(partial, pl->d_colmap, pl->d_scale, pl->nmom, dp.nsplits, nb, mom);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 3;
+        done += nb;
     }
     while (pl->batched && half_lo == 0 && half_hi == pl->H && batch - done >= pl->batched_min) {
         // a tile of up to 64 volumes when enough are left, else of up to 32 (a tile costs the same whatever it holds)

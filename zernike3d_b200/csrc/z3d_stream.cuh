@@ -1,0 +1,362 @@
+// zernike3d_b200 - batched analysis, streamed-T variant: tiles of up to 64 volumes, operand T read straight from HBM.
+//
+// Same contraction as z3d_batched.cuh,
+//     D[(n,l,m)][(re/im, b)] += T[(n,l,m)][k] * a[(m,pz)][k][(re/im, b)],   T = R_nl * Q_lm,  a = F_A,b trig_A + F_B,b trig_B,
+// but with the GEMM transposed and the volume-independent operand precomputed:
+//   * the MMA's M = 128 rows are the 2 x 64 (re/im, volume) columns of a tile - always full - and its N dimension are the
+//     moment rows of one (m, pz), padded to 16 instead of 128 (fill 94 % instead of 61 % at order 50);
+//   * T, already split into its TF32 high part and float32 remainder and already in the K-major core-matrix layout of
+//     the shared-memory descriptors, is a plan-owned table in HBM (k_build_T, once per plan: 13.7 GB at 128^3 / order 50,
+//     64 B per moment row and chunk) that the TMA engine (cp.async.bulk) streams into a ring of stages; the tensor core
+//     reads it where it lands.  No thread ever touches T: what the 31 producer warps of z3d_batched.cuh spent most of
+//     their shared-memory bandwidth on is gone, and so is the R / Q staging.
+//   * the producers only build the a panels (one per (m, pz) of the CTA's column set, 128 x 8 values) from the folds.
+// A CTA owns a *column set* - up to 512 accumulator columns (all of tensor memory) made of segments of <= 256 moment rows
+// of <= S_PANELS different (m, pz) - and one split of the chunk list.  Sets are packed by the planner (z3d_api.cu) to
+// equal cost; a (m, pz) may be cut between two sets.  The folds are stored by *kind* = (m parity, pz): a panel needs only
+// the 4 fold classes of its kind (8 KB per chunk), a set spans at most two kinds.
+//
+// HBM is the roofline of this kernel: every tile streams the whole T table once (64 B x rows16 x chunks), against
+// 3 x 2 x 128 x 8 flops per row and chunk on the tensor pipe.
+#pragma once
+#include "z3d_batched.cuh"
+
+namespace z3d {
+
+constexpr int SNV = 64;               // volumes per tile
+constexpr int SM_ROWS = 2 * SNV;      // MMA M: [re | im][volume]
+constexpr int S_PANELS = 4;           // a panels ((m, pz) pieces) per column set at most
+constexpr int S_SEGS = 8;             // MMA segments (<= 256 columns each) per column set at most
+constexpr int S_KINDS = 2;            // fold kinds staged per chunk at most
+constexpr int S_FK_BYTES = 4 * SNV * KC * 4;       // folds of one kind and chunk: [set A|B][re|im class][volume][k]
+constexpr int S_PANEL_BYTES = 2 * SM_ROWS * KC * 4;  // one a panel: [hi | lo][2 k halves][128 rows][4]
+constexpr int S_MAX_STAGES = 8;
+constexpr int S_OFF_TABS = 0;                       // int tables, see StreamTabs
+constexpr int S_OFF_MBAR = 256;                     // full[S_MAX_STAGES], empty[S_MAX_STAGES], aready[2], adone[2], tensor-memory base
+constexpr int S_OFF_SEG = 512;                      // per-segment descriptor parts, int4 [S_SEGS]
+constexpr int S_OFF_A = 1024;                       // a panels [2 buffers][S_PANELS], then the stages
+constexpr int S_A_TOTAL = 2 * S_PANELS * S_PANEL_BYTES;
+
+struct StreamTabs {          // per column set, copied to shared memory
+    int ncols, nseg, npanel, nkind;
+    int kind[S_KINDS];
+    int seg_cols[S_SEGS], seg_off[S_SEGS], seg_panel[S_SEGS];
+    int panel_code[S_PANELS];   // m | pz << 16 | kind slot << 24
+    long long toff;             // offset (floats) of the set's block inside a chunk record of the T table
+};
+static_assert(sizeof(StreamTabs) <= S_OFF_MBAR, "tables");
+
+struct DevPlanS {
+    int order, dim, H;
+    int nsets, nsplits, nstages;
+    int stage_bytes;           // T block of the widest set (rounded to 128) + S_KINDS fold kinds
+    int t_bytes_max;
+    long long trec;            // floats per chunk record of the T table (16 x all columns)
+    const StreamTabs *tabs;    // [nsets]
+    const float *Tt;           // [chunks][trec]: per set [hi | lo][2 k halves][ncols][4]
+    const float *trig;         // [items][4][LMAX + 1]
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// T table: one CTA per chunk; a thread per (column, k half): product of the R and Q table entries (k_build_basis), TF32
+// split, two 16-byte stores.  colsrc[j] = (R index, Q index, float offset of (column, k half 0, hi) in the record, set's
+// column count); padding columns have R index -1 and are written as zeros.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_build_T(const float *__restrict__ Rt, const float *__restrict__ Qt, int nrad, int nq,
+                                                  const int4 *__restrict__ colsrc, int ncols_all, long long trec,
+                                                  float *__restrict__ Tt) {
+    const long long chunk = blockIdx.x;
+    const float *Rs = Rt + (size_t)chunk * nrad * KC, *Qs = Qt + (size_t)chunk * nq * KC;
+    float *rec = Tt + (size_t)chunk * trec;
+    for (int it = threadIdx.x; it < 2 * ncols_all; it += blockDim.x) {
+        const int kh = it & 1, j = it >> 1;
+        const int4 cs = colsrc[j];
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cs.x >= 0) {
+            const int sr = ((cs.x >> 2) & 1) << 2, sq = ((cs.y >> 2) & 1) << 2;  // the tables' k-half swizzle
+            const float4 r = *reinterpret_cast<const float4 *>(Rs + cs.x * KC + ((4 * kh) ^ sr));
+            const float4 q = *reinterpret_cast<const float4 *>(Qs + cs.y * KC + ((4 * kh) ^ sq));
+            t = make_float4(r.x * q.x, r.y * q.y, r.z * q.z, r.w * q.w);
+        }
+        float4 hi, lo;
+        split4(t, hi, lo);
+        float *p = rec + cs.z + (size_t)kh * cs.w * 4;
+        *reinterpret_cast<float4 *>(p) = hi;
+        *reinterpret_cast<float4 *>(p + (size_t)2 * cs.w * 4) = lo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Folds of a tile, by kind: F[chunk][kind = (m parity) << 1 | pz][set A|B][re|im][volume][k].  The real part of a moment
+// with m parity mp needs the class (y even, x parity mp, z parity pz), the imaginary part (y odd, x parity mp ^ 1, pz).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(2 * SNV * KC) k_fold_tile_kind(const float *__restrict__ vol, int nvol, int N, int H,
+                                                                 float *__restrict__ Ft) {
+    const int CPR = (H + KC - 1) / KC;
+    const long long chunk = blockIdx.x;
+    ChunkPos p;
+    chunk_pos(chunk, CPR, H, p);
+    const int tid = threadIdx.x;
+    const int k = tid % KC, b = (tid / KC) % SNV, set = tid / (KC * SNV);
+    const int kk = p.kc * KC + k, k2 = N - 1 - kk;
+    const int ri = set ? p.jp : p.ip, rj = set ? p.ip : p.jp;
+    const int i2 = N - 1 - ri, j2 = N - 1 - rj;
+    const bool live = b < nvol && kk < H && (set == 0 || p.paired);
+    const float *vb = vol + (size_t)b * N * N * N;
+    float v[8];
+#pragma unroll
+    for (int img = 0; img < 8; ++img) {
+        const bool sy = img & 4, sx = img & 2, sz = img & 1;
+        const bool dup = (sy && i2 == ri) || (sx && j2 == rj) || (sz && k2 == kk);
+        v[img] = (live && !dup) ? __ldg(vb + ((size_t)(sy ? i2 : ri) * N + (sx ? j2 : rj)) * N + (sz ? k2 : kk)) : 0.0f;
+    }
+    wht8(v);
+    float *dst = Ft + (size_t)chunk * (4 * S_FK_BYTES / 4);
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {  // class c8 = (y parity = re/im) << 2 | (x parity) << 1 | z parity
+        const int reim = c8 >> 2, kind = ((((c8 >> 1) & 1) ^ reim) << 1) | (c8 & 1);
+        dst[(((kind * 2 + set) * 2 + reim) * SNV + b) * KC + (k ^ (((b >> 2) & 1) << 2))] = v[c8];
+    }
+}
+
+// ---- warp roles -----------------------------------------------------------------------------------------------------
+constexpr int S_NPW = 28;                 // producer warps: a panels + accumulator read-back (7 column blocks x 4 lane quarters)
+constexpr int S_NPROD = S_NPW * 32;
+constexpr int S_WARP_MMA = S_NPW;         // lane 0 issues the MMAs
+constexpr int S_WARP_TMA = S_NPW + 1;     // lane 0 issues the bulk copies
+constexpr int SNT = (S_NPW + 2) * 32;     // 960 threads
+
+__device__ __forceinline__ void mbar_arrive(unsigned mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_copy_hint(void *dst, const void *src, unsigned bytes, unsigned mbar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(mbar), "l"(pol) : "memory");
+}
+
+// a panels of the chunk: panel j, k half kh, row (re/im, volume) -> TF32 split -> [hi | lo][kh][row][4]
+__device__ __forceinline__ void s_a_products(const StreamTabs &T, const float *Fs, float *abuf, const float *__restrict__ trig,
+                                             float comp) {
+    for (int it = threadIdx.x; it < T.npanel * 2 * SM_ROWS; it += S_NPROD) {
+        const int b = it % SNV, reim = (it / SNV) & 1, kh = (it / SM_ROWS) & 1, j = it / (2 * SM_ROWS);
+        const int code = T.panel_code[j], m = code & 0xffff, slot = code >> 24;
+        float tA = __ldg(trig + reim * (LMAX + 1) + m), tB = __ldg(trig + (2 + reim) * (LMAX + 1) + m);
+        const float sg = reim ? -comp : comp;  // comp: truncation pre-compensation of this chunk (BTRUNC_PER_MMA)
+        tA *= sg;
+        tB *= sg;
+        const int sw = ((b >> 2) & 1) << 2;
+        const float *fa = Fs + slot * (S_FK_BYTES / 4) + (reim * SNV + b) * KC + ((4 * kh) ^ sw), *fb = fa + 2 * SNV * KC;
+        const float4 a = *reinterpret_cast<const float4 *>(fa), bq = *reinterpret_cast<const float4 *>(fb);
+        float4 hi, lo;
+        split_tf32(fmaf(a.x, tA, bq.x * tB), hi.x, lo.x);
+        split_tf32(fmaf(a.y, tA, bq.y * tB), hi.y, lo.y);
+        split_tf32(fmaf(a.z, tA, bq.z * tB), hi.z, lo.z);
+        split_tf32(fmaf(a.w, tA, bq.w * tB), hi.w, lo.w);
+        float *o = abuf + j * (S_PANEL_BYTES / 4) + (kh * SM_ROWS + reim * SNV + b) * 4;
+        *reinterpret_cast<float4 *>(o) = hi;
+        *reinterpret_cast<float4 *>(o + 2 * SM_ROWS * 4) = lo;
+    }
+}
+
+// accumulators -> the CTA's partial buffer [column][row]; producer warp w reads lane quarter w % 4 of the 64-column blocks
+// w / 4, w / 4 + 7, ..
+__device__ __forceinline__ void s_flush(unsigned tmem, int ncols, float *out, bool add) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3;
+#pragma unroll 1
+    for (int c64 = 64 * (warp >> 2); c64 < ncols; c64 += 64 * (S_NPW / 4)) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            unsigned v[32];
+            tmem_ld32(tmem + ((unsigned)(32 * q) << 16) + c64 + 32 * half, v);
+            float *p = out + ((size_t)c64 + 32 * half) * BTM + 32 * q + lane;
+            if (add) {
+#pragma unroll
+                for (int col = 0; col < 32; ++col) p[col * BTM] += __uint_as_float(v[col]);
+            } else {
+#pragma unroll
+                for (int col = 0; col < 32; ++col) p[col * BTM] = __uint_as_float(v[col]);
+            }
+        }
+    }
+}
+
+// Warp-specialised, no block barrier in the loop.  Chunk t uses stage s = t % NS and a buffer t & 1.
+//   copy warp     : waits empty[s] (the MMAs of chunk t - NS have retired), arms full[s], issues the bulk copies
+//   producer warps: wait full[s] and adone[t & 1] (MMAs of chunk t - 2 retired), build the a panels, arrive on aready[t & 1];
+//                   every BFLUSH_CHUNKS chunks they first wait for ALL issued MMAs and add the accumulators into the CTA's
+//                   partial buffer (see z3d_batched.cuh) - the issuing warp cannot pass them, it needs their a panels
+//   issuing warp  : waits full[s] and aready[t & 1], issues the MMAs, commits onto empty[s] and adone[t & 1]
+__global__ void __launch_bounds__(SNT, 1)
+k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int nparts, float *__restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int set = blockIdx.x / P.nsplits, split = blockIdx.x % P.nsplits;
+    StreamTabs &T = *reinterpret_cast<StreamTabs *>(smem + S_OFF_TABS);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + S_OFF_MBAR);
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + S_OFF_MBAR + 8 * (2 * S_MAX_STAGES + 4));
+    int4 *seginfo = reinterpret_cast<int4 *>(smem + S_OFF_SEG);
+    float *abase = reinterpret_cast<float *>(smem + S_OFF_A);
+    unsigned char *stage0 = smem + S_OFF_A + S_A_TOTAL;
+    const int NS = P.nstages, stage_bytes = P.stage_bytes, t_bytes_max = P.t_bytes_max;
+    for (int i = tid; i < (int)(sizeof(StreamTabs) / 4); i += SNT)
+        reinterpret_cast<int *>(smem + S_OFF_TABS)[i] = reinterpret_cast<const int *>(P.tabs + set)[i];
+    const unsigned full0 = smem_u32(bars), empty0 = full0 + 8 * S_MAX_STAGES, aready0 = empty0 + 8 * S_MAX_STAGES, adone0 = aready0 + 16;
+    if (tid == 0) {
+        for (int i = 0; i < 2 * S_MAX_STAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full0 + 8 * i));
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(aready0 + 8 * i), "r"(S_NPW));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(adone0 + 8 * i));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *tmem_slot;
+    const int ncols = T.ncols, nkind = T.nkind, nseg = T.nseg;
+    if (tid < nseg) {  // per segment: instruction descriptor, a panel and T offsets in descriptor units (16 B), accumulator column
+        const int n = T.seg_cols[tid];
+        seginfo[tid] = make_int4((int)((1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(SM_ROWS >> 4) << 24)),
+                                 T.seg_panel[tid] * (S_PANEL_BYTES >> 4), T.seg_off[tid], T.seg_off[tid]);
+    }
+    __syncthreads();
+
+    const int CPR = (P.H + KC - 1) / KC;
+    const long long total = (long long)analysis_items(0, P.H, P.H) * CPR;
+    const long long gbeg = total * part / nparts, glen = total * (part + 1) / nparts - gbeg;
+    const long long cbeg = gbeg + glen * split / P.nsplits, cend = gbeg + glen * (split + 1) / P.nsplits;
+    const unsigned nchunk = (unsigned)(cend - cbeg);
+    float *out = partial + (size_t)blockIdx.x * BSLOT_WORDS;
+
+    if (warp == S_WARP_TMA) {
+        // ---- copy warp: T block (evict-first: streamed once) and the folds of the set's kinds (evict-last: every set reads them)
+        const unsigned t_bytes = (unsigned)ncols * 64u;
+        const unsigned long long pol_t = l2_policy_evict_first(), pol_f = l2_policy_evict_last();
+        const float *tsrc = P.Tt + (size_t)cbeg * P.trec + T.toff;
+        const float *fsrc = Ft + (size_t)cbeg * (4 * S_FK_BYTES / 4);
+        const int k0 = T.kind[0], k1 = T.kind[1];
+        int s = 0;
+        unsigned use = 0;  // how often stage s has been filled before
+        for (unsigned t = 0; t < nchunk; ++t) {
+            if (use) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
+            if (lane == 0) {
+                unsigned char *st = stage0 + (size_t)s * stage_bytes;
+                const unsigned bar = full0 + 8 * s;
+                mbar_expect_tx(bar, t_bytes + (unsigned)nkind * S_FK_BYTES);
+                bulk_copy_hint(st, tsrc, t_bytes, bar, pol_t);
+                bulk_copy_hint(st + t_bytes_max, fsrc + k0 * (S_FK_BYTES / 4), S_FK_BYTES, bar, pol_f);
+                if (nkind > 1) bulk_copy_hint(st + t_bytes_max + S_FK_BYTES, fsrc + k1 * (S_FK_BYTES / 4), S_FK_BYTES, bar, pol_f);
+            }
+            __syncwarp();
+            tsrc += P.trec;
+            fsrc += 4 * S_FK_BYTES / 4;
+            if (++s == NS) { s = 0; ++use; }
+        }
+    } else if (warp == S_WARP_MMA) {
+        // ---- issuing warp
+        int s = 0;
+        unsigned use = 0;
+        int since_flush = 0;
+        const unsigned abase_u = smem_u32(abase), stage_u = smem_u32(stage0);
+        for (unsigned t = 0; t < nchunk; ++t) {
+            mbar_wait(full0 + 8 * s, use & 1);
+            mbar_wait(aready0 + 8 * (t & 1), (t >> 1) & 1);
+            tc_fence_after();
+            if (since_flush == BFLUSH_CHUNKS) since_flush = 0;
+            if (lane == 0) {
+                const unsigned tsm = stage_u + (unsigned)s * (unsigned)stage_bytes, asm_ = abase_u + (t & 1) * (S_PANELS * S_PANEL_BYTES);
+                const unsigned long long dA = umma_desc(asm_, SM_ROWS * 16, 128);
+                const unsigned long long dT = umma_desc(tsm, ncols * 16, 128);
+                const unsigned long long lo_a = (unsigned long long)(S_PANEL_BYTES / 2 >> 4), lo_t = (unsigned long long)(2 * ncols);
+                unsigned acc = since_flush > 0 ? 1u : 0u;
+#pragma unroll 1
+                for (int g = 0; g < nseg; ++g) {
+                    const int4 si = seginfo[g];
+                    const unsigned long long a = dA + (unsigned long long)si.y, b = dT + (unsigned long long)si.z;
+                    const unsigned d = tmem + (unsigned)si.w;
+                    umma_tf32(d, a, b + lo_t, (unsigned)si.x, acc);  // small terms first
+                    umma_tf32(d, a + lo_a, b, (unsigned)si.x, 1u);
+                    umma_tf32(d, a, b, (unsigned)si.x, 1u);
+                }
+                umma_commit(empty0 + 8 * s);
+                umma_commit(adone0 + 8 * (t & 1));
+            }
+            __syncwarp();
+            ++since_flush;
+            if (++s == NS) { s = 0; ++use; }
+        }
+    } else {
+        // ---- producer warps
+        int s = 0;
+        unsigned use = 0;
+        int since_flush = 0;
+        bool flushed = false;
+        int item = (int)(cbeg / CPR), kc = (int)(cbeg % CPR);
+        const float *trig = P.trig + (size_t)item * 4 * (LMAX + 1);
+        for (unsigned t = 0; t < nchunk; ++t) {
+            const unsigned char *stage = stage0 + (size_t)s * stage_bytes;
+            float *abuf = abase + (t & 1) * (S_PANELS * S_PANEL_BYTES / 4);
+            const int pos = since_flush == BFLUSH_CHUNKS ? 0 : since_flush;
+            const int ilen = min(BFLUSH_CHUNKS, (int)(nchunk - t) + pos);
+            const float comp = 1.0f + BTRUNC_PER_MMA * (float)(3 * (ilen - 1 - pos) + 1);
+            if (since_flush == BFLUSH_CHUNKS) {  // all MMAs issued so far have retired -> read the accumulators back
+                mbar_wait(adone0 + 8 * ((t - 1) & 1), ((t - 1) >> 1) & 1);
+                tc_fence_after();
+                s_flush(tmem, ncols, out, flushed);
+                flushed = true;
+                since_flush = 0;
+                tc_fence_before();
+            } else if (t >= 2) {                 // the MMAs of chunk t-2 read this a buffer
+                mbar_wait(adone0 + 8 * (t & 1), ((t >> 1) - 1) & 1);
+            }
+            mbar_wait(full0 + 8 * s, use & 1);
+            s_a_products(T, reinterpret_cast<const float *>(stage + t_bytes_max), abuf, trig, comp);
+            fence_async_smem();  // generic-proxy panel writes -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(aready0 + 8 * (t & 1));
+            ++since_flush;
+            if (++s == NS) { s = 0; ++use; }
+            if (++kc == CPR) { kc = 0; trig += 4 * (LMAX + 1); }
+        }
+        if (nchunk) {
+            mbar_wait(adone0 + 8 * ((nchunk - 1) & 1), ((nchunk - 1) >> 1) & 1);
+            tc_fence_after();
+            s_flush(tmem, ncols, out, flushed);
+        } else {
+            for (int i = tid; i < ncols * BTM; i += S_NPROD) out[i] = 0.0f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+// moments[b][mu][reim] = scale[mu] * sum over the splits of the owning accumulator (fixed order, float64)
+__global__ void k_reduce_stream(const float *__restrict__ partial, const int2 *__restrict__ colmap /* [nmom] (set, column) */,
+                                const double *__restrict__ scale, int nmom, int nsplits, int nvol, float *__restrict__ moments) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over nmom * 128
+    if (idx >= nmom * SM_ROWS) return;
+    const int mu = idx / SM_ROWS, row = idx % SM_ROWS, reim = row / SNV, b = row % SNV;
+    if (b >= nvol) return;
+    const int2 sc = colmap[mu];
+    const float *p = partial + (size_t)sc.x * nsplits * BSLOT_WORDS + (size_t)sc.y * BTM + row;
+    double sum = 0.0;
+    for (int s = 0; s < nsplits; ++s) sum += (double)p[(size_t)s * BSLOT_WORDS];
+    moments[((size_t)b * nmom + mu) * 2 + reim] = (float)(sum * scale[mu]);
+}
+
+}  // namespace z3d
