@@ -120,14 +120,31 @@ __global__ void __launch_bounds__(2 * SNV * KC) k_fold_tile_kind(const float *__
 }
 
 // ---- warp roles -----------------------------------------------------------------------------------------------------
-constexpr int S_NPW = 28;                 // producer warps: a panels + accumulator read-back (7 column blocks x 4 lane quarters)
+// Warps 0-3 are the special warps, one per scheduler (SM sub-partition = warp % 4), so that none of them competes with
+// another for issue slots: warp 0 issues the bulk copies, warps 1-3 issue the MMAs of segments g = w-1, w+2, w+5 (a single
+// thread needs ~250 clk per segment for descriptor arithmetic and the uniform-register traffic of three UTCHMMA; one
+// issuing warp was the critical path at 2 900 clk per chunk).  Warps 4-31 produce the a panels and read the accumulators back.
+constexpr int S_NMMA = 3;                 // issuing warps
+constexpr int S_WARP_TMA = 0;
+constexpr int S_WARP_PROD0 = 1 + S_NMMA;  // first producer warp
+constexpr int S_NPW = 28;                 // producer warps (7 column blocks x 4 lane quarters at the read-back)
 constexpr int S_NPROD = S_NPW * 32;
-constexpr int S_WARP_MMA = S_NPW;         // lane 0 issues the MMAs
-constexpr int S_WARP_TMA = S_NPW + 1;     // lane 0 issues the bulk copies
-constexpr int SNT = (S_NPW + 2) * 32;     // 960 threads
+constexpr int SNT = (S_WARP_PROD0 + S_NPW) * 32;   // 1024 threads
+constexpr int S_SEG_PER_WARP = (S_SEGS + S_NMMA - 1) / S_NMMA;
 
 __device__ __forceinline__ void mbar_arrive(unsigned mbar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+// wait with a suspend-time hint: the producers run up to two chunks ahead of the tensor core, their wake-up latency is hidden
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned mbar, unsigned parity) {
+#pragma unroll 1
+    for (int it = 0; it < (1 << 24); ++it) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity), "r"(2000u) : "memory");
+        if (ok) return;
+    }
+    __trap();
 }
 __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
     unsigned long long p;
@@ -147,7 +164,7 @@ __device__ __forceinline__ void bulk_copy_hint(void *dst, const void *src, unsig
 // a panels of the chunk: panel j, k half kh, row (re/im, volume) -> TF32 split -> [hi | lo][kh][row][4]
 __device__ __forceinline__ void s_a_products(const StreamTabs &T, const float *Fs, float *abuf, const float *__restrict__ trig,
                                              float comp) {
-    for (int it = threadIdx.x; it < T.npanel * 2 * SM_ROWS; it += S_NPROD) {
+    for (int it = threadIdx.x - S_WARP_PROD0 * 32; it < T.npanel * 2 * SM_ROWS; it += S_NPROD) {
         const int b = it % SNV, reim = (it / SNV) & 1, kh = (it / SM_ROWS) & 1, j = it / (2 * SM_ROWS);
         const int code = T.panel_code[j], m = code & 0xffff, slot = code >> 24;
         float tA = __ldg(trig + reim * (LMAX + 1) + m), tB = __ldg(trig + (2 + reim) * (LMAX + 1) + m);
@@ -169,11 +186,11 @@ __device__ __forceinline__ void s_a_products(const StreamTabs &T, const float *F
 }
 
 // accumulators -> the CTA's partial buffer [column][row]; producer warp w reads lane quarter w % 4 of the 64-column blocks
-// w / 4, w / 4 + 7, ..
+// (w - 4) / 4, (w - 4) / 4 + 7, ..
 __device__ __forceinline__ void s_flush(unsigned tmem, int ncols, float *out, bool add) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3;  // q: the lane quarter this warp can address
 #pragma unroll 1
-    for (int c64 = 64 * (warp >> 2); c64 < ncols; c64 += 64 * (S_NPW / 4)) {
+    for (int c64 = 64 * ((warp - S_WARP_PROD0) >> 2); c64 < ncols; c64 += 64 * (S_NPW / 4)) {
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             unsigned v[32];
@@ -212,10 +229,13 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
         reinterpret_cast<int *>(smem + S_OFF_TABS)[i] = reinterpret_cast<const int *>(P.tabs + set)[i];
     const unsigned full0 = smem_u32(bars), empty0 = full0 + 8 * S_MAX_STAGES, aready0 = empty0 + 8 * S_MAX_STAGES, adone0 = aready0 + 16;
     if (tid == 0) {
-        for (int i = 0; i < 2 * S_MAX_STAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full0 + 8 * i));
+        for (int i = 0; i < S_MAX_STAGES; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full0 + 8 * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * i), "r"(S_NMMA));
+        }
         for (int i = 0; i < 2; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(aready0 + 8 * i), "r"(S_NPW));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(adone0 + 8 * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(adone0 + 8 * i), "r"(S_NMMA));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -266,12 +286,20 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
             fsrc += 4 * S_FK_BYTES / 4;
             if (++s == NS) { s = 0; ++use; }
         }
-    } else if (warp == S_WARP_MMA) {
-        // ---- issuing warp
+    } else if (warp < S_WARP_PROD0) {
+        // ---- issuing warps: segments wi, wi + S_NMMA, ..
+        const int wi = warp - 1;
+        int4 sg[S_SEG_PER_WARP];
+#pragma unroll
+        for (int q = 0; q < S_SEG_PER_WARP; ++q) {
+            const int g = wi + q * S_NMMA;
+            sg[q] = g < nseg ? seginfo[g] : make_int4(0, 0, 0, -1);
+        }
         int s = 0;
         unsigned use = 0;
         int since_flush = 0;
         const unsigned abase_u = smem_u32(abase), stage_u = smem_u32(stage0);
+        const unsigned long long lo_a = (unsigned long long)(S_PANEL_BYTES / 2 >> 4), lo_t = (unsigned long long)(2 * ncols);
         for (unsigned t = 0; t < nchunk; ++t) {
             mbar_wait(full0 + 8 * s, use & 1);
             mbar_wait(aready0 + 8 * (t & 1), (t >> 1) & 1);
@@ -281,16 +309,16 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
                 const unsigned tsm = stage_u + (unsigned)s * (unsigned)stage_bytes, asm_ = abase_u + (t & 1) * (S_PANELS * S_PANEL_BYTES);
                 const unsigned long long dA = umma_desc(asm_, SM_ROWS * 16, 128);
                 const unsigned long long dT = umma_desc(tsm, ncols * 16, 128);
-                const unsigned long long lo_a = (unsigned long long)(S_PANEL_BYTES / 2 >> 4), lo_t = (unsigned long long)(2 * ncols);
-                unsigned acc = since_flush > 0 ? 1u : 0u;
-#pragma unroll 1
-                for (int g = 0; g < nseg; ++g) {
-                    const int4 si = seginfo[g];
-                    const unsigned long long a = dA + (unsigned long long)si.y, b = dT + (unsigned long long)si.z;
-                    const unsigned d = tmem + (unsigned)si.w;
-                    umma_tf32(d, a, b + lo_t, (unsigned)si.x, acc);  // small terms first
-                    umma_tf32(d, a + lo_a, b, (unsigned)si.x, 1u);
-                    umma_tf32(d, a, b, (unsigned)si.x, 1u);
+                const unsigned acc = since_flush > 0 ? 1u : 0u;
+#pragma unroll
+                for (int q = 0; q < S_SEG_PER_WARP; ++q) {
+                    if (sg[q].w >= 0) {
+                        const unsigned long long a = dA + (unsigned long long)sg[q].y, b = dT + (unsigned long long)sg[q].z;
+                        const unsigned d = tmem + (unsigned)sg[q].w;
+                        umma_tf32(d, a, b + lo_t, (unsigned)sg[q].x, acc);  // small terms first
+                        umma_tf32(d, a + lo_a, b, (unsigned)sg[q].x, 1u);
+                        umma_tf32(d, a, b, (unsigned)sg[q].x, 1u);
+                    }
                 }
                 umma_commit(empty0 + 8 * s);
                 umma_commit(adone0 + 8 * (t & 1));
@@ -321,9 +349,9 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
                 since_flush = 0;
                 tc_fence_before();
             } else if (t >= 2) {                 // the MMAs of chunk t-2 read this a buffer
-                mbar_wait(adone0 + 8 * (t & 1), ((t >> 1) - 1) & 1);
+                mbar_wait_relaxed(adone0 + 8 * (t & 1), ((t >> 1) - 1) & 1);
             }
-            mbar_wait(full0 + 8 * s, use & 1);
+            mbar_wait_relaxed(full0 + 8 * s, use & 1);
             s_a_products(T, reinterpret_cast<const float *>(stage + t_bytes_max), abuf, trig, comp);
             fence_async_smem();  // generic-proxy panel writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
@@ -337,7 +365,7 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
             tc_fence_after();
             s_flush(tmem, ncols, out, flushed);
         } else {
-            for (int i = tid; i < ncols * BTM; i += S_NPROD) out[i] = 0.0f;
+            for (int i = tid - S_WARP_PROD0 * 32; i < ncols * BTM; i += S_NPROD) out[i] = 0.0f;
         }
     }
     tc_fence_before();
