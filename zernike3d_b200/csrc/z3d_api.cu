@@ -517,7 +517,7 @@ void build_stream_plan(int L, int num_sms, const HostPlanB &hb, HostPlanS &hs, i
                 const bool newkind = !cur.empty() && kind != k_last;
                 const double kc = (cur.empty() || newkind) ? CK : 0.0;
                 int room = std::min(512 - cols, (int)((cap - cost - CB - kc) / CA) / 16 * 16);
-                if ((int)cur.size() >= S_PANELS || segs + 1 > S_SEGS || room < 16 || (newkind && k_first != k_last)) {
+                if ((int)cur.size() >= S_PANELS || segs + 1 > S_SEGS || room < 16 || (newkind && (S_KINDS == 1 || k_first != k_last))) {
                     if (cur.empty()) room = 16; else { close(); continue; }
                 }
                 int take = std::min(rem, room);
@@ -780,14 +780,16 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
             d2.order = order; d2.dim = dim; d2.H = pl->H; d2.nsets = hs.nsets; d2.nsplits = hs.nsplits;
             d2.t_bytes_max = hs.t_bytes_max;
             d2.stage_bytes = hs.t_bytes_max + S_KINDS * S_FK_BYTES;
-            d2.nstages = std::min(S_MAX_STAGES, ((int)prop.sharedMemPerBlockOptin - S_OFF_A - S_A_TOTAL) / d2.stage_bytes);
-            if (const char *e = getenv("Z3D_STREAM_STAGES")) d2.nstages = std::min(d2.nstages, std::max(2, atoi(e)));
+            // shared memory: three a-panel buffers (one per producer team) and a ring of copy stages (HBM latency)
+            const int budget = (int)prop.sharedMemPerBlockOptin - S_OFF_A - S_NTEAM * S_ABUF_BYTES;
+            d2.nstages = std::min(S_MAX_STAGES, budget / d2.stage_bytes);
+            if (const char *e = getenv("Z3D_STREAM_STAGES")) d2.nstages = std::min(d2.nstages, std::max(3, atoi(e)));
             d2.trec = hs.trec;
-            if (d2.nstages >= 2) {
+            if (d2.nstages >= 3) {  // with fewer the producers' read-back (after the panels of the chunks behind the boundary) could deadlock
                 StreamTabs *d_tabs;
                 UP(hs.tabs, d_tabs) UP(hs.colsrc, pl->d_colsrc) UP(hs.colmap, pl->d_colmap)
                 d2.tabs = d_tabs;
-                pl->s_smem = S_OFF_A + S_A_TOTAL + d2.nstages * d2.stage_bytes;
+                pl->s_smem = S_OFF_A + S_NTEAM * S_ABUF_BYTES + d2.nstages * d2.stage_bytes;
                 pl->s_ncols_all = hs.ncols_all;
                 pl->stream = true;
             }

@@ -27,15 +27,16 @@ constexpr int SNV = 64;               // volumes per tile
 constexpr int SM_ROWS = 2 * SNV;      // MMA M: [re | im][volume]
 constexpr int S_PANELS = 4;           // a panels ((m, pz) pieces) per column set at most
 constexpr int S_SEGS = 8;             // MMA segments (<= 256 columns each) per column set at most
-constexpr int S_KINDS = 2;            // fold kinds staged per chunk at most
+constexpr int S_KINDS = 1;            // fold kinds staged per chunk: the planner closes a column set at a kind boundary
 constexpr int S_FK_BYTES = 4 * SNV * KC * 4;       // folds of one kind and chunk: [set A|B][re|im class][volume][k]
 constexpr int S_PANEL_BYTES = 2 * SM_ROWS * KC * 4;  // one a panel: [hi | lo][2 k halves][128 rows][4]
 constexpr int S_MAX_STAGES = 8;
 constexpr int S_OFF_TABS = 0;                       // int tables, see StreamTabs
-constexpr int S_OFF_MBAR = 256;                     // full[S_MAX_STAGES], empty[S_MAX_STAGES], aready[2], adone[2], tensor-memory base
+constexpr int S_OFF_MBAR = 256;                     // full[S_MAX_STAGES], empty[S_MAX_STAGES], aready[3], adone[3], drained, flushed, tensor-memory base
 constexpr int S_OFF_SEG = 512;                      // per-segment descriptor parts, int4 [S_SEGS]
-constexpr int S_OFF_A = 1024;                       // a panels [2 buffers][S_PANELS], then the stages
-constexpr int S_A_TOTAL = 2 * S_PANELS * S_PANEL_BYTES;
+constexpr int S_OFF_BLK = 640;                      // read-back list: int nblk, pad, int blk[32] (16-column blocks of the accumulators)
+constexpr int S_OFF_A = 1024;                       // a panels [3 buffers, one per producer team][S_PANELS], then the stages
+constexpr int S_ABUF_BYTES = S_PANELS * S_PANEL_BYTES;
 
 struct StreamTabs {          // per column set, copied to shared memory
     int ncols, nseg, npanel, nkind;
@@ -122,20 +123,28 @@ __global__ void __launch_bounds__(2 * SNV * KC) k_fold_tile_kind(const float *__
 // ---- warp roles -----------------------------------------------------------------------------------------------------
 // Warps 0-3 are the special warps, one per scheduler (SM sub-partition = warp % 4), so that none of them competes with
 // another for issue slots: warp 0 issues the bulk copies, warps 1-3 issue the MMAs of segments g = w-1, w+2, w+5 (a single
-// thread needs ~250 clk per segment for descriptor arithmetic and the uniform-register traffic of three UTCHMMA; one
-// issuing warp was the critical path at 2 900 clk per chunk).  Warps 4-31 produce the a panels and read the accumulators back.
+// thread needs several hundred clocks per segment for descriptor arithmetic and the uniform-register traffic of three
+// UTCHMMA; one issuing warp was the critical path at 2 900 clk per chunk).  Warps 4-27 are three producer TEAMS of 8 warps:
+// team i builds the a panels of the chunks t = i, i + 3, .. into a buffer i (a thread owns one (row, k half) of every panel
+// of the set and loads its folds once per chunk), so a team has three chunk periods for the load -> split -> store ->
+// proxy fence -> arrive latency chain; all 24 warps read the accumulators back.
 constexpr int S_NMMA = 3;                 // issuing warps
 constexpr int S_WARP_TMA = 0;
 constexpr int S_WARP_PROD0 = 1 + S_NMMA;  // first producer warp
-constexpr int S_NPW = 28;                 // producer warps (7 column blocks x 4 lane quarters at the read-back)
+constexpr int S_NTEAM = 3;                // producer teams = a-panel buffers
+constexpr int S_TEAM_WARPS = 8;           // 256 threads = 128 rows x 2 k halves
+constexpr int S_NPW = S_NTEAM * S_TEAM_WARPS;
 constexpr int S_NPROD = S_NPW * 32;
-constexpr int SNT = (S_WARP_PROD0 + S_NPW) * 32;   // 1024 threads
+constexpr int SNT = (S_WARP_PROD0 + S_NPW) * 32;   // 896 threads
 constexpr int S_SEG_PER_WARP = (S_SEGS + S_NMMA - 1) / S_NMMA;
+// first read-back event of a CTA (chunks): CTAs sweep the chunk list in lock step, staggering spreads the L2 traffic of the
+// read-backs (360 KB per CTA and event) over the interval instead of bursting it from all 148 CTAs at once
+__device__ __forceinline__ int s_first_event() { return (int)(blockIdx.x % 8 + 1) * (BFLUSH_CHUNKS / 8); }
 
 __device__ __forceinline__ void mbar_arrive(unsigned mbar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
-// wait with a suspend-time hint: the producers run up to two chunks ahead of the tensor core, their wake-up latency is hidden
+// wait with a suspend-time hint: the producers run chunks ahead of the tensor core, their wake-up latency is hidden
 __device__ __forceinline__ void mbar_wait_relaxed(unsigned mbar, unsigned parity) {
 #pragma unroll 1
     for (int it = 0; it < (1 << 24); ++it) {
@@ -161,58 +170,106 @@ __device__ __forceinline__ void bulk_copy_hint(void *dst, const void *src, unsig
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(mbar), "l"(pol) : "memory");
 }
 
-// a panels of the chunk: panel j, k half kh, row (re/im, volume) -> TF32 split -> [hi | lo][kh][row][4]
-__device__ __forceinline__ void s_a_products(const StreamTabs &T, const float *Fs, float *abuf, const float *__restrict__ trig,
-                                             float comp) {
-    for (int it = threadIdx.x - S_WARP_PROD0 * 32; it < T.npanel * 2 * SM_ROWS; it += S_NPROD) {
-        const int b = it % SNV, reim = (it / SNV) & 1, kh = (it / SM_ROWS) & 1, j = it / (2 * SM_ROWS);
-        const int code = T.panel_code[j], m = code & 0xffff, slot = code >> 24;
-        float tA = __ldg(trig + reim * (LMAX + 1) + m), tB = __ldg(trig + (2 + reim) * (LMAX + 1) + m);
-        const float sg = reim ? -comp : comp;  // comp: truncation pre-compensation of this chunk (BTRUNC_PER_MMA)
-        tA *= sg;
-        tB *= sg;
-        const int sw = ((b >> 2) & 1) << 2;
-        const float *fa = Fs + slot * (S_FK_BYTES / 4) + (reim * SNV + b) * KC + ((4 * kh) ^ sw), *fb = fa + 2 * SNV * KC;
-        const float4 a = *reinterpret_cast<const float4 *>(fa), bq = *reinterpret_cast<const float4 *>(fb);
-        float4 hi, lo;
-        split_tf32(fmaf(a.x, tA, bq.x * tB), hi.x, lo.x);
-        split_tf32(fmaf(a.y, tA, bq.y * tB), hi.y, lo.y);
-        split_tf32(fmaf(a.z, tA, bq.z * tB), hi.z, lo.z);
-        split_tf32(fmaf(a.w, tA, bq.w * tB), hi.w, lo.w);
-        float *o = abuf + j * (S_PANEL_BYTES / 4) + (kh * SM_ROWS + reim * SNV + b) * 4;
-        *reinterpret_cast<float4 *>(o) = hi;
-        *reinterpret_cast<float4 *>(o + 2 * SM_ROWS * 4) = lo;
-    }
+// one a panel row: a = F_A trig_A + F_B trig_B (4 voxels of one k half), TF32 split, [hi | lo][kh][row][4]
+__device__ __forceinline__ void s_a_panel(const float4 &fa, const float4 &fb, float *abuf, const float *__restrict__ trig,
+                                          float sg, int tofs, int oofs) {
+    const float tA = __ldg(trig + tofs) * sg, tB = __ldg(trig + tofs + 2 * (LMAX + 1)) * sg;
+    float4 hi, lo;
+    split_tf32(fmaf(fa.x, tA, fb.x * tB), hi.x, lo.x);
+    split_tf32(fmaf(fa.y, tA, fb.y * tB), hi.y, lo.y);
+    split_tf32(fmaf(fa.z, tA, fb.z * tB), hi.z, lo.z);
+    split_tf32(fmaf(fa.w, tA, fb.w * tB), hi.w, lo.w);
+    *reinterpret_cast<float4 *>(abuf + oofs) = hi;
+    *reinterpret_cast<float4 *>(abuf + oofs + 2 * SM_ROWS * 4) = lo;
 }
 
-// accumulators -> the CTA's partial buffer [column][row]; producer warp w reads lane quarter w % 4 of the 64-column blocks
-// (w - 4) / 4, (w - 4) / 4 + 7, ..
-__device__ __forceinline__ void s_flush(unsigned tmem, int ncols, float *out, bool add) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3;  // q: the lane quarter this warp can address
-#pragma unroll 1
-    for (int c64 = 64 * ((warp - S_WARP_PROD0) >> 2); c64 < ncols; c64 += 64 * (S_NPW / 4)) {
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            unsigned v[32];
-            tmem_ld32(tmem + ((unsigned)(32 * q) << 16) + c64 + 32 * half, v);
-            float *p = out + ((size_t)c64 + 32 * half) * BTM + 32 * q + lane;
-            if (add) {
+// this warp's 32 lanes x 16 consecutive columns of tensor memory -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Accumulator read-back: the 16-column blocks blk[0..n) -> added into the CTA's partial buffer
+// [column][row].  Producer warp w can address lane quarter w % 4; the 6 warps of a quarter take blocks iq, iq + 6, ..
+// The partial sums of a warp's first two blocks are fetched BEFORE the wait for the tensor core to drain, so that the L2
+// round trip overlaps the drain and the critical path is wait -> tcgen05.ld -> add -> store.
+__device__ __forceinline__ void s_flush_group(unsigned tmem, const int *blk, int n, float *out, bool add, unsigned drained_bar,
+                                              unsigned parity, bool wait_first) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3, iq = (warp - S_WARP_PROD0) >> 2;
+    const unsigned tq = tmem + ((unsigned)(32 * q) << 16);
+    float pre0[16], pre1[16];
+    const int i0 = iq, i1 = iq + S_NPW / 4;
+    float *p0 = out + 32 * q + lane, *p1 = p0;
+    int c0 = 0, c1 = 0;
+    if (i0 < n) { c0 = blk[i0]; p0 += (size_t)c0 * BTM; }
+    if (i1 < n) { c1 = blk[i1]; p1 += (size_t)c1 * BTM; }
+    if (add && i0 < n) {
 #pragma unroll
-                for (int col = 0; col < 32; ++col) p[col * BTM] += __uint_as_float(v[col]);
-            } else {
+        for (int c = 0; c < 16; ++c) pre0[c] = p0[c * BTM];
+    } else {
 #pragma unroll
-                for (int col = 0; col < 32; ++col) p[col * BTM] = __uint_as_float(v[col]);
-            }
+        for (int c = 0; c < 16; ++c) pre0[c] = 0.0f;
+    }
+    if (add && i1 < n) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) pre1[c] = p1[c * BTM];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) pre1[c] = 0.0f;
+    }
+    if (wait_first) mbar_wait(drained_bar, parity);
+    tc_fence_after();
+    unsigned v[16];
+    if (i0 < n) {
+        tmem_ld16(tq + c0, v);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) p0[c * BTM] = pre0[c] + __uint_as_float(v[c]);
+    }
+    if (i1 < n) {
+        tmem_ld16(tq + c1, v);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) p1[c * BTM] = pre1[c] + __uint_as_float(v[c]);
+    }
+#pragma unroll 1
+    for (int i = iq + 2 * (S_NPW / 4); i < n; i += S_NPW / 4) {
+        const int cc = blk[i];
+        float *p = out + (size_t)cc * BTM + 32 * q + lane;
+        tmem_ld16(tq + cc, v);
+        if (add) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) p[c * BTM] += __uint_as_float(v[c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) p[c * BTM] = __uint_as_float(v[c]);
         }
     }
 }
 
-// Warp-specialised, no block barrier in the loop.  Chunk t uses stage s = t % NS and a buffer t & 1.
+// read-back interval containing chunk t: the accumulators are read back in front of the chunks ev0 + k * BFLUSH_CHUNKS and
+// after the last chunk
+__device__ __forceinline__ void s_interval(int t, int ev0, int nchunk, int &pos, int &len) {
+    const int og = BFLUSH_CHUNKS - ev0;
+    int start = ((t + og) / BFLUSH_CHUNKS) * BFLUSH_CHUNKS - og;
+    const int next = start + BFLUSH_CHUNKS;
+    start = max(start, 0);
+    len = min(next, nchunk) - start;
+    pos = t - start;
+}
+
+// Warp-specialised, no block barrier in the loop.  Chunk t uses copy stage s = t % NS and a buffer t % 3.
 //   copy warp     : waits empty[s] (the MMAs of chunk t - NS have retired), arms full[s], issues the bulk copies
-//   producer warps: wait full[s] and adone[t & 1] (MMAs of chunk t - 2 retired), build the a panels, arrive on aready[t & 1];
-//                   every BFLUSH_CHUNKS chunks they first wait for ALL issued MMAs and add the accumulators into the CTA's
-//                   partial buffer (see z3d_batched.cuh) - the issuing warp cannot pass them, it needs their a panels
-//   issuing warp  : waits full[s] and aready[t & 1], issues the MMAs, commits onto empty[s] and adone[t & 1]
+//   producer team : waits adone[i] (MMAs of chunk t - 3 retired) and full[s], builds the a panels, arrives on aready[i]
+//   issuing warps : wait full[s] and aready[t % 3], issue their MMAs, commit onto empty[s] and adone[t % 3]
+// Accumulator read-back every BFLUSH_CHUNKS chunks (see z3d_batched.cuh for why), the first one after s_first_event()
+// chunks: the issuing warps commit the last chunk in front of an event onto `drained`; every producer warp, after the
+// panels of its first chunk behind the boundary (they do not depend on the accumulators), waits for it, adds its 16-column
+// blocks into the CTA's partial buffer and arrives on `flushed`, which the issuing warps wait for before that chunk's
+// (overwriting) MMAs.
 __global__ void __launch_bounds__(SNT, 1)
 k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int nparts, float *__restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -220,23 +277,27 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
     const int set = blockIdx.x / P.nsplits, split = blockIdx.x % P.nsplits;
     StreamTabs &T = *reinterpret_cast<StreamTabs *>(smem + S_OFF_TABS);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + S_OFF_MBAR);
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + S_OFF_MBAR + 8 * (2 * S_MAX_STAGES + 4));
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + S_OFF_MBAR + 8 * (2 * S_MAX_STAGES + 2 * S_NTEAM + 2));
     int4 *seginfo = reinterpret_cast<int4 *>(smem + S_OFF_SEG);
+    int *nblk = reinterpret_cast<int *>(smem + S_OFF_BLK), *blk = nblk + 2;
     float *abase = reinterpret_cast<float *>(smem + S_OFF_A);
-    unsigned char *stage0 = smem + S_OFF_A + S_A_TOTAL;
+    unsigned char *stage0 = smem + S_OFF_A + S_NTEAM * S_ABUF_BYTES;
     const int NS = P.nstages, stage_bytes = P.stage_bytes, t_bytes_max = P.t_bytes_max;
     for (int i = tid; i < (int)(sizeof(StreamTabs) / 4); i += SNT)
         reinterpret_cast<int *>(smem + S_OFF_TABS)[i] = reinterpret_cast<const int *>(P.tabs + set)[i];
-    const unsigned full0 = smem_u32(bars), empty0 = full0 + 8 * S_MAX_STAGES, aready0 = empty0 + 8 * S_MAX_STAGES, adone0 = aready0 + 16;
+    const unsigned full0 = smem_u32(bars), empty0 = full0 + 8 * S_MAX_STAGES, aready0 = empty0 + 8 * S_MAX_STAGES,
+                   adone0 = aready0 + 8 * S_NTEAM, drained = adone0 + 8 * S_NTEAM, flushed = drained + 8;
     if (tid == 0) {
         for (int i = 0; i < S_MAX_STAGES; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full0 + 8 * i));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * i), "r"(S_NMMA));
         }
-        for (int i = 0; i < 2; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(aready0 + 8 * i), "r"(S_NPW));
+        for (int i = 0; i < S_NTEAM; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(aready0 + 8 * i), "r"(S_TEAM_WARPS));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(adone0 + 8 * i), "r"(S_NMMA));
         }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(drained), "r"(S_NMMA));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(flushed), "r"(S_NPW));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -247,11 +308,19 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
     __syncthreads();
     tc_fence_after();
     const unsigned tmem = *tmem_slot;
-    const int ncols = T.ncols, nkind = T.nkind, nseg = T.nseg;
-    if (tid < nseg) {  // per segment: instruction descriptor, a panel and T offsets in descriptor units (16 B), accumulator column
-        const int n = T.seg_cols[tid];
+    const int ncols = T.ncols, nseg = T.nseg;
+    if (tid < nseg) {  // per segment: instruction descriptor, a panel and T offsets in descriptor units (16 B), accumulator
+        const int n = T.seg_cols[tid];  // column | panel group << 16
         seginfo[tid] = make_int4((int)((1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(SM_ROWS >> 4) << 24)),
                                  T.seg_panel[tid] * (S_PANEL_BYTES >> 4), T.seg_off[tid], T.seg_off[tid]);
+    }
+    if (tid == 32) {   // read-back lists
+        int n0 = 0;
+        for (int g = 0; g < nseg; ++g)
+            for (int c = 0; c < T.seg_cols[g]; c += 16) {
+                blk[n0++] = T.seg_off[g] + c;
+            }
+        nblk[0] = n0;
     }
     __syncthreads();
 
@@ -259,27 +328,26 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
     const long long total = (long long)analysis_items(0, P.H, P.H) * CPR;
     const long long gbeg = total * part / nparts, glen = total * (part + 1) / nparts - gbeg;
     const long long cbeg = gbeg + glen * split / P.nsplits, cend = gbeg + glen * (split + 1) / P.nsplits;
-    const unsigned nchunk = (unsigned)(cend - cbeg);
+    const int nchunk = (int)(cend - cbeg);
     float *out = partial + (size_t)blockIdx.x * BSLOT_WORDS;
 
     if (warp == S_WARP_TMA) {
-        // ---- copy warp: T block (evict-first: streamed once) and the folds of the set's kinds (evict-last: every set reads them)
+        // ---- copy warp: T block (evict-first: streamed once) and the folds of the set's kind (evict-last: every set of the
+        //      kind reads them)
         const unsigned t_bytes = (unsigned)ncols * 64u;
         const unsigned long long pol_t = l2_policy_evict_first(), pol_f = l2_policy_evict_last();
         const float *tsrc = P.Tt + (size_t)cbeg * P.trec + T.toff;
-        const float *fsrc = Ft + (size_t)cbeg * (4 * S_FK_BYTES / 4);
-        const int k0 = T.kind[0], k1 = T.kind[1];
+        const float *fsrc = Ft + ((size_t)cbeg * 4 + T.kind[0]) * (S_FK_BYTES / 4);
         int s = 0;
         unsigned use = 0;  // how often stage s has been filled before
-        for (unsigned t = 0; t < nchunk; ++t) {
+        for (int t = 0; t < nchunk; ++t) {
             if (use) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
             if (lane == 0) {
                 unsigned char *st = stage0 + (size_t)s * stage_bytes;
                 const unsigned bar = full0 + 8 * s;
-                mbar_expect_tx(bar, t_bytes + (unsigned)nkind * S_FK_BYTES);
+                mbar_expect_tx(bar, t_bytes + S_FK_BYTES);
                 bulk_copy_hint(st, tsrc, t_bytes, bar, pol_t);
-                bulk_copy_hint(st + t_bytes_max, fsrc + k0 * (S_FK_BYTES / 4), S_FK_BYTES, bar, pol_f);
-                if (nkind > 1) bulk_copy_hint(st + t_bytes_max + S_FK_BYTES, fsrc + k1 * (S_FK_BYTES / 4), S_FK_BYTES, bar, pol_f);
+                bulk_copy_hint(st + t_bytes_max, fsrc, S_FK_BYTES, bar, pol_f);
             }
             __syncwarp();
             tsrc += P.trec;
@@ -295,75 +363,112 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
             const int g = wi + q * S_NMMA;
             sg[q] = g < nseg ? seginfo[g] : make_int4(0, 0, 0, -1);
         }
-        int s = 0;
-        unsigned use = 0;
-        int since_flush = 0;
-        const unsigned abase_u = smem_u32(abase), stage_u = smem_u32(stage0);
+        int s = 0, ai = 0;
+        int since = 0;   // chunks accumulated since the last read-back
+        unsigned use = 0, ause = 0, nev = 0;
+        // shared-memory descriptors advance with the rings: only the 14-bit start address field changes
+        const unsigned long long dA0 = umma_desc(smem_u32(abase), SM_ROWS * 16, 128), dT0 = umma_desc(smem_u32(stage0), ncols * 16, 128);
+        unsigned long long dA = dA0, dT = dT0;
         const unsigned long long lo_a = (unsigned long long)(S_PANEL_BYTES / 2 >> 4), lo_t = (unsigned long long)(2 * ncols);
-        for (unsigned t = 0; t < nchunk; ++t) {
+        const unsigned long long step_a = (unsigned long long)(S_ABUF_BYTES >> 4), step_t = (unsigned long long)(stage_bytes >> 4);
+        int to_event = s_first_event();  // chunks until the next read-back event
+        for (int t = 0; t < nchunk; ++t) {
+            if (to_event == 0) {  // event nev: its group's accumulators have been read back -> overwrite
+                mbar_wait(flushed, nev & 1);
+                since = 0;
+                ++nev;
+                to_event = BFLUSH_CHUNKS;
+            }
             mbar_wait(full0 + 8 * s, use & 1);
-            mbar_wait(aready0 + 8 * (t & 1), (t >> 1) & 1);
+            mbar_wait(aready0 + 8 * ai, ause & 1);
             tc_fence_after();
-            if (since_flush == BFLUSH_CHUNKS) since_flush = 0;
             if (lane == 0) {
-                const unsigned tsm = stage_u + (unsigned)s * (unsigned)stage_bytes, asm_ = abase_u + (t & 1) * (S_PANELS * S_PANEL_BYTES);
-                const unsigned long long dA = umma_desc(asm_, SM_ROWS * 16, 128);
-                const unsigned long long dT = umma_desc(tsm, ncols * 16, 128);
-                const unsigned acc = since_flush > 0 ? 1u : 0u;
 #pragma unroll
                 for (int q = 0; q < S_SEG_PER_WARP; ++q) {
                     if (sg[q].w >= 0) {
                         const unsigned long long a = dA + (unsigned long long)sg[q].y, b = dT + (unsigned long long)sg[q].z;
                         const unsigned d = tmem + (unsigned)sg[q].w;
+                        const unsigned acc = since > 0 ? 1u : 0u;
                         umma_tf32(d, a, b + lo_t, (unsigned)sg[q].x, acc);  // small terms first
                         umma_tf32(d, a + lo_a, b, (unsigned)sg[q].x, 1u);
                         umma_tf32(d, a, b, (unsigned)sg[q].x, 1u);
                     }
                 }
                 umma_commit(empty0 + 8 * s);
-                umma_commit(adone0 + 8 * (t & 1));
+                umma_commit(adone0 + 8 * ai);
+                if (to_event == 1 || t == nchunk - 1) umma_commit(drained);  // a read-back follows this chunk
             }
             __syncwarp();
-            ++since_flush;
-            if (++s == NS) { s = 0; ++use; }
+            ++since;
+            --to_event;
+            dT += step_t;
+            dA += step_a;
+            if (++s == NS) { s = 0; ++use; dT = dT0; }
+            if (++ai == S_NTEAM) { ai = 0; ++ause; dA = dA0; }
         }
     } else {
-        // ---- producer warps
-        int s = 0;
-        unsigned use = 0;
-        int since_flush = 0;
-        bool flushed = false;
-        int item = (int)(cbeg / CPR), kc = (int)(cbeg % CPR);
-        const float *trig = P.trig + (size_t)item * 4 * (LMAX + 1);
-        for (unsigned t = 0; t < nchunk; ++t) {
-            const unsigned char *stage = stage0 + (size_t)s * stage_bytes;
-            float *abuf = abase + (t & 1) * (S_PANELS * S_PANEL_BYTES / 4);
-            const int pos = since_flush == BFLUSH_CHUNKS ? 0 : since_flush;
-            const int ilen = min(BFLUSH_CHUNKS, (int)(nchunk - t) + pos);
-            const float comp = 1.0f + BTRUNC_PER_MMA * (float)(3 * (ilen - 1 - pos) + 1);
-            if (since_flush == BFLUSH_CHUNKS) {  // all MMAs issued so far have retired -> read the accumulators back
-                mbar_wait(adone0 + 8 * ((t - 1) & 1), ((t - 1) >> 1) & 1);
-                tc_fence_after();
-                s_flush(tmem, ncols, out, flushed);
-                flushed = true;
-                since_flush = 0;
-                tc_fence_before();
-            } else if (t >= 2) {                 // the MMAs of chunk t-2 read this a buffer
-                mbar_wait_relaxed(adone0 + 8 * (t & 1), ((t >> 1) - 1) & 1);
-            }
+        // ---- producer teams
+        const int pw = warp - S_WARP_PROD0, team = pw / S_TEAM_WARPS;
+        const int r = (pw % S_TEAM_WARPS) * 32 + lane, kh = r >> 7, row = r & 127, reim = row >> 6, b = row & 63;
+        const int fofs = (reim * SNV + b) * KC + ((4 * kh) ^ (((b >> 2) & 1) << 2));  // the thread's 4 fold values (set A)
+        const int oofs = (kh * SM_ROWS + row) * 4;
+        const float sign = reim ? -1.0f : 1.0f;  // im rows are negated
+        const int npanel = T.npanel;
+        int tofs[S_PANELS];
+#pragma unroll
+        for (int j = 0; j < S_PANELS; ++j) tofs[j] = reim * (LMAX + 1) + (T.panel_code[j < npanel ? j : 0] & 0xffff);
+        float *abuf = abase + team * (S_ABUF_BYTES / 4);
+        const unsigned my_ready = aready0 + 8 * team, my_done = adone0 + 8 * team;
+        int s = team % NS;
+        unsigned use = team / NS, ause = 0, nfl = 0;
+        int kc = (int)((cbeg + team) % CPR);
+        const float *trig = P.trig + (size_t)((cbeg + team) / CPR) * 4 * (LMAX + 1);
+        bool had = false;  // the accumulators have been read back before: add to the partial sums
+        const int ev0 = s_first_event();
+        const int nregular = nchunk > ev0 ? (nchunk - 1 - ev0) / BFLUSH_CHUNKS + 1 : 0;  // events in front of chunks ev0 + k BFLUSH_CHUNKS < nchunk
+        int nev = 0;
+        for (int t = team; t < nchunk; t += S_NTEAM) {
+            if (ause) mbar_wait_relaxed(my_done, (ause - 1) & 1);  // the MMAs of chunk t-3 read this a buffer
+            // truncation pre-compensation (BTRUNC_PER_MMA): the products of position pos of an interval of len chunks are
+            // followed by 3 (len - 1 - pos) + 1 truncating accumulations
+            int pos, len;
+            s_interval(t, ev0, nchunk, pos, len);
+            const float sg = sign * (1.0f + BTRUNC_PER_MMA * (float)(3 * (len - 1 - pos) + 1));
+            const float *Fs = reinterpret_cast<const float *>(stage0 + (size_t)s * stage_bytes + t_bytes_max);
             mbar_wait_relaxed(full0 + 8 * s, use & 1);
-            s_a_products(T, reinterpret_cast<const float *>(stage + t_bytes_max), abuf, trig, comp);
+            const float4 fa = *reinterpret_cast<const float4 *>(Fs + fofs), fb = *reinterpret_cast<const float4 *>(Fs + fofs + 2 * SNV * KC);
+#pragma unroll
+            for (int j = 0; j < S_PANELS; ++j)
+                if (j < npanel) s_a_panel(fa, fb, abuf, trig, sg, tofs[j], oofs + j * (S_PANEL_BYTES / 4));
             fence_async_smem();  // generic-proxy panel writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
-            if (lane == 0) mbar_arrive(aready0 + 8 * (t & 1));
-            ++since_flush;
-            if (++s == NS) { s = 0; ++use; }
-            if (++kc == CPR) { kc = 0; trig += 4 * (LMAX + 1); }
+            if (lane == 0) mbar_arrive(my_ready);
+            // read-back events in front of this chunk come AFTER its panels: the a panels do not depend on the accumulators, and
+            // the issuing warps find them ready when the read-back is done
+            while (nev < nregular && ev0 + nev * BFLUSH_CHUNKS <= t) {
+                s_flush_group(tmem, blk, nblk[0], out, had, drained, nev & 1, true);
+                had = true;
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(flushed);
+                ++nev;
+            }
+            ++ause;
+            s += S_NTEAM;
+            while (s >= NS) { s -= NS; ++use; }
+            kc += S_NTEAM;
+            while (kc >= CPR) { kc -= CPR; trig += 4 * (LMAX + 1); }
         }
-        if (nchunk) {
-            mbar_wait(adone0 + 8 * ((nchunk - 1) & 1), ((nchunk - 1) >> 1) & 1);
-            tc_fence_after();
-            s_flush(tmem, ncols, out, flushed);
+        if (nchunk) {  // remaining events, then both groups after the final chunk
+            while (nev < nregular) {
+                s_flush_group(tmem, blk, nblk[0], out, had, drained, nev & 1, true);
+                had = true;
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(flushed);
+                ++nev;
+            }
+            s_flush_group(tmem, blk, nblk[0], out, had, drained, nev & 1, true);
         } else {
             for (int i = tid - S_WARP_PROD0 * 32; i < ncols * BTM; i += S_NPROD) out[i] = 0.0f;
         }
