@@ -779,17 +779,14 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
             DevPlanS &d2 = pl->devs;
             d2.order = order; d2.dim = dim; d2.H = pl->H; d2.nsets = hs.nsets; d2.nsplits = hs.nsplits;
             d2.t_bytes_max = hs.t_bytes_max;
-            d2.stage_bytes = hs.t_bytes_max + S_KINDS * S_FK_BYTES;
-            // shared memory: three a-panel buffers (one per producer team) and a ring of copy stages (HBM latency)
-            const int budget = (int)prop.sharedMemPerBlockOptin - S_OFF_A - S_NTEAM * S_ABUF_BYTES;
-            d2.nstages = std::min(S_MAX_STAGES, budget / d2.stage_bytes);
-            if (const char *e = getenv("Z3D_STREAM_STAGES")) d2.nstages = std::min(d2.nstages, std::max(3, atoi(e)));
+            d2.stage_bytes = hs.t_bytes_max + S_FK_BYTES + S_ABUF_BYTES;  // a slot: T block, folds of one kind, a panels
+            d2.nstages = S_NTEAM;
             d2.trec = hs.trec;
-            if (d2.nstages >= 3) {  // with fewer the producers' read-back (after the panels of the chunks behind the boundary) could deadlock
+            if (S_OFF_A + S_NTEAM * d2.stage_bytes <= (int)prop.sharedMemPerBlockOptin) {
                 StreamTabs *d_tabs;
                 UP(hs.tabs, d_tabs) UP(hs.colsrc, pl->d_colsrc) UP(hs.colmap, pl->d_colmap)
                 d2.tabs = d_tabs;
-                pl->s_smem = S_OFF_A + S_NTEAM * S_ABUF_BYTES + d2.nstages * d2.stage_bytes;
+                pl->s_smem = S_OFF_A + S_NTEAM * d2.stage_bytes;
                 pl->s_ncols_all = hs.ncols_all;
                 pl->stream = true;
             }

@@ -32,10 +32,10 @@ constexpr int S_FK_BYTES = 4 * SNV * KC * 4;       // folds of one kind and chun
 constexpr int S_PANEL_BYTES = 2 * SM_ROWS * KC * 4;  // one a panel: [hi | lo][2 k halves][128 rows][4]
 constexpr int S_MAX_STAGES = 8;
 constexpr int S_OFF_TABS = 0;                       // int tables, see StreamTabs
-constexpr int S_OFF_MBAR = 256;                     // full[S_MAX_STAGES], empty[S_MAX_STAGES], aready[3], adone[3], drained, flushed, tensor-memory base
+constexpr int S_OFF_MBAR = 256;                     // fready[3], ready[3], done[3], drained, flushed, tensor-memory base
 constexpr int S_OFF_SEG = 512;                      // per-segment descriptor parts, int4 [S_SEGS]
 constexpr int S_OFF_BLK = 640;                      // read-back list: int nblk, pad, int blk[32] (16-column blocks of the accumulators)
-constexpr int S_OFF_A = 1024;                       // a panels [3 buffers, one per producer team][S_PANELS], then the stages
+constexpr int S_OFF_A = 1024;                       // the three slots: [T block][folds][a panels]
 constexpr int S_ABUF_BYTES = S_PANELS * S_PANEL_BYTES;
 
 struct StreamTabs {          // per column set, copied to shared memory
@@ -50,7 +50,7 @@ static_assert(sizeof(StreamTabs) <= S_OFF_MBAR, "tables");
 struct DevPlanS {
     int order, dim, H;
     int nsets, nsplits, nstages;
-    int stage_bytes;           // T block of the widest set (rounded to 128) + S_KINDS fold kinds
+    int stage_bytes;           // bytes of a slot: T block of the widest set + the folds of one kind + the a panels
     int t_bytes_max;
     long long trec;            // floats per chunk record of the T table (16 x all columns)
     const StreamTabs *tabs;    // [nsets]
@@ -170,82 +170,26 @@ __device__ __forceinline__ void bulk_copy_hint(void *dst, const void *src, unsig
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(mbar), "l"(pol) : "memory");
 }
 
-// one a panel row: a = F_A trig_A + F_B trig_B (4 voxels of one k half), TF32 split, [hi | lo][kh][row][4]
-__device__ __forceinline__ void s_a_panel(const float4 &fa, const float4 &fb, float *abuf, const float *__restrict__ trig,
-                                          float sg, int tofs, int oofs) {
-    const float tA = __ldg(trig + tofs) * sg, tB = __ldg(trig + tofs + 2 * (LMAX + 1)) * sg;
-    float4 hi, lo;
-    split_tf32(fmaf(fa.x, tA, fb.x * tB), hi.x, lo.x);
-    split_tf32(fmaf(fa.y, tA, fb.y * tB), hi.y, lo.y);
-    split_tf32(fmaf(fa.z, tA, fb.z * tB), hi.z, lo.z);
-    split_tf32(fmaf(fa.w, tA, fb.w * tB), hi.w, lo.w);
-    *reinterpret_cast<float4 *>(abuf + oofs) = hi;
-    *reinterpret_cast<float4 *>(abuf + oofs + 2 * SM_ROWS * 4) = lo;
-}
-
-// this warp's 32 lanes x 16 consecutive columns of tensor memory -> 16 registers per thread
-__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Accumulator read-back: the 16-column blocks blk[0..n) -> added into the CTA's partial buffer
-// [column][row].  Producer warp w can address lane quarter w % 4; the 6 warps of a quarter take blocks iq, iq + 6, ..
-// The partial sums of a warp's first two blocks are fetched BEFORE the wait for the tensor core to drain, so that the L2
-// round trip overlaps the drain and the critical path is wait -> tcgen05.ld -> add -> store.
-__device__ __forceinline__ void s_flush_group(unsigned tmem, const int *blk, int n, float *out, bool add, unsigned drained_bar,
-                                              unsigned parity, bool wait_first) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3, iq = (warp - S_WARP_PROD0) >> 2;
-    const unsigned tq = tmem + ((unsigned)(32 * q) << 16);
-    float pre0[16], pre1[16];
-    const int i0 = iq, i1 = iq + S_NPW / 4;
-    float *p0 = out + 32 * q + lane, *p1 = p0;
-    int c0 = 0, c1 = 0;
-    if (i0 < n) { c0 = blk[i0]; p0 += (size_t)c0 * BTM; }
-    if (i1 < n) { c1 = blk[i1]; p1 += (size_t)c1 * BTM; }
-    if (add && i0 < n) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) pre0[c] = p0[c * BTM];
-    } else {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) pre0[c] = 0.0f;
-    }
-    if (add && i1 < n) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) pre1[c] = p1[c * BTM];
-    } else {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) pre1[c] = 0.0f;
-    }
-    if (wait_first) mbar_wait(drained_bar, parity);
+// Accumulator read-back: accumulators -> added into the CTA's partial buffer [column][row].  Producer warp w can address lane
+// quarter w % 4; the 6 warps of a quarter take the 64-column blocks (w - 4) / 4, (w - 4) / 4 + 6.
+__device__ __forceinline__ void s_flush(unsigned tmem, int ncols, float *out, bool add, unsigned drained_bar, unsigned parity) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3;
+    mbar_wait(drained_bar, parity);  // every MMA issued so far has retired
     tc_fence_after();
-    unsigned v[16];
-    if (i0 < n) {
-        tmem_ld16(tq + c0, v);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) p0[c * BTM] = pre0[c] + __uint_as_float(v[c]);
-    }
-    if (i1 < n) {
-        tmem_ld16(tq + c1, v);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) p1[c * BTM] = pre1[c] + __uint_as_float(v[c]);
-    }
 #pragma unroll 1
-    for (int i = iq + 2 * (S_NPW / 4); i < n; i += S_NPW / 4) {
-        const int cc = blk[i];
-        float *p = out + (size_t)cc * BTM + 32 * q + lane;
-        tmem_ld16(tq + cc, v);
-        if (add) {
+    for (int c64 = 64 * ((warp - S_WARP_PROD0) >> 2); c64 < ncols; c64 += 64 * (S_NPW / 4)) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            unsigned v[32];
+            tmem_ld32(tmem + ((unsigned)(32 * q) << 16) + c64 + 32 * half, v);
+            float *p = out + ((size_t)c64 + 32 * half) * BTM + 32 * q + lane;
+            if (add) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) p[c * BTM] += __uint_as_float(v[c]);
-        } else {
+                for (int col = 0; col < 32; ++col) p[col * BTM] += __uint_as_float(v[col]);
+            } else {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) p[c * BTM] = __uint_as_float(v[c]);
+                for (int col = 0; col < 32; ++col) p[col * BTM] = __uint_as_float(v[col]);
+            }
         }
     }
 }
@@ -261,10 +205,13 @@ __device__ __forceinline__ void s_interval(int t, int ev0, int nchunk, int &pos,
     pos = t - start;
 }
 
-// Warp-specialised, no block barrier in the loop.  Chunk t uses copy stage s = t % NS and a buffer t % 3.
-//   copy warp     : waits empty[s] (the MMAs of chunk t - NS have retired), arms full[s], issues the bulk copies
-//   producer team : waits adone[i] (MMAs of chunk t - 3 retired) and full[s], builds the a panels, arrives on aready[i]
-//   issuing warps : wait full[s] and aready[t % 3], issue their MMAs, commit onto empty[s] and adone[t % 3]
+// Warp-specialised, no block barrier in the loop.  ONE ring of S_NTEAM = 3 slots; slot i = chunk t % 3 holds the chunk's T
+// block, its folds and its a panels and belongs to producer team i.  Three mbarriers per slot:
+//   fready[i]: the folds have landed (tx bytes)                                  copy warp  -> team i
+//   ready[i] : the T block has landed (tx bytes) AND team i's 8 warps have arrived  copy warp + team i -> issuing warps
+//   done[i]  : the MMAs of the slot's chunk have retired (tcgen05.commit of every active issuing warp)
+//                                                                             issuing warps -> copy warp + team i
+// so an issuing warp waits once and commits once per chunk (its serial per-chunk work is the kernel's critical path).
 // Accumulator read-back every BFLUSH_CHUNKS chunks (see z3d_batched.cuh for why), the first one after s_first_event()
 // chunks: the issuing warps commit the last chunk in front of an event onto `drained`; every producer warp, after the
 // panels of its first chunk behind the boundary (they do not depend on the accumulators), waits for it, adds its 16-column
@@ -277,26 +224,26 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
     const int set = blockIdx.x / P.nsplits, split = blockIdx.x % P.nsplits;
     StreamTabs &T = *reinterpret_cast<StreamTabs *>(smem + S_OFF_TABS);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + S_OFF_MBAR);
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + S_OFF_MBAR + 8 * (2 * S_MAX_STAGES + 2 * S_NTEAM + 2));
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + S_OFF_MBAR + 8 * (3 * S_NTEAM + 2));
     int4 *seginfo = reinterpret_cast<int4 *>(smem + S_OFF_SEG);
     int *nblk = reinterpret_cast<int *>(smem + S_OFF_BLK), *blk = nblk + 2;
-    float *abase = reinterpret_cast<float *>(smem + S_OFF_A);
-    unsigned char *stage0 = smem + S_OFF_A + S_NTEAM * S_ABUF_BYTES;
-    const int NS = P.nstages, stage_bytes = P.stage_bytes, t_bytes_max = P.t_bytes_max;
+    // slot: [T block (t_bytes_max)][folds of the set's kind (S_FK_BYTES)][a panels (S_ABUF_BYTES)]
+    unsigned char *slot0 = smem + S_OFF_A;
+    const int slot_bytes = P.stage_bytes, t_bytes_max = P.t_bytes_max;
     for (int i = tid; i < (int)(sizeof(StreamTabs) / 4); i += SNT)
         reinterpret_cast<int *>(smem + S_OFF_TABS)[i] = reinterpret_cast<const int *>(P.tabs + set)[i];
-    const unsigned full0 = smem_u32(bars), empty0 = full0 + 8 * S_MAX_STAGES, aready0 = empty0 + 8 * S_MAX_STAGES,
-                   adone0 = aready0 + 8 * S_NTEAM, drained = adone0 + 8 * S_NTEAM, flushed = drained + 8;
+    __syncthreads();
+    const int ncols = T.ncols, nseg = T.nseg;
+    const int nactive = min(nseg, S_NMMA);  // issuing warps that own a segment
+    const unsigned fready0 = smem_u32(bars), ready0 = fready0 + 8 * S_NTEAM, done0 = ready0 + 8 * S_NTEAM,
+                   drained = done0 + 8 * S_NTEAM, flushed = drained + 8;
     if (tid == 0) {
-        for (int i = 0; i < S_MAX_STAGES; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full0 + 8 * i));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * i), "r"(S_NMMA));
-        }
         for (int i = 0; i < S_NTEAM; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(aready0 + 8 * i), "r"(S_TEAM_WARPS));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(adone0 + 8 * i), "r"(S_NMMA));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fready0 + 8 * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ready0 + 8 * i), "r"(1 + S_TEAM_WARPS));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(done0 + 8 * i), "r"(nactive));
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(drained), "r"(S_NMMA));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(drained), "r"(nactive));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(flushed), "r"(S_NPW));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -304,25 +251,21 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    if (tid < nseg) {  // per segment: instruction descriptor, a panel and T offsets in descriptor units (16 B), accumulator column
+        const int n = T.seg_cols[tid];
+        seginfo[tid] = make_int4((int)((1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(SM_ROWS >> 4) << 24)),
+                                 T.seg_panel[tid] * (S_PANEL_BYTES >> 4), T.seg_off[tid], T.seg_off[tid]);
+    }
+    if (tid == 32) {   // read-back list
+        int n0 = 0;
+        for (int g = 0; g < nseg; ++g)
+            for (int c = 0; c < T.seg_cols[g]; c += 16) blk[n0++] = T.seg_off[g] + c;
+        nblk[0] = n0;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const unsigned tmem = *tmem_slot;
-    const int ncols = T.ncols, nseg = T.nseg;
-    if (tid < nseg) {  // per segment: instruction descriptor, a panel and T offsets in descriptor units (16 B), accumulator
-        const int n = T.seg_cols[tid];  // column | panel group << 16
-        seginfo[tid] = make_int4((int)((1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(SM_ROWS >> 4) << 24)),
-                                 T.seg_panel[tid] * (S_PANEL_BYTES >> 4), T.seg_off[tid], T.seg_off[tid]);
-    }
-    if (tid == 32) {   // read-back lists
-        int n0 = 0;
-        for (int g = 0; g < nseg; ++g)
-            for (int c = 0; c < T.seg_cols[g]; c += 16) {
-                blk[n0++] = T.seg_off[g] + c;
-            }
-        nblk[0] = n0;
-    }
-    __syncthreads();
 
     const int CPR = (P.H + KC - 1) / KC;
     const long long total = (long long)analysis_items(0, P.H, P.H) * CPR;
@@ -339,72 +282,70 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
         const float *tsrc = P.Tt + (size_t)cbeg * P.trec + T.toff;
         const float *fsrc = Ft + ((size_t)cbeg * 4 + T.kind[0]) * (S_FK_BYTES / 4);
         int s = 0;
-        unsigned use = 0;  // how often stage s has been filled before
+        unsigned use = 0;  // how often slot s has been filled before
         for (int t = 0; t < nchunk; ++t) {
-            if (use) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
+            if (use) mbar_wait(done0 + 8 * s, (use - 1) & 1);
             if (lane == 0) {
-                unsigned char *st = stage0 + (size_t)s * stage_bytes;
-                const unsigned bar = full0 + 8 * s;
-                mbar_expect_tx(bar, t_bytes + S_FK_BYTES);
-                bulk_copy_hint(st, tsrc, t_bytes, bar, pol_t);
-                bulk_copy_hint(st + t_bytes_max, fsrc, S_FK_BYTES, bar, pol_f);
+                unsigned char *st = slot0 + (size_t)s * slot_bytes;
+                mbar_expect_tx(fready0 + 8 * s, S_FK_BYTES);
+                bulk_copy_hint(st + t_bytes_max, fsrc, S_FK_BYTES, fready0 + 8 * s, pol_f);
+                mbar_expect_tx(ready0 + 8 * s, t_bytes);
+                bulk_copy_hint(st, tsrc, t_bytes, ready0 + 8 * s, pol_t);
             }
             __syncwarp();
             tsrc += P.trec;
             fsrc += 4 * S_FK_BYTES / 4;
-            if (++s == NS) { s = 0; ++use; }
+            if (++s == S_NTEAM) { s = 0; ++use; }
         }
     } else if (warp < S_WARP_PROD0) {
-        // ---- issuing warps: segments wi, wi + S_NMMA, ..
+        // ---- issuing warps: segments wi, wi + S_NMMA, ..; a warp without segments has nothing to do
         const int wi = warp - 1;
-        int4 sg[S_SEG_PER_WARP];
+        if (wi < nactive) {
+            int4 sg[S_SEG_PER_WARP];
 #pragma unroll
-        for (int q = 0; q < S_SEG_PER_WARP; ++q) {
-            const int g = wi + q * S_NMMA;
-            sg[q] = g < nseg ? seginfo[g] : make_int4(0, 0, 0, -1);
-        }
-        int s = 0, ai = 0;
-        int since = 0;   // chunks accumulated since the last read-back
-        unsigned use = 0, ause = 0, nev = 0;
-        // shared-memory descriptors advance with the rings: only the 14-bit start address field changes
-        const unsigned long long dA0 = umma_desc(smem_u32(abase), SM_ROWS * 16, 128), dT0 = umma_desc(smem_u32(stage0), ncols * 16, 128);
-        unsigned long long dA = dA0, dT = dT0;
-        const unsigned long long lo_a = (unsigned long long)(S_PANEL_BYTES / 2 >> 4), lo_t = (unsigned long long)(2 * ncols);
-        const unsigned long long step_a = (unsigned long long)(S_ABUF_BYTES >> 4), step_t = (unsigned long long)(stage_bytes >> 4);
-        int to_event = s_first_event();  // chunks until the next read-back event
-        for (int t = 0; t < nchunk; ++t) {
-            if (to_event == 0) {  // event nev: its group's accumulators have been read back -> overwrite
-                mbar_wait(flushed, nev & 1);
-                since = 0;
-                ++nev;
-                to_event = BFLUSH_CHUNKS;
+            for (int q = 0; q < S_SEG_PER_WARP; ++q) {
+                const int g = wi + q * S_NMMA;
+                sg[q] = g < nseg ? seginfo[g] : make_int4(0, 0, 0, -1);
             }
-            mbar_wait(full0 + 8 * s, use & 1);
-            mbar_wait(aready0 + 8 * ai, ause & 1);
-            tc_fence_after();
-            if (lane == 0) {
-#pragma unroll
-                for (int q = 0; q < S_SEG_PER_WARP; ++q) {
-                    if (sg[q].w >= 0) {
-                        const unsigned long long a = dA + (unsigned long long)sg[q].y, b = dT + (unsigned long long)sg[q].z;
-                        const unsigned d = tmem + (unsigned)sg[q].w;
-                        const unsigned acc = since > 0 ? 1u : 0u;
-                        umma_tf32(d, a, b + lo_t, (unsigned)sg[q].x, acc);  // small terms first
-                        umma_tf32(d, a + lo_a, b, (unsigned)sg[q].x, 1u);
-                        umma_tf32(d, a, b, (unsigned)sg[q].x, 1u);
-                    }
+            int s = 0, since = 0;   // since: chunks accumulated since the last read-back
+            unsigned use = 0, nev = 0;
+            // shared-memory descriptors advance with the ring: only the 14-bit start address field changes
+            const unsigned long long dT0 = umma_desc(smem_u32(slot0), ncols * 16, 128);
+            const unsigned long long dA0 = umma_desc(smem_u32(slot0 + t_bytes_max + S_FK_BYTES), SM_ROWS * 16, 128);
+            unsigned long long dA = dA0, dT = dT0;
+            const unsigned long long lo_a = (unsigned long long)(S_PANEL_BYTES / 2 >> 4), lo_t = (unsigned long long)(2 * ncols);
+            const unsigned long long step = (unsigned long long)(slot_bytes >> 4);
+            int to_event = s_first_event();  // chunks until the next read-back event
+            for (int t = 0; t < nchunk; ++t) {
+                if (to_event == 0) {  // the accumulators have been read back -> overwrite
+                    mbar_wait(flushed, nev & 1);
+                    since = 0;
+                    ++nev;
+                    to_event = BFLUSH_CHUNKS;
                 }
-                umma_commit(empty0 + 8 * s);
-                umma_commit(adone0 + 8 * ai);
-                if (to_event == 1 || t == nchunk - 1) umma_commit(drained);  // a read-back follows this chunk
+                mbar_wait(ready0 + 8 * s, use & 1);
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < S_SEG_PER_WARP; ++q) {
+                        if (sg[q].w >= 0) {
+                            const unsigned long long a = dA + (unsigned long long)sg[q].y, b = dT + (unsigned long long)sg[q].z;
+                            const unsigned d = tmem + (unsigned)sg[q].w;
+                            umma_tf32(d, a, b + lo_t, (unsigned)sg[q].x, since > 0 ? 1u : 0u);  // small terms first
+                            umma_tf32(d, a + lo_a, b, (unsigned)sg[q].x, 1u);
+                            umma_tf32(d, a, b, (unsigned)sg[q].x, 1u);
+                        }
+                    }
+                    umma_commit(done0 + 8 * s);
+                    if (to_event == 1 || t == nchunk - 1) umma_commit(drained);  // a read-back follows this chunk
+                }
+                __syncwarp();
+                ++since;
+                --to_event;
+                dT += step;
+                dA += step;
+                if (++s == S_NTEAM) { s = 0; ++use; dT = dT0; dA = dA0; }
             }
-            __syncwarp();
-            ++since;
-            --to_event;
-            dT += step_t;
-            dA += step_a;
-            if (++s == NS) { s = 0; ++use; dT = dT0; }
-            if (++ai == S_NTEAM) { ai = 0; ++ause; dA = dA0; }
         }
     } else {
         // ---- producer teams
@@ -417,10 +358,10 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
         int tofs[S_PANELS];
 #pragma unroll
         for (int j = 0; j < S_PANELS; ++j) tofs[j] = reim * (LMAX + 1) + (T.panel_code[j < npanel ? j : 0] & 0xffff);
-        float *abuf = abase + team * (S_ABUF_BYTES / 4);
-        const unsigned my_ready = aready0 + 8 * team, my_done = adone0 + 8 * team;
-        int s = team % NS;
-        unsigned use = team / NS, ause = 0, nfl = 0;
+        const float *Fs = reinterpret_cast<const float *>(slot0 + (size_t)team * slot_bytes + t_bytes_max);
+        float *abuf = reinterpret_cast<float *>(slot0 + (size_t)team * slot_bytes + t_bytes_max + S_FK_BYTES);
+        const unsigned my_fready = fready0 + 8 * team, my_ready = ready0 + 8 * team, my_done = done0 + 8 * team;
+        unsigned use = 0;
         int kc = (int)((cbeg + team) % CPR);
         const float *trig = P.trig + (size_t)((cbeg + team) / CPR) * 4 * (LMAX + 1);
         bool had = false;  // the accumulators have been read back before: add to the partial sums
@@ -428,47 +369,59 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
         const int nregular = nchunk > ev0 ? (nchunk - 1 - ev0) / BFLUSH_CHUNKS + 1 : 0;  // events in front of chunks ev0 + k BFLUSH_CHUNKS < nchunk
         int nev = 0;
         for (int t = team; t < nchunk; t += S_NTEAM) {
-            if (ause) mbar_wait_relaxed(my_done, (ause - 1) & 1);  // the MMAs of chunk t-3 read this a buffer
             // truncation pre-compensation (BTRUNC_PER_MMA): the products of position pos of an interval of len chunks are
             // followed by 3 (len - 1 - pos) + 1 truncating accumulations
             int pos, len;
             s_interval(t, ev0, nchunk, pos, len);
             const float sg = sign * (1.0f + BTRUNC_PER_MMA * (float)(3 * (len - 1 - pos) + 1));
-            const float *Fs = reinterpret_cast<const float *>(stage0 + (size_t)s * stage_bytes + t_bytes_max);
-            mbar_wait_relaxed(full0 + 8 * s, use & 1);
+            float tA[S_PANELS], tB[S_PANELS];   // row trig of every panel, fetched before the waits
+#pragma unroll
+            for (int j = 0; j < S_PANELS; ++j) {
+                tA[j] = __ldg(trig + tofs[j]) * sg;
+                tB[j] = __ldg(trig + tofs[j] + 2 * (LMAX + 1)) * sg;
+            }
+            mbar_wait_relaxed(my_fready, use & 1);                    // the folds have landed
             const float4 fa = *reinterpret_cast<const float4 *>(Fs + fofs), fb = *reinterpret_cast<const float4 *>(Fs + fofs + 2 * SNV * KC);
+            // (the slot's previous MMAs retired before the copy warp refilled it: the a panels are free)
 #pragma unroll
             for (int j = 0; j < S_PANELS; ++j)
-                if (j < npanel) s_a_panel(fa, fb, abuf, trig, sg, tofs[j], oofs + j * (S_PANEL_BYTES / 4));
+                if (j < npanel) {
+                    float4 hi, lo;
+                    split_tf32(fmaf(fa.x, tA[j], fb.x * tB[j]), hi.x, lo.x);
+                    split_tf32(fmaf(fa.y, tA[j], fb.y * tB[j]), hi.y, lo.y);
+                    split_tf32(fmaf(fa.z, tA[j], fb.z * tB[j]), hi.z, lo.z);
+                    split_tf32(fmaf(fa.w, tA[j], fb.w * tB[j]), hi.w, lo.w);
+                    float *o = abuf + oofs + j * (S_PANEL_BYTES / 4);
+                    *reinterpret_cast<float4 *>(o) = hi;
+                    *reinterpret_cast<float4 *>(o + 2 * SM_ROWS * 4) = lo;
+                }
             fence_async_smem();  // generic-proxy panel writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
             if (lane == 0) mbar_arrive(my_ready);
             // read-back events in front of this chunk come AFTER its panels: the a panels do not depend on the accumulators, and
             // the issuing warps find them ready when the read-back is done
             while (nev < nregular && ev0 + nev * BFLUSH_CHUNKS <= t) {
-                s_flush_group(tmem, blk, nblk[0], out, had, drained, nev & 1, true);
+                s_flush(tmem, ncols, out, had, drained, nev & 1);
                 had = true;
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(flushed);
                 ++nev;
             }
-            ++ause;
-            s += S_NTEAM;
-            while (s >= NS) { s -= NS; ++use; }
+            ++use;
             kc += S_NTEAM;
             while (kc >= CPR) { kc -= CPR; trig += 4 * (LMAX + 1); }
         }
-        if (nchunk) {  // remaining events, then both groups after the final chunk
+        if (nchunk) {  // remaining events, then the read-back after the final chunk
             while (nev < nregular) {
-                s_flush_group(tmem, blk, nblk[0], out, had, drained, nev & 1, true);
+                s_flush(tmem, ncols, out, had, drained, nev & 1);
                 had = true;
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(flushed);
                 ++nev;
             }
-            s_flush_group(tmem, blk, nblk[0], out, had, drained, nev & 1, true);
+            s_flush(tmem, ncols, out, had, drained, nev & 1);
         } else {
             for (int i = tid - S_WARP_PROD0 * 32; i < ncols * BTM; i += S_NPROD) out[i] = 0.0f;
         }
