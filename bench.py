@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 One step = the hot path (`z3d_decompose`) over one batch of 128 synthetic 128^3 volumes per GPU: two tiles of 64
-volumes, each k_fold_tile -> 3 rounds of k_decompose_batched (tcgen05 3xTF32 contraction against the plan's basis tables)
--> k_reduce_batched.  N > 1 is launched by torchrun, one rank per GPU; the path shards by
+volumes, each k_fold_tile_kind -> k_decompose_stream (tcgen05 3xTF32 contraction, operand T streamed from the plan's HBM
+table) -> k_reduce_stream.  N > 1 is launched by torchrun, one rank per GPU; the path shards by
 independent volumes (weak scaling, no data-path collective); the voxel-sharded single-volume latency with its
 NCCL all-reduce is reported alongside as `sharded_single_volume`.  Rank 0 prints ONE JSON line.
 
@@ -140,7 +140,7 @@ def run_reference_arm(args):
                                    "(bounded sample), value extrapolated to whole volumes"},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -275,22 +275,19 @@ def run_gpu_arm(args):
         fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_max * 1e6 / 1e12     # 74.45 TFLOP/s at 1965 MHz
         info = plan.info()
         batched = info["batched_min"] > 0 and BATCH >= info["batched_min"]
-        if not batched:
-            raise SystemExit("bench.py: the batched tensor-core path is unavailable for this plan")
-        # z3d_decompose runs the batch in tiles of 64 volumes: k_fold_tile, ROUNDS x k_decompose_batched, k_reduce_batched
-        # per tile; last_kernel_ms() is the sum over the contraction launches of one call; the roofline unit is one
-        # tile (all its rounds: the row groups of one tile do not fit one launch)
-        rounds = info["batched_rounds_wide"]
-        n_launch = -(-BATCH // TILE) * rounds                         # k_decompose_batched launches per step
-        k_ms = float(np.mean(kernel_ms)) / n_launch                   # average duration of one launch (one round of a tile)
-        W = algorithmic_flops(nmom, DIM) * TILE / rounds              # algorithmic flops of one launch (a third of a 64-volume tile)
+        if not batched or info["stream_state"] != 2:
+            raise SystemExit("bench.py: the streamed-T tensor-core path is unavailable for this plan")
+        # z3d_decompose runs the batch in tiles of 64 volumes: k_fold_tile_kind, k_decompose_stream, k_reduce_stream per tile;
+        # last_kernel_ms() is the sum over the contraction launches of one call; the roofline unit is one launch = one tile
+        n_launch = -(-BATCH // TILE)                                  # k_decompose_stream launches per step
+        k_ms = float(np.mean(kernel_ms)) / n_launch                   # average duration of one launch
+        W = algorithmic_flops(nmom, DIM) * TILE                       # algorithmic flops of one launch (a 64-volume tile)
         achieved = W / (k_ms * 1e-3) / 1e12
-        # executed tensor work: 3 TF32 MMAs (128 x 64 x 8) per 128-row tile and 8-voxel chunk of the 16-fold folded volume
-        H = (DIM + 1) // 2
-        chunks = (H * (H + 1) // 2) * (-(-H // 8))
-        tiles_total = sum(-(-sum((ORDER - l) // 2 + 1 for l in range(m + pz, ORDER + 1, 2)) // 128)
-                          for m in range(ORDER + 1) for pz in (0, 1) if m + pz <= ORDER)
-        executed = 3.0 * tiles_total * chunks * 2 * 128 * (2 * TILE) * 8 / rounds
+        # executed tensor work: 3 TF32 MMAs (M = 128 = re/im x 64 volumes, K = 8) per moment row (padded to 16) and 8-voxel
+        # chunk of the 16-fold folded volume; T table bytes streamed per launch: 64 B per row and chunk
+        chunks, rows16 = info["chunks"], info["stream_rows16"]
+        executed = 3.0 * 2 * 128 * 8 * rows16 * chunks
+        t_bytes = 64.0 * rows16 * chunks
         bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0)))
         fma_live = [fma_peak_tflops(local, v, 4096) for v in (0, 1)]
         traffic = None
@@ -305,30 +302,35 @@ def run_gpu_arm(args):
             "config": {"workload": f"128^3 volumes, order 50 ({nmom} complex moments), batch of {BATCH} volumes per GPU per step "
                                    f"in tiles of {TILE}; inputs {BATCH * DIM ** 3 * 4 / 2 ** 20:.0f} MiB per GPU > 126 MB L2 (no flush needed)",
                        "dim": DIM, "order": ORDER, "batch_per_gpu": BATCH, "sharding": "independent volumes per GPU, no collective",
-                       "tile_volumes": TILE, "row_groups": info["batched_row_groups_wide"],
-                       "arithmetic": "3xTF32 tcgen05.mma (M 128, N 128, K 8), float32 accumulate (TMEM)"},
+                       "tile_volumes": TILE, "column_sets": info["stream_sets"], "chunk_splits": info["stream_splits"],
+                       "moment_rows_padded": rows16, "t_table_mib": info["stream_table_mib"],
+                       "arithmetic": "3xTF32 tcgen05.mma (M 128 = re/im x 64 volumes, N = moment rows of one (m, z parity), K 8), float32 "
+                                     "accumulate (TMEM), operand T = R_nl * Q_lm streamed from a plan-owned HBM table"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * DIM ** 3 * 4,
                     "d2h_bytes_per_step": BATCH * nmom * 8,
                     "how": "Plan.decompose_host -> z3d_decompose_host: pinned host volumes -> H2D -> kernels -> D2H moments, "
                            "64-volume groups double buffered"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "z3d::k_decompose_batched", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "kernel": "z3d::k_decompose_stream", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
                          "frac": achieved / bf16_peak, "traffic": traffic,
                          "kernel_ms": k_ms, "algorithmic_flops_per_launch": W, "launches_per_step": n_launch,
-                         "volumes_per_launch": TILE, "rounds_per_tile": rounds,
-                         "algorithmic_bytes_per_launch": TILE * (DIM ** 3 * 4 + nmom * 8) / rounds,
+                         "volumes_per_launch": TILE,
+                         "algorithmic_bytes_per_launch": TILE * (DIM ** 3 * 4 + nmom * 8),
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense cuBLAS bf16, kernel timed inside a long step); "
                                         "the kernel issues kind::tf32 MMAs whose dense peak is half of that",
                          "executed_tensor_flops_per_launch": executed, "executed_tflops": executed / (k_ms * 1e-3) / 1e12,
                          "executed_frac_of_tf32_peak": executed / (k_ms * 1e-3) / 1e12 / (bf16_peak / 2),
+                         "t_table_bytes_per_launch": t_bytes, "t_stream_gbs": t_bytes / (k_ms * 1e-3) / 1e9,
+                         "t_stream_frac_of_hbm_peak": t_bytes / (k_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6553.0)),
                          "fp32_peak_tflops": fp32_peak, "algorithmic_frac_of_fp32_peak": achieved / fp32_peak,
                          "fma_microbench_tflops": {"ffma": fma_live[0], "ffma2": fma_live[1]},
                          "note": "achieved = 4*N_mom*N^3 flops per volume (SURVEY 8d: complex MAC per moment and voxel, no symmetry) x 64 "
-                                 "volumes / k_decompose_batched time.  16-fold mirror/transpose folding and the real-valued "
-                                 "contraction execute 1/16 of that as useful MACs; 3xTF32 and 128-row tile padding bring the "
-                                 "executed tensor flops to `executed_tensor_flops_per_launch`",
-                         "hbm_frac": (TILE * (DIM ** 3 * 4 + nmom * 8) / rounds) / (k_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6553.0))},
+                                 "volumes / k_decompose_stream time; it exceeds the peak because 16-fold mirror/transpose folding and "
+                                 "the real-valued contraction execute 1/16 of that as useful MACs.  What the kernel really spends: "
+                                 "`executed_tensor_flops_per_launch` (3xTF32, rows padded to 16) on the tensor pipe and "
+                                 "`t_table_bytes_per_launch` of HBM reads (the T = R*Q table, hi and lo parts, streamed once per "
+                                 "tile) - the two resources are within 20 % of each other by design"},
             "cpu_baseline": cpu,
             "sharded_single_volume": {"ms": sharded_ms, "decompositions_per_s": 1e3 / sharded_ms, "gpus": world,
                                       "how": "one 128^3 volume replicated, the kernel's work list split evenly over the ranks, "
@@ -340,13 +342,31 @@ def run_gpu_arm(args):
                                                    "vectors in rank order through NVLink loads"},
             "reconstructions_per_s_per_gpu": rec_per_s,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL's version banner, library chatter) was
+    diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)   # native libraries (NCCL prints its version to stdout) and stray prints -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

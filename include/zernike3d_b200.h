@@ -66,7 +66,10 @@ int z3d_plan_destroy(z3d_plan *plan);
  * 5 threads per CTA, 6 tiles per thread, 7 dynamic smem bytes, 8 voxels per chunk, 9 SM count,
  * 10 useful accumulators, 11 padded accumulators, 12 smallest batch routed to the batched (tensor-core) analysis kernels
  * (0 = unavailable for this order / box), 13 row groups of the 32-volume tile kernel, 14 of the 64-volume one,
- * 15 smallest remaining batch that takes a 64-volume tile, 16 / 17 rounds (contraction launches per tile) of the two. */
+ * 15 smallest remaining batch that takes a 64-volume tile, 16 / 17 rounds (contraction launches per tile) of the two;
+ * streamed-T variant of the batched path (preferred when its table fits in device memory): 18 state (0 unavailable,
+ * 1 planned, 2 table resident), 19 column sets, 20 splits of the chunk list (sets x splits CTAs), 21 moment rows padded
+ * to 16, 22 size of the T table in MiB, 23 chunks of 8 folded voxels per volume. */
 int z3d_plan_info(const z3d_plan *plan, int *info, int n_info);
 
 /* Bytes of device scratch z3d_decompose / z3d_reconstruct need for `batch` volumes. */

@@ -5,6 +5,8 @@ Tolerances are the north-star's, norm-wise (relative L2 over the whole vector, S
 The reference itself is 2e-6 (64^3) .. 5e-6 (128^3) away from an exact evaluation because it sums float32
 products in BLAS (zm:2210); against the float64 oracle the kernels are held to a tighter 1.5e-6.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -16,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_MOM, TOL_MAP, TOL_INV = 1e-5, 1e-5, 1e-6
 TOL_EXACT = 1.5e-6
-# batches take the tensor-core path (3xTF32 products, TMEM accumulators, basis tables): T = R*Q is rounded to float32
+# batches take the tensor-core path (3xTF32 products, TMEM accumulators, basis / T tables): T = R*Q is rounded to float32
 # before the contraction, which costs a little against the float64 oracle (1.0e-6 at order 50, 1.4e-6 at order 60)
 TOL_EXACT_BATCHED = 2.0e-6
 
@@ -118,7 +120,8 @@ BATCHED = [("d16_o10", 13), ("d15_o8", 12), ("d32_o20", 35), ("d20_o25", 45), ("
 
 @pytest.mark.parametrize("name,count", BATCHED)
 def test_batched_tensor_core_path(plans, oracle_mod, name, count):
-    """Batches of >= info['batched_min'] volumes: k_fold_tile + basis tables + k_decompose_batched (tcgen05)."""
+    """Batches of >= info['batched_min'] volumes: basis / T tables + k_fold_tile_kind + k_decompose_stream (tcgen05, T streamed
+    from HBM) + k_reduce_stream; k_decompose_batched when the T table is disabled or does not fit."""
     from zernike3d_b200.plan import launch_count
 
     g = golden(name)
@@ -132,9 +135,11 @@ def test_batched_tensor_core_path(plans, oracle_mod, name, count):
     P.decompose(dv)                                           # first call also builds the basis tables
     l0 = launch_count()
     mb = P.decompose(dv)
-    tiles, left, covered = 0, count, 0                        # the C side's tiling: 64-volume tiles while >= wide_min are left,
-    while left >= info["batched_min"]:                        # then 32-volume tiles, then the per-volume kernel
-        take = min(64 if left >= info["batched_wide_min"] else 32, left)
+    stream = P.info()["stream_state"] == 2                    # streamed-T kernel (its table is resident after the first call)
+    assert stream or os.environ.get("Z3D_STREAM") == "0" or dim > 128
+    tiles, left, covered = 0, count, 0                        # the C side's tiling: streamed-T: 64-volume tiles; else 64-volume
+    while left >= info["batched_min"]:                        # tiles while >= wide_min are left, then 32-volume tiles; the rest
+        take = min(64 if (stream or left >= info["batched_wide_min"]) else 32, left)   # goes through the per-volume kernel
         tiles, left, covered = tiles + 1, left - take, covered + take
     tail = left
     assert launch_count() - l0 >= 3 * tiles + (2 if tail else 0)  # fold + contraction round(s) + reduction per tile, then the tail
@@ -157,6 +162,29 @@ def test_batched_tensor_core_path(plans, oracle_mod, name, count):
         assert rel_l2(mb[i], exact) < TOL_EXACT_BATCHED
         inv = P.invariants(dev(mb[i])).cpu().numpy()
         assert rel_l2(inv, oracle_mod.invariants(exact, order)) < TOL_INV
+
+
+@pytest.mark.parametrize("name,count", [("d32_o20", 35), ("c1_d64_o50", 70)])
+def test_batched_path_without_the_T_table(oracle_mod, monkeypatch, name, count):
+    """Z3D_STREAM=0 (or a T table that does not fit in device memory): the R / Q table kernel k_decompose_batched, 32- and
+    64-volume tiles; same results as the streamed-T kernel to the batched tolerance."""
+    from zernike3d_b200.plan import Plan
+
+    g = golden(name)
+    order, dim = int(g["order"]), int(g["dim"])
+    vols = np.stack([volume(int(g["seeds"][0]) + i, dim) for i in range(count)])
+    dv = dev(vols)
+    monkeypatch.setenv("Z3D_STREAM", "0")
+    old = Plan(order, dim)
+    monkeypatch.delenv("Z3D_STREAM")
+    new = Plan(order, dim)
+    mo, mn = old.decompose(dv).cpu().numpy(), new.decompose(dv).cpu().numpy()
+    assert old.info()["stream_state"] == 0 and new.info()["stream_state"] == 2
+    assert rel_l2(mo[0], g["moments"][0]) < TOL_MOM and rel_l2(mn[0], g["moments"][0]) < TOL_MOM
+    assert rel_l2(mo, mn) < 2 * TOL_EXACT_BATCHED
+    for i in (0, count - 1):
+        exact = oracle_mod.decompose(vols[i], order, oracle_mod.EXACT)
+        assert rel_l2(mo[i], exact) < TOL_EXACT_BATCHED and rel_l2(mn[i], exact) < TOL_EXACT_BATCHED
 
 
 def test_batched_128_order50_headline(plans, oracle_mod):

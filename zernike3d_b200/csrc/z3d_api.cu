@@ -834,11 +834,17 @@ extern "C" int z3d_plan_destroy(z3d_plan *pl) {
 
 extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
     if (!pl || !info) return fail(Z3D_ERR_INVALID, "z3d_plan_info: NULL argument");
-    const int v[18] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
+    const long long t_mb = pl->stream ? (long long)((double)pl->b_chunks * (double)pl->devs.trec * 4.0 / 1048576.0) : 0;
+    const int v[24] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
                        KC, pl->num_sms, pl->useful_acc, pl->padded_acc,
                        pl->batched ? pl->batched_min : 0, pl->devb[0].ngroups, pl->devb[1].ngroups, pl->batched ? pl->batched_wide : 0,
-                       pl->devb[0].nrounds, pl->devb[1].nrounds};
-    for (int i = 0; i < n && i < 18; ++i) info[i] = v[i];
+                       pl->devb[0].nrounds, pl->devb[1].nrounds,
+                       // streamed-T variant: 18 state (0 unavailable, 1 planned - the T table is built on the first batched call and
+                       // may still be refused for lack of device memory, 2 table resident), 19 column sets, 20 splits of the chunk
+                       // list, 21 moment rows padded to 16 (all sets), 22 T table MiB, 23 chunks of 8 folded voxels
+                       (pl->batched && pl->stream) ? (pl->stream_ready ? 2 : 1) : 0, pl->devs.nsets, pl->devs.nsplits, pl->s_ncols_all,
+                       (int)std::min<long long>(t_mb, 0x7fffffff), (int)std::min<long long>(pl->b_chunks, 0x7fffffff)};
+    for (int i = 0; i < n && i < 24; ++i) info[i] = v[i];
     return Z3D_OK;
 }
 

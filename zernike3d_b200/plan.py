@@ -23,7 +23,8 @@ class Plan:
     INFO_KEYS = ("order", "dim", "num_moments", "passes", "ctas", "threads", "tiles_per_thread", "smem_bytes",
                  "voxels_per_chunk", "sms", "useful_accumulators", "padded_accumulators",
                  "batched_min", "batched_row_groups", "batched_row_groups_wide", "batched_wide_min", "batched_rounds",
-                 "batched_rounds_wide")
+                 "batched_rounds_wide", "stream_state", "stream_sets", "stream_splits", "stream_rows16", "stream_table_mib",
+                 "chunks")
 
     def __init__(self, order: int, dim: int, device: int | None = None):
         if not torch.cuda.is_available():
@@ -49,8 +50,8 @@ class Plan:
 
     # ------------------------------------------------------------------ helpers
     def info(self) -> dict:
-        arr = (ctypes.c_int * 18)()
-        _lib.check(self._L.z3d_plan_info(self._h, arr, 18))
+        arr = (ctypes.c_int * 24)()
+        _lib.check(self._L.z3d_plan_info(self._h, arr, 24))
         return dict(zip(self.INFO_KEYS, list(arr)))
 
     def workspace_bytes(self, batch: int) -> int:
