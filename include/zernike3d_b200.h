@@ -72,6 +72,12 @@ int z3d_plan_destroy(z3d_plan *plan);
  * to 16, 22 size of the T table in MiB, 23 chunks of 8 folded voxels per volume. */
 int z3d_plan_info(const z3d_plan *plan, int *info, int n_info);
 
+/* Host-only planner query (no device needed): the column-set layout of the streamed-T batched analysis kernel for `order` on a
+ * device with `num_sms` SMs.  out[]: 0 available, 1 column sets, 2 splits of the chunk list, 3 moment rows padded to 16,
+ * 4 columns of the widest set, 5 violated invariants (0 = the layout passed its self-check), 6 / 7 most panels / segments of
+ * a set. */
+int z3d_stream_layout(int order, int num_sms, int *out, int n_out);
+
 /* Bytes of device scratch z3d_decompose / z3d_reconstruct need for `batch` volumes. */
 size_t z3d_workspace_bytes(const z3d_plan *plan, int batch);
 

@@ -61,3 +61,23 @@ def test_bad_arguments_rejected_before_touching_the_device():
     assert L.z3d_workspace_bytes(None, 1) == 0
     assert L.z3d_scale_moments(None, None, 1, None, 1, None, None) == _lib.ERR_INVALID
     assert L.z3d_reconstruct(None, None, 1, 0, 1, None, None, 0, None) == _lib.ERR_INVALID
+
+
+@pytest.mark.parametrize("sms", [148, 132, 64])
+def test_streamed_T_column_set_layout_for_every_order(sms):
+    """Host-only planner of the streamed-T batched kernel (z3d_stream.cuh): for every supported order the column sets respect
+    the kernel's limits (<= 512 accumulator columns, <= 4 panels, <= 8 segments of <= 256 rows, one fold kind), every moment
+    owns exactly one column and sets x splits fit the device."""
+    L = _lib.lib()
+    out = (ctypes.c_int * 8)()
+    for order in list(range(0, 75)):
+        assert L.z3d_stream_layout(order, sms, out, 8) == 0
+        ok, nsets, nsplits, rows16, widest, bad, maxpanel, maxseg = list(out)
+        nmom = L.z3d_num_moments(order)
+        if not ok:                       # no layout: batches of such a plan use k_decompose_batched / the per-volume kernel
+            continue
+        assert bad == 0, (order, list(out))
+        assert 1 <= nsets * nsplits <= sms and nmom <= rows16 <= nmom + 16 * (2 * (order + 1) + nsets)
+        assert widest <= 512 and rows16 % 16 == 0 and maxpanel <= 4 and maxseg <= 8
+    assert L.z3d_stream_layout(50, 148, out, 8) == 0 and list(out)[:4] == [1, 37, 4, 12832]
+    assert L.z3d_stream_layout(-1, 148, out, 8) == _lib.ERR_INVALID

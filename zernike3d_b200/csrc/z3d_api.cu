@@ -805,6 +805,48 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
     return Z3D_OK;
 }
 
+// Host-only: the column-set layout the streamed-T kernel would use (no device needed; tests/test_cabi.py checks its
+// invariants for every supported order).
+extern "C" int z3d_stream_layout(int order, int num_sms, int *out, int n_out) {
+    if (order < 0 || order > LMAX || num_sms < 1 || !out) return fail(Z3D_ERR_INVALID, "z3d_stream_layout: bad arguments");
+    HostPlan hp;
+    int rc = build_host_plan(order, hp);
+    if (rc) return rc;
+    HostPlanB hb;
+    build_batched_plan(order, num_sms, BCfg<64>::TILES, hp, hb);
+    HostPlanS hs;
+    if (hb.nrad > 0) build_stream_plan(order, num_sms, hb, hs, 0);
+    int v[8] = {hs.ok ? 1 : 0, hs.nsets, hs.nsplits, hs.ncols_all, hs.t_bytes_max / 64, 0, 0, 0};
+    if (hs.ok) {  // self-check: every set within the kernel's limits, every moment in exactly one column, columns in range
+        int bad = 0, maxpanel = 0, maxseg = 0;
+        std::vector<char> seen((size_t)hs.ncols_all, 0);
+        std::vector<int> base(hs.nsets + 1, 0);
+        for (int i = 0; i < hs.nsets; ++i) {
+            const StreamTabs &T = hs.tabs[i];
+            base[i + 1] = base[i] + T.ncols;
+            int cols = 0;
+            for (int g = 0; g < T.nseg; ++g) {
+                if (T.seg_cols[g] < 16 || T.seg_cols[g] > 256 || T.seg_cols[g] % 16 || T.seg_off[g] != cols) ++bad;
+                if (T.seg_panel[g] < 0 || T.seg_panel[g] >= T.npanel) ++bad;
+                cols += T.seg_cols[g];
+            }
+            if (cols != T.ncols || T.ncols > 512 || T.npanel < 1 || T.npanel > S_PANELS || T.nseg > S_SEGS || T.nkind != 1) ++bad;
+            if (T.toff != 16LL * base[i]) ++bad;
+            maxpanel = std::max(maxpanel, T.npanel);
+            maxseg = std::max(maxseg, T.nseg);
+        }
+        for (const int2 &c : hs.colmap) {
+            if (c.x < 0 || c.x >= hs.nsets || c.y < 0 || c.y >= hs.tabs[c.x].ncols || seen[base[c.x] + c.y]++) ++bad;
+        }
+        if (hs.nsets * hs.nsplits > num_sms || (int)hs.colsrc.size() != hs.ncols_all || base[hs.nsets] != hs.ncols_all) ++bad;
+        v[5] = bad;
+        v[6] = maxpanel;
+        v[7] = maxseg;
+    }
+    for (int i = 0; i < n_out && i < 8; ++i) out[i] = v[i];
+    return Z3D_OK;
+}
+
 extern "C" int z3d_plan_destroy(z3d_plan *pl) {
     if (!pl) return Z3D_OK;
     cudaSetDevice(pl->device);
