@@ -160,6 +160,11 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ unsigned long long l2_policy_evict_normal() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
     unsigned long long p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -170,26 +175,39 @@ __device__ __forceinline__ void bulk_copy_hint(void *dst, const void *src, unsig
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(mbar), "l"(pol) : "memory");
 }
 
+__device__ __forceinline__ float ld_hint(const float *p, unsigned long long pol) {
+    float v;
+    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_hint(float *p, float v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+
 // Accumulator read-back: accumulators -> added into the CTA's partial buffer [column][row].  Producer warp w can address lane
-// quarter w % 4; the 6 warps of a quarter take the 64-column blocks (w - 4) / 4, (w - 4) / 4 + 6.
+// quarter w % 4; the 6 warps of a quarter take the 32-column units iq, iq + 6, ..  A unit is one dependent round trip to L2
+// (tcgen05.ld, 32 loads, add, 32 stores) of 2 000 - 3 500 clk while the T stream saturates the memory system (measured with
+// clock64 stamps), and the tensor core idles until the slowest warp is through: the units are dealt out evenly (at most 3 per
+// warp for 512 columns) and the partial sums are kept L2-resident (evict-last; the folds, 537 MB per tile, are evict-normal).
 __device__ __forceinline__ void s_flush(unsigned tmem, int ncols, float *out, bool add, unsigned drained_bar, unsigned parity) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3;
+    const unsigned long long pol = l2_policy_evict_last();
     mbar_wait(drained_bar, parity);  // every MMA issued so far has retired
     tc_fence_after();
 #pragma unroll 1
-    for (int c64 = 64 * ((warp - S_WARP_PROD0) >> 2); c64 < ncols; c64 += 64 * (S_NPW / 4)) {
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            unsigned v[32];
-            tmem_ld32(tmem + ((unsigned)(32 * q) << 16) + c64 + 32 * half, v);
-            float *p = out + ((size_t)c64 + 32 * half) * BTM + 32 * q + lane;
-            if (add) {
+    for (int c32 = 32 * ((warp - S_WARP_PROD0) >> 2); c32 < ncols; c32 += 32 * (S_NPW / 4)) {
+        unsigned v[32];
+        tmem_ld32(tmem + ((unsigned)(32 * q) << 16) + c32, v);
+        float *p = out + (size_t)c32 * BTM + 32 * q + lane;
+        if (add) {
+            float old[32];
 #pragma unroll
-                for (int col = 0; col < 32; ++col) p[col * BTM] += __uint_as_float(v[col]);
-            } else {
+            for (int col = 0; col < 32; ++col) old[col] = ld_hint(p + col * BTM, pol);
 #pragma unroll
-                for (int col = 0; col < 32; ++col) p[col * BTM] = __uint_as_float(v[col]);
-            }
+            for (int col = 0; col < 32; ++col) st_hint(p + col * BTM, old[col] + __uint_as_float(v[col]), pol);
+        } else {
+#pragma unroll
+            for (int col = 0; col < 32; ++col) st_hint(p + col * BTM, __uint_as_float(v[col]), pol);
         }
     }
 }
@@ -275,10 +293,10 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
     float *out = partial + (size_t)blockIdx.x * BSLOT_WORDS;
 
     if (warp == S_WARP_TMA) {
-        // ---- copy warp: T block (evict-first: streamed once) and the folds of the set's kind (evict-last: every set of the
-        //      kind reads them)
+        // ---- copy warp: T block (evict-first: streamed once) and the folds of the set's kind (evict-normal: every set of the
+        //      kind reads them, within a short window)
         const unsigned t_bytes = (unsigned)ncols * 64u;
-        const unsigned long long pol_t = l2_policy_evict_first(), pol_f = l2_policy_evict_last();
+        const unsigned long long pol_t = l2_policy_evict_first(), pol_f = l2_policy_evict_normal();
         const float *tsrc = P.Tt + (size_t)cbeg * P.trec + T.toff;
         const float *fsrc = Ft + ((size_t)cbeg * 4 + T.kind[0]) * (S_FK_BYTES / 4);
         int s = 0;
