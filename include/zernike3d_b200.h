@@ -57,7 +57,7 @@ int z3d_nlm_table(int order, int *nlm);
  * materialised basis: recurrence coefficient tables (zm:1992-1998, 2013-2024), per-l tile tables and
  * the launch geometry, uploaded once to `device`.  No R_nl / Y_lm voxel grid is ever built.  Orders 0..74 and box sizes
  * 2..4096 are supported (Z3D_ERR_UNSUPPORTED beyond: the per-pass coefficient tables are sized for order 74; the
- * reference's documented use is order <= 60).  For batches of >= 12 volumes the first z3d_decompose call additionally
+ * reference's documented use is order <= 60).  For batches of >= 8 volumes (12 without the streamed-T table) the first z3d_decompose call additionally
  * builds the plan's folded R_nl / Q_lm factor tables on the device (see z3d_plan_info entry 12). */
 int z3d_plan_create(int order, int dim, int device, z3d_plan **out);
 int z3d_plan_destroy(z3d_plan *plan);

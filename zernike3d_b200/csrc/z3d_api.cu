@@ -794,6 +794,9 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
     }
 #undef UP
 
+    // break-even against the per-volume kernel: a streamed-T tile costs the same whatever it holds (3.9 ms at 128^3 / order 50,
+    // i.e. 6.2 volumes of the per-volume kernel; 4-5 at 64^3 and 96^3 / order 60); the R / Q table kernel breaks even at ~9
+    if (pl->stream) pl->batched_min = 8;
     if (const char *e = getenv("Z3D_BATCHED_MIN")) pl->batched_min = std::max(1, atoi(e));  // tuning / tests
     if (const char *e = getenv("Z3D_BATCHED_WIDE")) pl->batched_wide = std::max(1, atoi(e));
     rc = set_kernel_attrs((int)prop.sharedMemPerBlockOptin);  // per-function attribute: plans of any size coexist
