@@ -14,10 +14,11 @@
 // A CTA owns a *column set* - up to 512 accumulator columns (all of tensor memory) made of segments of <= 256 moment rows
 // of <= S_PANELS different (m, pz) - and one split of the chunk list.  Sets are packed by the planner (z3d_api.cu) to
 // equal cost; a (m, pz) may be cut between two sets.  The folds are stored by *kind* = (m parity, pz): a panel needs only
-// the 4 fold classes of its kind (8 KB per chunk), a set spans at most two kinds.
+// the 4 fold classes of its kind (8 KB per chunk), a set holds one kind.
 //
-// HBM is the roofline of this kernel: every tile streams the whole T table once (64 B x rows16 x chunks), against
-// 3 x 2 x 128 x 8 flops per row and chunk on the tensor pipe.
+// Designed floors per tile: the HBM stream of T (every tile streams the whole table once, 64 B x rows16 x chunks) and
+// 3 x 2 x 128 x 8 flops per row and chunk on the tensor pipe, within 20 % of each other; DESIGN.md section 3 has what the kernel
+// measures against them and why.
 #pragma once
 #include "z3d_batched.cuh"
 
