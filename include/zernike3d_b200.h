@@ -135,6 +135,11 @@ int z3d_invariants(const z3d_plan *plan, const float *d_moments, int batch, floa
 int z3d_scale_moments(const z3d_plan *plan, const float *d_dims, int ncomp, const float *d_latents, int npoints,
                       float *d_out, void *stream);
 
+/* Per-order correlation of two moment sets ("Zernike FSC"; replaces Z_3DVA.calc_ZCC, moment_analysis_3dva.py:402-422):
+ *   out[b][n] = sum |A conj(B)| / sqrt(sum |A|^2 sum |B|^2) over the stored moments (m >= 0) of order n, n = 0..order.
+ * d_moments_a / d_moments_b [batch][num_moments] complex64, d_out [batch][order + 1] float32; 0 / 0 gives NaN like numpy. */
+int z3d_zcc(const z3d_plan *plan, const float *d_moments_a, const float *d_moments_b, int batch, float *d_out, void *stream);
+
 /* Host-buffer convenience calls: the same operations for callers that hold numpy / C arrays, the way
  * zm's Decompose(volume, ...) receives `mrc.data` and Reconstruct() returns a host map.  They stage
  * through pinned memory owned by the plan, overlap H2D copies with compute in chunks of volumes, and

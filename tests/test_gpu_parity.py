@@ -252,6 +252,26 @@ def test_latent_scaling_on_device_matches_apply_scaling(plans, tmp_path):
     assert len(jobs) == P.num_moments
 
 
+def test_zcc_on_device_matches_the_host_curve(plans):
+    """z3d_zcc (Plan.zcc) against Moments.zcc, the restatement of Z_3DVA.calc_ZCC (moment_analysis_3dva.py:402-422)."""
+    from zernike3d_b200.moments import Moments
+
+    order, dim = 20, 32
+    P = plans(order, dim)
+    vols = np.stack([volume(40 + i, dim) for i in range(4)])
+    mom = P.decompose(dev(vols))
+    curves = P.zcc(mom[:2], mom[2:]).cpu().numpy()            # pairs (0, 2) and (1, 3)
+    assert curves.shape == (2, order + 1)
+    M = Moments()
+    for i in range(4):
+        M.from_array(mom[i].cpu().numpy(), order)
+        M.add_dimension()
+    for p, (i, j) in enumerate(((0, 2), (1, 3))):
+        assert np.allclose(curves[p], M.zcc(M, i, j), rtol=2e-6, atol=1e-7)
+    same = P.zcc(mom[0], mom[0]).cpu().numpy()
+    assert same.shape == (order + 1,) and np.allclose(same, 1.0, atol=1e-6)
+
+
 def test_slab_partials_are_additive_and_only_read_their_planes(plans):
     order, dim = 20, 32
     P = plans(order, dim)

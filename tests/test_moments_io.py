@@ -121,3 +121,34 @@ def test_mrc_roundtrip(tmp_path):
     open(q, "wb").write(b"short")
     with pytest.raises(ValueError):
         mrc.read(q)
+
+
+def test_zcc_curve_matches_the_reference_formula():
+    """Moments.zcc against a literal restatement of Z_3DVA.calc_ZCC (moment_analysis_3dva.py:402-422)."""
+    from zernike3d_b200.moments import Moments
+
+    order = 9
+    rng = np.random.default_rng(4)
+    A, B = Moments(), Moments()
+    for M in (A, B):
+        for n in range(order + 1):
+            for l in range(n % 2, n + 1, 2):
+                for m in range(l + 1):
+                    M.set_moment(n, l, m, np.complex64(rng.normal() + 1j * rng.normal() * (m > 0)))
+        M.add_dimension()
+    got = A.zcc(B)
+    want = []
+    a, b = A.ndmoments[0], B.ndmoments[0]
+    for n in range(order + 1):          # calc_ZCC, line by line
+        _sum, xs, ys = [], [], []
+        for l in range(n + 1):
+            if (n - l) % 2 == 0:
+                for m in range(l + 1):
+                    momA = a[(n, l, m)]
+                    momB = np.conjugate(b[(n, l, m)])
+                    _sum.append(np.abs(momA * momB))
+                    xs.append(momA)
+                    ys.append(momB)
+        want.append(np.sum(_sum) / np.sqrt(np.sum(np.abs(xs) ** 2) * np.sum(np.abs(ys) ** 2)))
+    assert got.shape == (order + 1,) and np.allclose(got, want, rtol=1e-6)
+    assert np.allclose(A.zcc(A), 1.0, atol=1e-6)

@@ -1161,6 +1161,17 @@ extern "C" int z3d_invariants(const z3d_plan *pl, const float *d_moments, int ba
     return Z3D_OK;
 }
 
+extern "C" int z3d_zcc(const z3d_plan *pl, const float *d_moments_a, const float *d_moments_b, int batch, float *d_out, void *stream) {
+    if (!pl || !d_moments_a || !d_moments_b || !d_out || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_zcc: bad arguments");
+    if (batch > 65535) return fail(Z3D_ERR_INVALID, "z3d_zcc: at most 65535 pairs per call");
+    CUDA_TRY(cudaSetDevice(pl->device));
+    dim3 g(pl->order + 1, batch);
+    k_zcc<<<g, 32, 0, (cudaStream_t)stream>>>(d_moments_a, d_moments_b, pl->order, pl->nmom, batch, d_out);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    return Z3D_OK;
+}
+
 extern "C" int z3d_scale_moments(const z3d_plan *pl, const float *d_dims, int ncomp, const float *d_latents, int npoints,
                                  float *d_out, void *stream) {
     if (!pl || !d_dims || !d_out || ncomp < 0 || npoints < 1 || (ncomp > 0 && !d_latents))

@@ -913,6 +913,34 @@ __global__ void k_invariants(const float *__restrict__ moments, const int *__res
     inv[(size_t)b * nrad + q] = (float)sqrt(s);
 }
 
+// "Zernike FSC" of two moment sets (moment_analysis_3dva.py calc_ZCC, ma:402-422): per order n, over its stored moments (m >= 0),
+//   c_n = sum |A conj(B)| / sqrt(sum |A|^2 * sum |B|^2).        One warp per (order, pair); float64 sums; 0 / 0 -> NaN like numpy.
+__global__ void k_zcc(const float *__restrict__ ma, const float *__restrict__ mb, int order, int nmom, int batch,
+                      float *__restrict__ out) {
+    const int n = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+    int base = 0;  // moments of the orders < n: sum over k < n of sum over l = k, k-2, .. of (l + 1)
+    for (int k = 0; k < n; ++k)
+        for (int l = k & 1; l <= k; l += 2) base += l + 1;
+    int cnt = 0;
+    for (int l = n & 1; l <= n; l += 2) cnt += l + 1;
+    const float2 *A = reinterpret_cast<const float2 *>(ma) + (size_t)b * nmom + base;
+    const float2 *B = reinterpret_cast<const float2 *>(mb) + (size_t)b * nmom + base;
+    double nom = 0.0, d1 = 0.0, d2 = 0.0;
+    for (int i = lane; i < cnt; i += 32) {
+        const float2 a = A[i], c = B[i];
+        const double a2 = (double)a.x * a.x + (double)a.y * a.y, b2 = (double)c.x * c.x + (double)c.y * c.y;
+        nom += sqrt(a2 * b2);  // |A conj(B)| = |A| |B|
+        d1 += a2;
+        d2 += b2;
+    }
+    for (int o = 16; o; o >>= 1) {
+        nom += __shfl_xor_sync(0xffffffffu, nom, o);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    }
+    if (lane == 0) out[(size_t)b * (order + 1) + n] = (float)(nom / sqrt(d1 * d2));
+}
+
 // FP32 FMA throughput probes for the roofline denominator
 // 3DVA latent scaling: out[p][e] = dims[0][e] + sum_k lat[p][k] * dims[k+1][e] over the 2 * nmom float components (zm:78-95)
 __global__ void k_scale_moments(const float *__restrict__ dims, int ncomp, const float *__restrict__ lat, int npoints, int nelem,

@@ -91,6 +91,21 @@ class Moments:
             self.ndinvariants[dimension] = {nl: np.float32(np.sqrt(v)) for nl, v in acc.items()}
         self.invariants = {}
 
+    def zcc(self, other, dimension=0, other_dimension=0):
+        """Per-order correlation curve against another ``Moments`` ("Zernike FSC", ``Z_3DVA.calc_ZCC``
+        moment_analysis_3dva.py:402-422): c_n = sum |A conj(B)| / sqrt(sum |A|^2 sum |B|^2) over the stored moments of order n.
+        The device version for batches is ``Plan.zcc`` (``z3d_zcc``)."""
+        a, b = self.ndmoments[dimension], other.ndmoments[other_dimension]
+        order = max(n for (n, _, _) in a)
+        nom, d1, d2 = np.zeros(order + 1), np.zeros(order + 1), np.zeros(order + 1)
+        for (n, l, m), va in a.items():
+            vb = np.conjugate(b[(n, l, m)])
+            nom[n] += np.abs(va * vb)
+            d1[n] += np.abs(va) ** 2
+            d2[n] += np.abs(vb) ** 2
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return (nom / np.sqrt(d1 * d2)).astype(np.float32)
+
     def apply_scaling(self, z_ind=None, scales=None):
         """Omega = [1, latent...] . Omega_dims   (zm:78-95)."""
         mat = self.as_matrix()  # [K+1, num_moments]

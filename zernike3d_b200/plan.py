@@ -163,6 +163,18 @@ class Plan:
         _lib.check(self._L.z3d_invariants(self._h, _ptr(m), m.shape[0], _ptr(out), self._stream(stream)))
         return out[0] if single else out
 
+    def zcc(self, moments_a: torch.Tensor, moments_b: torch.Tensor, stream=None) -> torch.Tensor:
+        """Per-order correlation curve(s) of two moment sets on the device (``Z_3DVA.calc_ZCC``, moment_analysis_3dva.py:402-422):
+        ``[num_moments]`` or ``[B, num_moments]`` complex64 each -> ``[order + 1]`` or ``[B, order + 1]`` float32."""
+        single = moments_a.dim() == 1
+        a = (moments_a.unsqueeze(0) if single else moments_a).contiguous()
+        b = (moments_b.unsqueeze(0) if single else moments_b).contiguous()
+        if a.shape != b.shape or a.shape[1] != self.num_moments:
+            raise ValueError("zcc: moment sets of different shapes")
+        out = torch.empty((a.shape[0], self.order + 1), dtype=torch.float32, device=a.device)
+        _lib.check(self._L.z3d_zcc(self._h, _ptr(a), _ptr(b), a.shape[0], _ptr(out), self._stream(stream)))
+        return out[0] if single else out
+
     # ------------------------------------------------------------------ host-buffer API
     def decompose_host(self, vol, out=None):
         """numpy / pinned-tensor volumes ``[B, N, N, N]`` float32 -> numpy complex64 ``[B, num_moments]``.
