@@ -185,6 +185,12 @@ def test_batched_path_without_the_T_table(oracle_mod, monkeypatch, name, count):
     for i in (0, count - 1):
         exact = oracle_mod.decompose(vols[i], order, oracle_mod.EXACT)
         assert rel_l2(mo[i], exact) < TOL_EXACT_BATCHED and rel_l2(mn[i], exact) < TOL_EXACT_BATCHED
+    # a T table that is refused for lack of memory (here: by the cap) silently leaves the plan on the R / Q table kernel
+    monkeypatch.setenv("Z3D_STREAM_MAX_GB", "0.000001")
+    capped = Plan(order, dim)
+    assert capped.info()["stream_state"] == 1
+    mc = capped.decompose(dv).cpu().numpy()
+    assert capped.info()["stream_state"] == 0 and np.array_equal(mc, mo)
 
 
 def test_batched_128_order50_headline(plans, oracle_mod):
