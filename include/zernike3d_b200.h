@@ -140,6 +140,13 @@ int z3d_scale_moments(const z3d_plan *plan, const float *d_dims, int ncomp, cons
  * d_moments_a / d_moments_b [batch][num_moments] complex64, d_out [batch][order + 1] float32; 0 / 0 gives NaN like numpy. */
 int z3d_zcc(const z3d_plan *plan, const float *d_moments_a, const float *d_moments_b, int batch, float *d_out, void *stream);
 
+/* Pre-processing of an ensemble on the device (replaces ZernikeSpherical.bin_crop_array_center zm:2781-2815 and the --bin branch
+ * of run() zm:2867-2876, which loop over host arrays with scipy): crop = 0 keeps the box, else the centred crop
+ * v[c - half : c + half], half = (crop - crop % 2) / 2, around (cz, cy, cx); then nearest-neighbour resampling to n_out^3 with
+ * the index arithmetic of scipy.ndimage.zoom(order = 0) (n_out = round(box / bin) is the caller's; n_out = box: crop only).
+ * d_in [batch][n_in]^3, d_out [batch][n_out]^3 float32.  No plan needed. */
+int z3d_crop_bin(const float *d_in, int batch, int n_in, int cz, int cy, int cx, int crop, int n_out, float *d_out, void *stream);
+
 /* Host-buffer convenience calls: the same operations for callers that hold numpy / C arrays, the way
  * zm's Decompose(volume, ...) receives `mrc.data` and Reconstruct() returns a host map.  They stage
  * through pinned memory owned by the plan, overlap H2D copies with compute in chunks of volumes, and

@@ -61,6 +61,7 @@ def test_bad_arguments_rejected_before_touching_the_device():
     assert L.z3d_workspace_bytes(None, 1) == 0
     assert L.z3d_scale_moments(None, None, 1, None, 1, None, None) == _lib.ERR_INVALID
     assert L.z3d_zcc(None, None, None, 1, None, None) == _lib.ERR_INVALID
+    assert L.z3d_crop_bin(None, 1, 32, 16, 16, 16, 0, 16, None, None) == _lib.ERR_INVALID
     assert L.z3d_reconstruct(None, None, 1, 0, 1, None, None, 0, None) == _lib.ERR_INVALID
 
 

@@ -278,6 +278,26 @@ def test_zcc_on_device_matches_the_host_curve(plans):
     assert same.shape == (order + 1,) and np.allclose(same, 1.0, atol=1e-6)
 
 
+@pytest.mark.parametrize("n,crop,bin_,center", [(32, None, 2, None), (32, 20, None, (14, 16, 17)), (40, 24, 2, (20, 19, 21)),
+                                                  (33, None, 3, None), (64, 48, 1.5, (30, 33, 32)), (31, 17, 2.5, (15, 15, 16))])
+def test_crop_bin_on_device_is_bit_identical_to_the_host_path(n, crop, bin_, center):
+    """z3d_crop_bin (plan.crop_bin) against ZernikeSpherical.bin_crop_array_center / scipy.ndimage.zoom(order=0), the host path
+    that mirrors zm:2781-2815 and zm:2867-2876 (index work: bit-exact, including scipy's out-of-range zero at e.g. 32 -> 16)."""
+    import scipy.ndimage
+
+    from zernike3d_b200.plan import crop_bin
+    from zernike3d_b200.spherical import ZernikeSpherical
+
+    rng = np.random.default_rng(n)
+    vols = (rng.normal(size=(3, n, n, n)) + 2.0).astype(np.float32)
+    got = crop_bin(dev(vols), crop_to=crop, bin=bin_, center=center).cpu().numpy()
+    if crop is not None:
+        want = np.stack(ZernikeSpherical.bin_crop_array_center(list(vols), crop, bin=bin_, center=center))
+    else:
+        want = np.stack([scipy.ndimage.zoom(v, 1 / bin_, order=0) for v in vols])
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
 def test_slab_partials_are_additive_and_only_read_their_planes(plans):
     order, dim = 20, 32
     P = plans(order, dim)

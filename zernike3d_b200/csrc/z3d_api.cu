@@ -1172,6 +1172,27 @@ extern "C" int z3d_zcc(const z3d_plan *pl, const float *d_moments_a, const float
     return Z3D_OK;
 }
 
+extern "C" int z3d_crop_bin(const float *d_in, int batch, int n_in, int cz, int cy, int cx, int crop, int n_out, float *d_out,
+                            void *stream) {
+    if (!d_in || !d_out || batch < 1 || batch > 65535 || n_in < 1 || n_out < 1 || crop < 0)
+        return fail(Z3D_ERR_INVALID, "z3d_crop_bin: bad arguments");
+    int nc = n_in, oz = 0, oy = 0, ox = 0;
+    if (crop > 0) {  // v[c - half : c + half] on every axis (zm:2796-2800)
+        const int half = (crop - crop % 2) / 2;
+        nc = 2 * half;
+        oz = cz - half; oy = cy - half; ox = cx - half;
+        if (nc < 1 || oz < 0 || oy < 0 || ox < 0 || oz + nc > n_in || oy + nc > n_in || ox + nc > n_in)
+            return fail(Z3D_ERR_INVALID, "z3d_crop_bin: crop box %d around (%d, %d, %d) leaves the %d^3 volume", crop, cz, cy, cx, n_in);
+    }
+    if (n_out > nc) return fail(Z3D_ERR_INVALID, "z3d_crop_bin: output box %d larger than the cropped box %d", n_out, nc);
+    const size_t per = (size_t)n_out * n_out * n_out;
+    dim3 g((unsigned)((per + 255) / 256), batch);
+    k_crop_bin<<<g, 256, 0, (cudaStream_t)stream>>>(d_in, n_in, oz, oy, ox, nc, n_out, d_out);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    return Z3D_OK;
+}
+
 extern "C" int z3d_scale_moments(const z3d_plan *pl, const float *d_dims, int ncomp, const float *d_latents, int npoints,
                                  float *d_out, void *stream) {
     if (!pl || !d_dims || !d_out || ncomp < 0 || npoints < 1 || (ncomp > 0 && !d_latents))

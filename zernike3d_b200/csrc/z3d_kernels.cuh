@@ -941,6 +941,31 @@ __global__ void k_zcc(const float *__restrict__ ma, const float *__restrict__ mb
     if (lane == 0) out[(size_t)b * (order + 1) + n] = (float)(nom / sqrt(d1 * d2));
 }
 
+// Pre-processing of an ensemble on the device (ZernikeSpherical.bin_crop_array_center zm:2781-2815, run() zm:2867-2876): centred
+// crop, then scipy.ndimage.zoom(v, 1 / bin, order = 0): output index i samples input coordinate x = i (nc - 1) / (n_out - 1)
+// (float64), nearest neighbour floor(x + 0.5), and - scipy's mode = 'constant' - 0 when x falls outside [0, nc - 1], which
+// rounding makes happen for the last sample of some sizes (e.g. 32 -> 16).  One thread per output voxel.
+__device__ __forceinline__ int zoom0_index(int i, int nc, int n_out, bool &inside) {
+    if (n_out == nc) {
+        inside = true;
+        return i;
+    }
+    const double x = n_out > 1 ? (double)i * ((double)(nc - 1) / (double)(n_out - 1)) : 0.0;
+    inside = x >= 0.0 && x <= (double)(nc - 1);
+    return min(max((int)floor(x + 0.5), 0), nc - 1);
+}
+__global__ void k_crop_bin(const float *__restrict__ in, int n_in, int oz, int oy, int ox, int nc, int n_out, float *__restrict__ out) {
+    const size_t per = (size_t)n_out * n_out * n_out;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= per) return;
+    const int b = blockIdx.y;
+    const int k = (int)(e % n_out), j = (int)((e / n_out) % n_out), i = (int)(e / ((size_t)n_out * n_out));
+    bool a, c, d;
+    const int zi = zoom0_index(i, nc, n_out, a), yi = zoom0_index(j, nc, n_out, c), xi = zoom0_index(k, nc, n_out, d);
+    const float v = in[(size_t)b * n_in * n_in * n_in + ((size_t)(oz + zi) * n_in + (oy + yi)) * n_in + (ox + xi)];
+    out[(size_t)b * per + e] = (a && c && d) ? v : 0.0f;
+}
+
 // FP32 FMA throughput probes for the roofline denominator
 // 3DVA latent scaling: out[p][e] = dims[0][e] + sum_k lat[p][k] * dims[k+1][e] over the 2 * nmom float components (zm:78-95)
 __global__ void k_scale_moments(const float *__restrict__ dims, int ncomp, const float *__restrict__ lat, int npoints, int nelem,

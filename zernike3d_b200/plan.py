@@ -235,6 +235,25 @@ class PeerComm:
             pass
 
 
+def crop_bin(volumes: torch.Tensor, crop_to: int | None = None, bin: float | None = None, center=None, stream=None) -> torch.Tensor:
+    """Centred crop and nearest-neighbour binning of ``[B, N, N, N]`` (or ``[N, N, N]``) float32 CUDA volumes on the device, with
+    the index arithmetic of ``ZernikeSpherical.bin_crop_array_center`` / ``scipy.ndimage.zoom(order=0)`` (zm:2781-2815,
+    2867-2876) - bit-identical to the host path, for ensembles that are already in device memory."""
+    single = volumes.dim() == 3
+    v = (volumes.unsqueeze(0) if single else volumes).contiguous()
+    if v.dtype != torch.float32 or not v.is_cuda or v.shape[1] != v.shape[2] or v.shape[2] != v.shape[3]:
+        raise ValueError("crop_bin: need float32 CUDA volumes [B, N, N, N]")
+    n_in = int(v.shape[1])
+    crop = 0 if crop_to is None else int(crop_to)
+    box = n_in if crop == 0 else 2 * int((crop - crop % 2) / 2)
+    n_out = box if bin is None else int(round(box * (1 / bin)))
+    cz, cy, cx = (n_in // 2,) * 3 if center is None else (int(c) for c in center)
+    out = torch.empty((v.shape[0], n_out, n_out, n_out), dtype=torch.float32, device=v.device)
+    s = torch.cuda.current_stream() if stream is None else stream
+    _lib.check(_lib.lib().z3d_crop_bin(_ptr(v), v.shape[0], n_in, cz, cy, cx, crop, n_out, _ptr(out), ctypes.c_void_p(s.cuda_stream)))
+    return out[0] if single else out
+
+
 def launch_count() -> int:
     return int(_lib.lib().z3d_launch_count())
 
