@@ -142,6 +142,11 @@ constexpr int S_SEG_PER_WARP = (S_SEGS + S_NMMA - 1) / S_NMMA;
 // read-backs (360 KB per CTA and event) over the interval instead of bursting it from all 148 CTAs at once
 __device__ __forceinline__ int s_first_event() { return (int)(blockIdx.x % 8 + 1) * (BFLUSH_CHUNKS / 8); }
 
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+    unsigned p;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void mbar_arrive(unsigned mbar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
@@ -344,7 +349,10 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
                 }
                 mbar_wait(ready0 + 8 * s, use & 1);
                 tc_fence_after();
-                if (lane == 0) {
+                // converged warp + elect.sync: the MMAs of the elected lane compile to back-to-back UTCHMMA on uniform registers
+                // (an `if (lane == 0)` region costs an ELECT / R2UR / BRA.U.ANY loop per instruction: 64-72 clk per MMA for
+                // any N against 23 clk or the tensor pipe's N / 2, scripts/experiments/tc_probe4.cu)
+                if (elect_one()) {
 #pragma unroll
                     for (int q = 0; q < S_SEG_PER_WARP; ++q) {
                         if (sg[q].w >= 0) {
