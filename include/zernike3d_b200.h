@@ -64,12 +64,15 @@ int z3d_plan_destroy(z3d_plan *plan);
 
 /* Plan queries (host only). info[]: 0 order, 1 dim, 2 num_moments, 3 passes, 4 CTAs per launch,
  * 5 threads per CTA, 6 tiles per thread, 7 dynamic smem bytes, 8 voxels per chunk, 9 SM count,
- * 10 useful accumulators, 11 padded accumulators, 12 smallest batch routed to the batched (tensor-core) analysis kernels
+ * 10 useful accumulators, 11 padded accumulators, 12 smallest batch routed to the TABLE-FED batched analysis kernels
  * (0 = unavailable for this order / box), 13 row groups of the 32-volume tile kernel, 14 of the 64-volume one,
  * 15 smallest remaining batch that takes a 64-volume tile, 16 / 17 rounds (contraction launches per tile) of the two;
  * streamed-T variant of the batched path (preferred when its table fits in device memory): 18 state (0 unavailable,
  * 1 planned, 2 table resident), 19 column sets, 20 splits of the chunk list (sets x splits CTAs), 21 moment rows padded
- * to 16, 22 size of the T table in MiB, 23 chunks of 8 folded voxels per volume. */
+ * to 16, 22 size of the T table in MiB, 23 chunks of 8 folded voxels per volume;
+ * table-free tensor-core variant (the default for batches): 24 available, 25 column sets, 26 splits, 27 accumulator columns over all
+ * sets, 28 depth of the shared-memory T ring, 29 smallest batch routed to it, 30 basis-table level in use (z3d_plan_prepare_tables),
+ * 31 columns of the widest set. */
 int z3d_plan_info(const z3d_plan *plan, int *info, int n_info);
 
 /* Host-only planner query (no device needed): the column-set layout of the streamed-T batched analysis kernel for `order` on a
@@ -77,6 +80,21 @@ int z3d_plan_info(const z3d_plan *plan, int *info, int n_info);
  * 4 columns of the widest set, 5 violated invariants (0 = the layout passed its self-check), 6 / 7 most panels / segments of
  * a set. */
 int z3d_stream_layout(int order, int num_sms, int *out, int n_out);
+
+/* Host-only planner query (no device needed): the column-set layout of the table-free tensor-core batched analysis kernel
+ * (the default for batches) for `order` on a device with `num_sms` SMs.  out[]: 0 available, 1 column sets, 2 splits of the chunk
+ * list, 3 accumulator columns over all sets, 4 columns of the widest set, 5 violated invariants (0 = self-check passed),
+ * 6 / 7 / 8 most a panels / MMA segments / recurrence-chain tasks of a set, 9 most seed rows, 10 estimated clocks per chunk. */
+int z3d_gen_layout(int order, int num_sms, int *out, int n_out);
+
+/* Opt-in basis tables.  The default path never materialises a basis function: batches run through a tensor-core kernel that
+ * generates R_nl * Q_lm in registers.  A caller with memory to spare may instead ask for the table-fed kernels of round 1:
+ * level 1 = folded R_nl / Q_lm factor tables (1.1 GB at 128^3 / order 50), level 2 = additionally the folded product table
+ * T = R Q (13.7 GB) that the TMA engine streams into the tensor core's operand layout.  Synchronous (the tables are complete on
+ * return, usable from any stream afterwards); max_bytes caps the T table (0 = 45 % of the free device memory); *level_out
+ * receives the level reached (a table that does not fit is not an error); level 0 frees the tables again.  Not thread-safe
+ * against concurrent calls on the same plan. */
+int z3d_plan_prepare_tables(z3d_plan *plan, int level, size_t max_bytes, int *level_out);
 
 /* Bytes of device scratch z3d_decompose / z3d_reconstruct need for `batch` volumes. */
 size_t z3d_workspace_bytes(const z3d_plan *plan, int batch);

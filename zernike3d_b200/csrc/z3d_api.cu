@@ -3,6 +3,7 @@
 #include "z3d_kernels.cuh"
 #include "z3d_batched.cuh"
 #include "z3d_stream.cuh"
+#include "z3d_gen.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -50,6 +51,24 @@ inline int num_radial(int order) {
     return c;
 }
 
+// Every entry point runs on the plan's device and restores the caller's current device on return (a library call must not
+// change torch.cuda.current_device() of the calling thread).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) err = cudaSetDevice(dev);
+        else prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define USE_DEVICE(dev)            \
+    DeviceGuard _guard(dev);       \
+    CUDA_TRY(_guard.err)
+
 template <class T>
 int upload(const std::vector<T> &h, T **d, std::vector<void *> &owned) {
     CUDA_TRY(cudaMalloc((void **)d, std::max<size_t>(1, h.size()) * sizeof(T)));
@@ -82,6 +101,13 @@ struct z3d_plan {
     int4 *d_colsrc = nullptr;
     int2 *d_colmap = nullptr;
     float *d_Tt = nullptr;
+    int tables_level = 0;        // 0: no basis tables (default), 1: R / Q tables, 2: R / Q + T tables (z3d_plan_prepare_tables)
+    // table-free tensor-core variant (z3d_gen.cuh): the default for batches
+    bool gen = false;
+    int gen_min = 4;             // smallest (remaining) batch routed to it
+    DevPlanG devg{};
+    int g_smem = 0, g_ncols_all = 0, g_maxcols = 0;
+    int2 *d_gcolmap = nullptr;
     // reduce / prepare tables
     int *d_src = nullptr;        // [2*nmom]  pass*SLOT_WORDS + word
     double *d_scale = nullptr;   // [nmom]    coeff(n) * kappa_lm
@@ -96,6 +122,7 @@ struct z3d_plan {
     float *d_stage_mom[2] = {nullptr, nullptr};
     void *d_stage_ws[2] = {nullptr, nullptr};
     int stage_batch = 0;
+    bool staged_ok = false;
     // optional per-kernel timing (bench.py roofline): events around the dominant kernel of the last call
     bool profiling = false;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;       // synthesis kernel / fused path
@@ -575,7 +602,7 @@ void build_stream_plan(int L, int num_sms, const HostPlanB &hb, HostPlanS &hs, i
         for (const Piece &p : best[si]) cols += p.cols;
         T.ncols = cols;
         T.toff = toff;
-        T.kind[0] = T.kind[1] = 0;
+        T.kind[0] = 0;
         int off = 0;
         for (const Piece &p : best[si]) {
             const Group &g = groups[p.group];
@@ -621,6 +648,212 @@ void build_stream_plan(int L, int num_sms, const HostPlanB &hb, HostPlanS &hs, i
     hs.ok = true;
 }
 
+// ---- planner of the table-free variant (z3d_gen.cuh) ------------------------------------------------------------------
+struct HostPlanG {
+    bool ok = false;
+    int nsets = 0, nsplits = 0, maxcols = 0, maxseedrows = 0, gd_entries = 0, rk_entries = 0, ncols_all = 0;
+    double est_period = 0.0;
+    std::vector<GenTabs> tabs;
+    std::vector<int4> tasks;
+    std::vector<float2> gd;
+    std::vector<float4> rk;
+    std::vector<int2> colmap;
+};
+
+// Column sets of the table-free kernel.  The moment rows of every (m, pz) are a list of CHAINS (l = m + pz, m + pz + 2, ..: the
+// rows n = l, l + 2, .. of one chain are produced by one thread's recurrence), laid end to end in kind order and cut - at chain
+// boundaries only - into sets of equal estimated tensor-pipe time per chunk: an MMA of N columns takes max(24, N / 2) clocks
+// (scripts/experiments/tc_probe4.cu), three per segment.  Limits per set: accumulator columns + 2 a-panel slots of 16 columns
+// per panel <= 512 (tensor memory), <= G_PANELS panels, <= G_SEGS segments, <= G_TASKS chain tasks, one kind.
+void build_gen_plan(int L, int num_sms, const HostPlan &hp, HostPlanG &hg, int force_splits) {
+    const int S = L + 1;
+    struct Chain { int l, len; };
+    struct Group { int kind, m, pz; std::vector<Chain> chains; };
+    std::vector<Group> groups;
+    for (int mp = 0; mp < 2; ++mp)
+        for (int pz = 0; pz < 2; ++pz)
+            for (int m = mp; m <= L; m += 2) {
+                Group g{(mp << 1) | pz, m, pz, {}};
+                for (int l = m + pz; l <= L; l += 2) g.chains.push_back({l, (L - l) / 2 + 1});
+                if (!g.chains.empty()) groups.push_back(std::move(g));
+            }
+    struct Piece { int group, first, count, rows; };   // chains [first, first + count) of the group, rows = sum of their lengths
+    typedef std::vector<std::vector<Piece>> Sets;
+    auto pad16 = [](int x) { return (x + 15) / 16 * 16; };
+    auto piece_cost = [&](int rows) {
+        double c = 48.0;  // a panel: the a-panel team's work
+        for (int c0 = 0, cols = pad16(rows); c0 < cols; c0 += 256) c += 3.0 * std::max(24.0, 0.5 * std::min(256, cols - c0));
+        return c;
+    };
+    auto set_cost = [&](const std::vector<Piece> &st) {
+        double c = 0.0;
+        for (const Piece &p : st) c += piece_cost(p.rows);
+        return c;
+    };
+    auto fits = [&](const std::vector<Piece> &st) {
+        int cols = 0, segs = 0, chains = 0;
+        for (const Piece &p : st) {
+            cols += pad16(p.rows);
+            segs += (pad16(p.rows) + 255) / 256;
+            chains += p.count;
+        }
+        return cols + 32 * (int)st.size() <= 512 && (int)st.size() <= G_PANELS && segs <= G_SEGS && 2 * chains <= G_TASKS;
+    };
+    auto pack = [&](double cap) {
+        Sets sets;
+        std::vector<Piece> cur;
+        auto close = [&]() {
+            if (!cur.empty()) sets.push_back(cur);
+            cur.clear();
+        };
+        for (int gi = 0; gi < (int)groups.size(); ++gi) {
+            const Group &g = groups[gi];
+            if (!cur.empty() && groups[cur.back().group].kind != g.kind) close();
+            for (int ci = 0; ci < (int)g.chains.size(); ++ci) {
+                std::vector<Piece> trial = cur;
+                if (!trial.empty() && trial.back().group == gi) {
+                    trial.back().count += 1;
+                    trial.back().rows += g.chains[ci].len;
+                } else {
+                    trial.push_back({gi, ci, 1, g.chains[ci].len});
+                }
+                if (!cur.empty() && (!fits(trial) || set_cost(trial) > cap)) {
+                    close();
+                    trial.assign(1, Piece{gi, ci, 1, g.chains[ci].len});
+                }
+                cur = trial;
+            }
+        }
+        close();
+        return sets;
+    };
+    Sets best;
+    double best_t = 1e300;
+    int best_splits = 0;
+    const double PMIN = 300.0, POVH = 40.0;   // shortest sustainable chunk period, per-chunk overhead on top of the tensor time
+    for (int ns = 1; ns <= 16; ++ns) {
+        if (force_splits > 0 && ns != force_splits) continue;
+        const int target = num_sms / ns;
+        if (target < 1) break;
+        double lo = 0.0, hi = 1e7;
+        if ((int)pack(hi).size() > target) continue;
+        for (int it = 0; it < 50; ++it) {
+            const double mid = 0.5 * (lo + hi);
+            if ((int)pack(mid).size() > target) lo = mid; else hi = mid;
+        }
+        Sets st = pack(hi);
+        double mx = 0.0;
+        for (auto &x : st) mx = std::max(mx, set_cost(x));
+        const double t = (std::max(mx, PMIN) + POVH) / ns;
+        if (t < best_t) { best_t = t; best = st; best_splits = ns; hg.est_period = std::max(mx, PMIN) + POVH; }
+    }
+    if (best.empty()) return;
+    hg.nsets = (int)best.size();
+    hg.nsplits = best_splits;
+    // radial tables by parity of l: (K1, K2, K3, 0) of zm:1992-1998, l-major, entry 0 of a chain = (0, 0, 1): R_ll = r^l enters as seed
+    std::vector<int> rkoff(S, 0);
+    std::vector<float4> rkp[2];
+    for (int l = 0; l <= L; ++l) {
+        std::vector<float4> &t = rkp[l & 1];
+        rkoff[l] = (int)t.size();
+        for (int n = l; n <= L; n += 2) {
+            float4 K = make_float4(0.f, 0.f, 1.f, 0.f);
+            if (n > l) {
+                const double k0 = (double)(n - l) * (n + l + 1) * (2 * n - 3);
+                const double k1 = (double)(2 * n - 1) * (2 * n + 1) * (2 * n - 3);
+                const double k2 = 0.5 * (double)(-2 * n + 1) * (double)((2 * l + 1) * (2 * l + 1)) - k1 / 2.0;
+                const double k3 = -1.0 * (double)(n - l - 2) * (n + l - 1) * (2 * n + 1);
+                K = make_float4((float)(k1 / k0), (float)(k2 / k0), (float)(k3 / k0), 0.f);
+            }
+            t.push_back(K);
+        }
+    }
+    hg.rk_entries = (int)std::max(rkp[0].size(), rkp[1].size()) + 8;
+    hg.rk.assign((size_t)2 * hg.rk_entries, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int par = 0; par < 2; ++par) std::copy(rkp[par].begin(), rkp[par].end(), hg.rk.begin() + (size_t)par * hg.rk_entries);
+    std::vector<int> mubase((size_t)S * S, -1);
+    {
+        int mu = 0;
+        for (int n = 0; n <= L; ++n)
+            for (int l = n & 1; l <= n; l += 2) {
+                mubase[(size_t)n * S + l] = mu;
+                mu += l + 1;
+            }
+    }
+    hg.tabs.assign(hg.nsets, GenTabs{});
+    hg.tasks.assign((size_t)hg.nsets * G_TASKS, make_int4(0, 0, 0, 0));
+    hg.colmap.assign(num_moments(L), make_int2(-1, -1));
+    int maxgd = 0;
+    for (const auto &st : best) {
+        int rows = 0;
+        for (const Piece &p : st) rows += p.first + p.count;
+        maxgd = std::max(maxgd, rows);
+    }
+    hg.gd_entries = maxgd + 64;
+    hg.gd.assign((size_t)hg.nsets * hg.gd_entries, make_float2(0.f, 0.f));
+    for (int si = 0; si < hg.nsets; ++si) {
+        GenTabs &T = hg.tabs[si];
+        const auto &st = best[si];
+        T.npanel = (int)st.size();
+        T.kind = groups[st[0].group].kind;
+        T.lpar = (groups[st[0].group].m + groups[st[0].group].pz) & 1;
+        T.acol0 = 512 - 2 * 16 * T.npanel;
+        struct TaskC { int row0, len, rk, srow; };
+        std::vector<TaskC> chains;
+        int off = 0, soff = 0, gdo = 0;
+        for (int j = 0; j < T.npanel; ++j) {
+            const Piece &p = st[j];
+            const Group &g = groups[p.group];
+            const int cols = pad16(p.rows), l0 = g.m + g.pz;
+            T.panel_m[j] = g.m;
+            T.panel_pz[j] = g.pz;
+            T.panel_nl[j] = p.first + p.count;   // the seed recurrence starts at l0 whichever chain the piece starts with
+            T.panel_soff[j] = soff;
+            T.panel_gd[j] = gdo;
+            const double *bm = &hp.beta[(size_t)g.m * (S + 3)];
+            auto B = [&](int l) { return (l >= 0 && l < S + 3) ? bm[l] : 0.0; };
+            for (int i = 0; i + 1 < T.panel_nl[j]; ++i) {  // step l -> l + 2: (gamma_l, -delta_l)
+                const int l = l0 + 2 * i;
+                hg.gd[(size_t)si * hg.gd_entries + gdo + i] = make_float2((float)(B(l + 2) + B(l + 1)), (float)(-(B(l + 1) * B(l))));
+            }
+            gdo += T.panel_nl[j];
+            for (int c0 = 0; c0 < cols; c0 += 256) {
+                T.seg_cols[T.nseg] = std::min(256, cols - c0);
+                T.seg_off[T.nseg] = off + c0;
+                T.seg_panel[T.nseg] = j;
+                ++T.nseg;
+            }
+            int r = 0;
+            for (int ci = p.first; ci < p.first + p.count; ++ci) {
+                const Chain &ch = g.chains[ci];
+                chains.push_back({off + r, ch.len, rkoff[ch.l], soff + ci});
+                for (int i = 0; i < ch.len; ++i) hg.colmap[mubase[(size_t)(ch.l + 2 * i) * S + ch.l] + g.m] = make_int2(si, off + r + i);
+                r += ch.len;
+            }
+            soff += T.panel_nl[j];
+            off += cols;
+        }
+        T.ncols = off;
+        T.nseedrows = soff;
+        hg.maxcols = std::max(hg.maxcols, off);
+        hg.maxseedrows = std::max(hg.maxseedrows, soff);
+        hg.ncols_all += off;
+        // tasks: chains sorted by length (longest first), in blocks of 16 chains: 16 x k half 0, then 16 x k half 1 (a quarter
+        // warp's 16-byte stores then belong to 8 different chains)
+        std::stable_sort(chains.begin(), chains.end(), [](const TaskC &a, const TaskC &b) { return a.len > b.len; });
+        int nt = 0;
+        for (size_t c0 = 0; c0 < chains.size(); c0 += 16)
+            for (int kh = 0; kh < 2; ++kh)
+                for (size_t c = c0; c < std::min(chains.size(), c0 + 16); ++c)
+                    hg.tasks[(size_t)si * G_TASKS + nt++] = make_int4(chains[c].row0, chains[c].len, chains[c].rk, chains[c].srow | (kh << 16));
+        T.ntask = nt;
+        if (nt > G_TASKS || T.nseg > G_SEGS || T.ncols + 32 * T.npanel > 512) return;
+    }
+    for (const int2 &r : hg.colmap)
+        if (r.x < 0) return;
+    hg.ok = true;
+}
+
 template <int NPH>
 int set_kernel_attrs_t(int smem) {
     CUDA_TRY(cudaFuncSetAttribute(k_decompose<NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -639,6 +872,8 @@ int set_kernel_attrs(int smem) {
     CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUDA_TRY(cudaFuncSetAttribute(k_decompose_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaFuncSetAttribute(k_decompose_stream, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_gen, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return set_kernel_attrs_t<0>(smem);
 }
 
@@ -655,7 +890,7 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
         return fail(Z3D_ERR_NODEVICE, "z3d_plan_create: no CUDA device (this library has no CPU fallback)");
     }
     if (device < 0 || device >= ndev) return fail(Z3D_ERR_INVALID, "z3d_plan_create: device %d of %d", device, ndev);
-    CUDA_TRY(cudaSetDevice(device));
+    USE_DEVICE(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
@@ -792,6 +1027,38 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
             }
         }
     }
+    if (dim >= 14) {  // table-free variant (dim >= 14 keeps every 8-voxel chunk and its z-mirror inside a row)
+        HostPlanG hg;
+        int force = 0;
+        if (const char *e = getenv("Z3D_GEN_SPLITS")) force = atoi(e);
+        const char *off = getenv("Z3D_GEN");
+        if (!(off && atoi(off) == 0)) build_gen_plan(order, prop.multiProcessorCount, hp, hg, force);
+        if (hg.ok) {
+            DevPlanG &g = pl->devg;
+            g.order = order; g.dim = dim; g.H = pl->H; g.nsets = hg.nsets; g.nsplits = hg.nsplits;
+            g.tslot_bytes = hg.maxcols * 64;
+            g.gslot_bytes = (40 + hg.maxseedrows * 8) * 4;
+            g.gd_bytes = hg.gd_entries * 8;
+            g.rk_bytes = hg.rk_entries * 16;
+            g.off_rk = (G_OFF_GD + g.gd_bytes + 15) / 16 * 16;
+            g.off_g = g.off_rk + g.rk_bytes;
+            g.off_t = (g.off_g + G_DG * g.gslot_bytes + 127) / 128 * 128;
+            g.dbg = 0;
+            if (const char *e = getenv("Z3D_GEN_DBG")) g.dbg = atoi(e);
+            g.nslots = std::min(G_NS_MAX, ((int)prop.sharedMemPerBlockOptin - g.off_t) / g.tslot_bytes);
+            if (const char *e = getenv("Z3D_GEN_SLOTS")) g.nslots = std::max(2, std::min(g.nslots, atoi(e)));
+            if (g.nslots >= G_NTT) {   // a T team's first chunk behind a read-back must find a free slot (see z3d_gen.cuh)
+                GenTabs *d_tabs; int4 *d_tasks; float2 *d_ggd; float4 *d_grk;
+                UP(hg.tabs, d_tabs) UP(hg.tasks, d_tasks) UP(hg.gd, d_ggd) UP(hg.rk, d_grk) UP(hg.colmap, pl->d_gcolmap)
+                g.tabs = d_tabs; g.tasks = d_tasks; g.gd = d_ggd; g.rk = d_grk; g.side = d_side;
+                pl->g_smem = g.off_t + g.nslots * g.tslot_bytes;
+                pl->g_ncols_all = hg.ncols_all;
+                pl->g_maxcols = hg.maxcols;
+                pl->b_chunks = (long long)analysis_items(0, pl->H, pl->H) * ((pl->H + KC - 1) / KC);
+                pl->gen = true;
+            }
+        }
+    }
 #undef UP
 
     // break-even against the per-volume kernel: a streamed-T tile costs the same whatever it holds (3.9 ms at 128^3 / order 50,
@@ -799,6 +1066,7 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
     if (pl->stream) pl->batched_min = 8;
     if (const char *e = getenv("Z3D_BATCHED_MIN")) pl->batched_min = std::max(1, atoi(e));  // tuning / tests
     if (const char *e = getenv("Z3D_BATCHED_WIDE")) pl->batched_wide = std::max(1, atoi(e));
+    if (const char *e = getenv("Z3D_GEN_MIN")) pl->gen_min = std::max(1, atoi(e));
     rc = set_kernel_attrs((int)prop.sharedMemPerBlockOptin);  // per-function attribute: plans of any size coexist
     if (rc) {
         z3d_plan_destroy(pl);
@@ -850,9 +1118,66 @@ extern "C" int z3d_stream_layout(int order, int num_sms, int *out, int n_out) {
     return Z3D_OK;
 }
 
+// Host-only: the column-set layout of the table-free kernel (no device needed; tests/test_cabi.py checks its invariants).
+// out[]: 0 available, 1 sets, 2 splits, 3 columns (all sets), 4 widest set, 5 violated invariants, 6 most panels, 7 most
+// segments, 8 most chain tasks, 9 most seed rows, 10 estimated clocks per chunk of the slowest set
+extern "C" int z3d_gen_layout(int order, int num_sms, int *out, int n_out) {
+    if (order < 0 || order > LMAX || num_sms < 1 || !out) return fail(Z3D_ERR_INVALID, "z3d_gen_layout: bad arguments");
+    HostPlan hp;
+    int rc = build_host_plan(order, hp);
+    if (rc) return rc;
+    HostPlanG hg;
+    int force = 0;
+    if (const char *e = getenv("Z3D_GEN_SPLITS")) force = atoi(e);
+    build_gen_plan(order, num_sms, hp, hg, force);
+    if (getenv("Z3D_GEN_DUMP"))   // developer aid: the sets on stderr
+        for (int i = 0; i < hg.nsets && hg.ok; ++i) {
+            const GenTabs &T = hg.tabs[i];
+            fprintf(stderr, "set %d: kind %d cols %d segs %d panels %d tasks %d seedrows %d lpar %d acol0 %d |", i, T.kind, T.ncols, T.nseg, T.npanel,
+                    T.ntask, T.nseedrows, T.lpar, T.acol0);
+            for (int j = 0; j < T.npanel; ++j) fprintf(stderr, " (m %d pz %d nl %d soff %d gd %d)", T.panel_m[j], T.panel_pz[j], T.panel_nl[j], T.panel_soff[j], T.panel_gd[j]);
+            fprintf(stderr, " | segs");
+            for (int g = 0; g < T.nseg; ++g) fprintf(stderr, " %d@%d:p%d", T.seg_cols[g], T.seg_off[g], T.seg_panel[g]);
+            fprintf(stderr, "\n");
+        }
+    int v[11] = {hg.ok ? 1 : 0, hg.nsets, hg.nsplits, hg.ncols_all, hg.maxcols, 0, 0, 0, 0, hg.maxseedrows, (int)hg.est_period};
+    if (hg.ok) {
+        int bad = 0;
+        std::vector<std::vector<char>> seen(hg.nsets);
+        for (int i = 0; i < hg.nsets; ++i) {
+            const GenTabs &T = hg.tabs[i];
+            seen[i].assign(T.ncols, 0);
+            int cols = 0;
+            for (int g = 0; g < T.nseg; ++g) {
+                if (T.seg_cols[g] < 16 || T.seg_cols[g] > 256 || T.seg_cols[g] % 16 || T.seg_off[g] != cols) ++bad;
+                if (T.seg_panel[g] < 0 || T.seg_panel[g] >= T.npanel) ++bad;
+                cols += T.seg_cols[g];
+            }
+            if (cols != T.ncols || T.ncols + 32 * T.npanel > 512 || T.npanel < 1 || T.npanel > G_PANELS || T.nseg > G_SEGS) ++bad;
+            if (T.ntask > G_TASKS || T.acol0 != 512 - 32 * T.npanel) ++bad;
+            std::vector<char> covered(T.ncols, 0);   // every chain task writes its own rows, twice (two k halves)
+            for (int t = 0; t < T.ntask; ++t) {
+                const int4 tk = hg.tasks[(size_t)i * G_TASKS + t];
+                if (tk.y < 1 || tk.x < 0 || tk.x + tk.y > T.ncols || (tk.w & 0xffff) >= T.nseedrows || tk.z < 0 || tk.z + tk.y > hg.rk_entries) { ++bad; continue; }
+                for (int r = 0; r < tk.y; ++r) covered[tk.x + r] += 1;
+            }
+            for (int c = 0; c < T.ncols; ++c) if (covered[c] != 0 && covered[c] != 2) ++bad;
+            v[6] = std::max(v[6], T.npanel);
+            v[7] = std::max(v[7], T.nseg);
+            v[8] = std::max(v[8], T.ntask);
+        }
+        for (const int2 &c : hg.colmap)
+            if (c.x < 0 || c.x >= hg.nsets || c.y < 0 || c.y >= hg.tabs[c.x].ncols || seen[c.x][c.y]++) ++bad;
+        if (hg.nsets * hg.nsplits > num_sms) ++bad;
+        v[5] = bad;
+    }
+    for (int i = 0; i < n_out && i < 11; ++i) out[i] = v[i];
+    return Z3D_OK;
+}
+
 extern "C" int z3d_plan_destroy(z3d_plan *pl) {
     if (!pl) return Z3D_OK;
-    cudaSetDevice(pl->device);
+    DeviceGuard _guard(pl->device);
     for (void *p : pl->owned) cudaFree(p);
     if (pl->d_Rt) cudaFree(pl->d_Rt);
     if (pl->d_Qt) cudaFree(pl->d_Qt);
@@ -880,7 +1205,7 @@ extern "C" int z3d_plan_destroy(z3d_plan *pl) {
 extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
     if (!pl || !info) return fail(Z3D_ERR_INVALID, "z3d_plan_info: NULL argument");
     const long long t_mb = pl->stream ? (long long)((double)pl->b_chunks * (double)pl->devs.trec * 4.0 / 1048576.0) : 0;
-    const int v[24] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
+    const int v[32] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
                        KC, pl->num_sms, pl->useful_acc, pl->padded_acc,
                        pl->batched ? pl->batched_min : 0, pl->devb[0].ngroups, pl->devb[1].ngroups, pl->batched ? pl->batched_wide : 0,
                        pl->devb[0].nrounds, pl->devb[1].nrounds,
@@ -888,8 +1213,12 @@ extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
                        // may still be refused for lack of device memory, 2 table resident), 19 column sets, 20 splits of the chunk
                        // list, 21 moment rows padded to 16 (all sets), 22 T table MiB, 23 chunks of 8 folded voxels
                        (pl->batched && pl->stream) ? (pl->stream_ready ? 2 : 1) : 0, pl->devs.nsets, pl->devs.nsplits, pl->s_ncols_all,
-                       (int)std::min<long long>(t_mb, 0x7fffffff), (int)std::min<long long>(pl->b_chunks, 0x7fffffff)};
-    for (int i = 0; i < n && i < 24; ++i) info[i] = v[i];
+                       (int)std::min<long long>(t_mb, 0x7fffffff), (int)std::min<long long>(pl->b_chunks, 0x7fffffff),
+                       // table-free tensor-core variant: 24 available, 25 column sets, 26 splits, 27 moment rows padded to 16 per
+                       // chain piece, 28 T-ring slots, 29 smallest batch routed to it, 30 basis-table level in use, 31 widest set
+                       pl->gen ? 1 : 0, pl->devg.nsets, pl->devg.nsplits, pl->g_ncols_all, pl->devg.nslots, pl->gen ? pl->gen_min : 0,
+                       pl->tables_level, pl->g_maxcols};
+    for (int i = 0; i < n && i < 32; ++i) info[i] = v[i];
     return Z3D_OK;
 }
 
@@ -902,9 +1231,11 @@ static int decompose_group(const z3d_plan *pl) {
 }
 static size_t ws_decompose(const z3d_plan *pl, int batch) {
     size_t w = (size_t)std::min(batch, decompose_group(pl)) * pl->npass * pl->nsplit * SLOT_WORDS * sizeof(float);
-    if (pl->batched && batch >= pl->batched_min)  // per-(CTA, segment) partial sums + the folds of one tile of volumes
+    if (pl->tables_level > 0 && pl->batched && batch >= pl->batched_min)  // per-(CTA, segment) partial sums + the folds of one tile of volumes
         w = std::max(w, (size_t)pl->num_sms * std::max(pl->devb[0].nrounds, pl->devb[1].nrounds) * BSLOT_WORDS * sizeof(float) +
                             (size_t)pl->b_chunks * ((pl->stream || batch >= pl->batched_wide) ? BCfg<64>::F_BYTES : BCfg<32>::F_BYTES));
+    if (pl->gen && batch >= pl->gen_min)  // table-free tensor-core kernel: per-CTA partial sums + the folds of one tile of 64 volumes
+        w = std::max(w, (size_t)pl->num_sms * BSLOT_WORDS * sizeof(float) + (size_t)pl->b_chunks * 4 * S_FK_BYTES);
     return w;
 }
 static size_t ws_reconstruct(const z3d_plan *pl, int batch) {
@@ -953,7 +1284,6 @@ static int ensure_basis(z3d_plan *pl, cudaStream_t st) {
         if (pl->d_Rt) cudaFree(pl->d_Rt);
         if (pl->d_Qt) cudaFree(pl->d_Qt);
         pl->d_Rt = pl->d_Qt = pl->d_trig = nullptr;
-        pl->batched = false;
         return Z3D_OK;
     }
     pl->basis.Rt = pl->d_Rt; pl->basis.Qt = pl->d_Qt; pl->basis.trig = pl->d_trig;
@@ -970,17 +1300,16 @@ static int ensure_basis(z3d_plan *pl, cudaStream_t st) {
 
 // T table of the streamed variant (13.7 GB at 128^3 / order 50): built from the R / Q tables on the first batched call when it
 // fits in 45 % of the free device memory; otherwise the plan keeps to k_decompose_batched (R / Q tables, products in-kernel).
-static int ensure_stream(z3d_plan *pl, cudaStream_t st) {
+static int ensure_stream(z3d_plan *pl, cudaStream_t st, size_t max_bytes) {
     if (pl->stream_ready || !pl->stream || !pl->batched || !pl->basis_ready) return Z3D_OK;
     const size_t bytes = (size_t)pl->b_chunks * (size_t)pl->devs.trec * sizeof(float);
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     size_t limit = (size_t)(0.45 * (double)free_b);
-    if (const char *e = getenv("Z3D_STREAM_MAX_GB")) limit = std::min(limit, (size_t)(atof(e) * 1e9));
+    if (max_bytes) limit = std::min(limit, max_bytes);
     if (bytes > limit || cudaMalloc((void **)&pl->d_Tt, bytes) != cudaSuccess) {
         cudaGetLastError();
         pl->d_Tt = nullptr;
-        pl->stream = false;
         return Z3D_OK;
     }
     pl->devs.Tt = pl->d_Tt;
@@ -993,6 +1322,43 @@ static int ensure_stream(z3d_plan *pl, cudaStream_t st) {
     return Z3D_OK;
 }
 
+// Opt-in basis tables (NOT needed by the default path, which generates everything in registers): level 1 builds the folded
+// R_nl / Q_lm factor tables (k_decompose_batched), level 2 also the product table T = R Q that k_decompose_stream reads with the
+// TMA engine (13.7 GB at 128^3 / order 50).  Synchronous: the tables are complete when the call returns, so later calls on any
+// stream may use them.  max_bytes = 0: up to 45 % of the free device memory.  Returns the level actually reached in *level_out
+// (a table that does not fit is not an error).  Level 0 frees the tables and returns the plan to the table-free kernels.
+extern "C" int z3d_plan_prepare_tables(z3d_plan *pl, int level, size_t max_bytes, int *level_out) {
+    if (!pl || level < 0 || level > 2) return fail(Z3D_ERR_INVALID, "z3d_plan_prepare_tables: bad arguments");
+    USE_DEVICE(pl->device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (level == 0) {
+        if (pl->d_Tt) cudaFree(pl->d_Tt);
+        if (pl->d_Rt) cudaFree(pl->d_Rt);
+        if (pl->d_Qt) cudaFree(pl->d_Qt);
+        if (pl->d_trig) cudaFree(pl->d_trig);
+        pl->d_Tt = pl->d_Rt = pl->d_Qt = pl->d_trig = nullptr;
+        pl->basis_ready = pl->stream_ready = false;
+        pl->tables_level = 0;
+        if (level_out) *level_out = 0;
+        return Z3D_OK;
+    }
+    int reached = 0;
+    if (pl->batched) {
+        int rc = ensure_basis(pl, nullptr);
+        if (rc) return rc;
+        if (pl->basis_ready) reached = 1;
+        if (reached == 1 && level == 2 && pl->stream) {
+            rc = ensure_stream(pl, nullptr, max_bytes);
+            if (rc) return rc;
+            if (pl->stream_ready) reached = 2;
+        }
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    pl->tables_level = reached;
+    if (level_out) *level_out = reached;
+    return Z3D_OK;
+}
+
 static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int half_lo, int half_hi, int part, int nparts,
                           float *d_moments, void *d_ws, size_t ws_bytes, void *stream) {
     int rc = check_range(pl, batch, half_lo, half_hi, "z3d_decompose");
@@ -1000,7 +1366,7 @@ static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int
     if (!d_vol || !d_moments || !d_ws) return fail(Z3D_ERR_INVALID, "z3d_decompose: NULL buffer");
     if (ws_bytes < ws_decompose(pl, batch))
         return fail(Z3D_ERR_WORKSPACE, "z3d_decompose: workspace %zu < %zu bytes", ws_bytes, ws_decompose(pl, batch));
-    CUDA_TRY(cudaSetDevice(pl->device));
+    USE_DEVICE(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
     float *partial = (float *)d_ws;
     const int grp = decompose_group(pl);
@@ -1011,13 +1377,28 @@ static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int
     int done = 0;
     // batches: tiles of up to BNV volumes through the batched kernel (whole-volume calls only); what is left below
     // the threshold goes through the per-volume kernel
-    if (pl->batched && half_lo == 0 && half_hi == pl->H && batch >= pl->batched_min) {
-        rc = ensure_basis(mpl, st);
-        if (rc) return rc;
-        rc = ensure_stream(mpl, st);
-        if (rc) return rc;
+    const bool whole = half_lo == 0 && half_hi == pl->H;
+    // default for batches: the table-free tensor-core kernel (tiles of up to 64 volumes; a tile costs the same whatever it holds)
+    while (pl->gen && pl->tables_level == 0 && whole && batch - done >= pl->gen_min) {
+        const int nb = std::min(SNV, batch - done);
+        const DevPlanG &dp = pl->devg;
+        const float *vol = d_vol + (size_t)done * N3;
+        float *folds = partial + (size_t)pl->num_sms * BSLOT_WORDS;
+        float *mom = d_moments + (size_t)done * 2 * pl->nmom;
+        k_fold_tile_gen<<<(unsigned)pl->b_chunks, 2 * SNV * KC, 0, st>>>(vol, nb, pl->dim, pl->H, folds);
+        CUDA_TRY(cudaGetLastError());
+        const bool timed = pl->profiling && mpl->n_timed < z3d_plan::MAX_TIMED;
+        if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t0[mpl->n_timed], st));
+        k_decompose_gen<<<dp.nsets * dp.nsplits, GNT, pl->g_smem, st>>>(dp, folds, part, nparts, partial);
+        CUDA_TRY(cudaGetLastError());
+        if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t1[mpl->n_timed++], st));
+        k_reduce_stream<<<(pl->nmom * SM_ROWS + 255) / 256, 256, 0, st>>>(partial, pl->d_gcolmap, pl->d_scale, pl->nmom, dp.nsplits, nb, mom);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 3;
+        done += nb;
     }
-    while (pl->batched && pl->stream_ready && half_lo == 0 && half_hi == pl->H && batch - done >= pl->batched_min) {
+    // opt-in (z3d_plan_prepare_tables): the table-fed kernels
+    while (pl->tables_level == 2 && pl->batched && pl->stream_ready && whole && batch - done >= pl->batched_min) {
         // streamed-T variant: tiles of up to 64 volumes (a tile costs the same whatever it holds)
         const int nb = std::min(SNV, batch - done);
         const DevPlanS &dp = pl->devs;
@@ -1036,7 +1417,7 @@ static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int
         g_launches += 3;
         done += nb;
     }
-    while (pl->batched && half_lo == 0 && half_hi == pl->H && batch - done >= pl->batched_min) {
+    while (pl->tables_level >= 1 && pl->batched && pl->basis_ready && whole && batch - done >= pl->batched_min) {
         // a tile of up to 64 volumes when enough are left, else of up to 32 (a tile costs the same whatever it holds)
         const int wide = (batch - done >= pl->batched_wide) ? 1 : 0;
         const int nb = std::min(wide ? 64 : 32, batch - done);
@@ -1096,7 +1477,7 @@ extern "C" int z3d_reconstruct(const z3d_plan *pl, const float *d_moments, int b
     if (ws_bytes < ws_reconstruct(pl, batch))
         return fail(Z3D_ERR_WORKSPACE, "z3d_reconstruct: workspace %zu < %zu bytes", ws_bytes, ws_reconstruct(pl, batch));
     if (half_lo == half_hi) return Z3D_OK;
-    CUDA_TRY(cudaSetDevice(pl->device));
+    USE_DEVICE(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
     float *otiles = (float *)d_ws;
     float *pvol = otiles + (size_t)batch * pl->npass * SLOT_WORDS;
@@ -1120,7 +1501,7 @@ extern "C" int z3d_reconstruct(const z3d_plan *pl, const float *d_moments, int b
 
 extern "C" int z3d_profile_enable(z3d_plan *pl, int on) {
     if (!pl) return fail(Z3D_ERR_INVALID, "z3d_profile_enable: plan is NULL");
-    CUDA_TRY(cudaSetDevice(pl->device));
+    USE_DEVICE(pl->device);
     if (on && !pl->ev_k0) {
         CUDA_TRY(cudaEventCreate(&pl->ev_k0));
         CUDA_TRY(cudaEventCreate(&pl->ev_k1));
@@ -1153,7 +1534,7 @@ extern "C" int z3d_profile_last_ms(z3d_plan *pl, float *ms) {
 
 extern "C" int z3d_invariants(const z3d_plan *pl, const float *d_moments, int batch, float *d_inv, void *stream) {
     if (!pl || !d_moments || !d_inv || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_invariants: bad arguments");
-    CUDA_TRY(cudaSetDevice(pl->device));
+    USE_DEVICE(pl->device);
     dim3 g((pl->nrad + 127) / 128, batch);
     k_invariants<<<g, 128, 0, (cudaStream_t)stream>>>(d_moments, pl->d_nl_base, pl->d_nl_l, pl->nrad, pl->nmom, batch, d_inv);
     CUDA_TRY(cudaGetLastError());
@@ -1164,7 +1545,7 @@ extern "C" int z3d_invariants(const z3d_plan *pl, const float *d_moments, int ba
 extern "C" int z3d_zcc(const z3d_plan *pl, const float *d_moments_a, const float *d_moments_b, int batch, float *d_out, void *stream) {
     if (!pl || !d_moments_a || !d_moments_b || !d_out || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_zcc: bad arguments");
     if (batch > 65535) return fail(Z3D_ERR_INVALID, "z3d_zcc: at most 65535 pairs per call");
-    CUDA_TRY(cudaSetDevice(pl->device));
+    USE_DEVICE(pl->device);
     dim3 g(pl->order + 1, batch);
     k_zcc<<<g, 32, 0, (cudaStream_t)stream>>>(d_moments_a, d_moments_b, pl->order, pl->nmom, batch, d_out);
     CUDA_TRY(cudaGetLastError());
@@ -1198,7 +1579,7 @@ extern "C" int z3d_scale_moments(const z3d_plan *pl, const float *d_dims, int nc
     if (!pl || !d_dims || !d_out || ncomp < 0 || npoints < 1 || (ncomp > 0 && !d_latents))
         return fail(Z3D_ERR_INVALID, "z3d_scale_moments: bad arguments");
     if (npoints > 65535) return fail(Z3D_ERR_INVALID, "z3d_scale_moments: at most 65535 latent coordinates per call");
-    CUDA_TRY(cudaSetDevice(pl->device));
+    USE_DEVICE(pl->device);
     const int nelem = 2 * pl->nmom;
     dim3 g((nelem + 255) / 256, npoints);
     k_scale_moments<<<g, 256, 0, (cudaStream_t)stream>>>(d_dims, ncomp, d_latents, npoints, nelem, d_out);
@@ -1210,14 +1591,31 @@ extern "C" int z3d_scale_moments(const z3d_plan *pl, const float *d_dims, int nc
 // ------------------------------------------------------------------------------------------------
 // host-buffer calls: double-buffered groups of volumes, H2D on one stream, compute + D2H on another
 // ------------------------------------------------------------------------------------------------
-static int ensure_staging(z3d_plan *pl) {
-    if (pl->s_copy) return Z3D_OK;
-    CUDA_TRY(cudaSetDevice(pl->device));
+static void free_staging(z3d_plan *pl) {
+    for (int i = 0; i < 2; ++i) {
+        if (pl->d_stage_vol[i]) cudaFree(pl->d_stage_vol[i]);
+        if (pl->d_stage_mom[i]) cudaFree(pl->d_stage_mom[i]);
+        if (pl->d_stage_ws[i]) cudaFree(pl->d_stage_ws[i]);
+        if (pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]);
+        if (pl->ev_done[i]) cudaEventDestroy(pl->ev_done[i]);
+        pl->d_stage_vol[i] = pl->d_stage_mom[i] = nullptr;
+        pl->d_stage_ws[i] = nullptr;
+        pl->ev_in[i] = pl->ev_done[i] = nullptr;
+    }
+    if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
+    if (pl->s_comp) cudaStreamDestroy(pl->s_comp);
+    pl->s_copy = pl->s_comp = nullptr;
+    pl->staged_ok = false;
+}
+
+// Staging of the host-buffer calls; `staged_ok` is set only when every allocation succeeded (a partial failure frees everything,
+// so a later call starts from scratch instead of finding half-initialised buffers).  The caller holds the device guard.
+static int ensure_staging_impl(z3d_plan *pl) {
     const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
-    // group size: one wide tile of the batched kernels (64 volumes) when that path exists and a sixteenth of the free
-    // device memory holds the two stages; otherwise ~32 MiB of volume data per stage, at least 1 volume
+    // group size: one tile of the batched kernels (64 volumes) when that path exists and a sixteenth of the free device memory
+    // holds the two stages; otherwise ~32 MiB of volume data per stage, at least 1 volume
     int gb = (int)std::min<size_t>(32, std::max<size_t>(1, ((size_t)32 << 20) / (N3 * sizeof(float))));
-    if (pl->batched) {
+    if (pl->gen || pl->tables_level > 0) {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         const size_t need = 2 * ((size_t)64 * N3 * sizeof(float) + z3d_workspace_bytes(pl, 64));
@@ -1233,11 +1631,40 @@ static int ensure_staging(z3d_plan *pl) {
         CUDA_TRY(cudaMalloc((void **)&pl->d_stage_mom[i], (size_t)gb * pl->nmom * 2 * sizeof(float)));
         CUDA_TRY(cudaMalloc(&pl->d_stage_ws[i], z3d_workspace_bytes(pl, gb)));
     }
+    pl->staged_ok = true;
     return Z3D_OK;
 }
+static int ensure_staging(z3d_plan *pl) {
+    if (pl->staged_ok) return Z3D_OK;
+    const int rc = ensure_staging_impl(pl);
+    if (rc) {
+        const std::string keep = g_err;
+        free_staging(pl);
+        cudaGetLastError();
+        g_err = keep;
+    }
+    return rc;
+}
+
+// an error in the middle of a host-buffer call must not leave copies to / from the caller's buffers in flight
+static int host_call_fail(z3d_plan *pl, int rc) {
+    const std::string keep = g_err;
+    if (pl->s_comp) cudaStreamSynchronize(pl->s_comp);
+    if (pl->s_copy) cudaStreamSynchronize(pl->s_copy);
+    cudaGetLastError();
+    g_err = keep;
+    return rc;
+}
+#define HOST_TRY(expr)                                                                                                    \
+    do {                                                                                                                  \
+        cudaError_t _e = (expr);                                                                                          \
+        if (_e != cudaSuccess)                                                                                            \
+            return host_call_fail(pl, fail(Z3D_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__)); \
+    } while (0)
 
 extern "C" int z3d_decompose_host(z3d_plan *pl, const float *h_vol, int batch, float *h_mom) {
     if (!pl || !h_vol || !h_mom || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_decompose_host: bad arguments");
+    USE_DEVICE(pl->device);
     int rc = ensure_staging(pl);
     if (rc) return rc;
     const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
@@ -1246,25 +1673,26 @@ extern "C" int z3d_decompose_host(z3d_plan *pl, const float *h_vol, int batch, f
     for (int b0 = 0; b0 < batch; b0 += gb, stage ^= 1) {
         const int nb = std::min(gb, batch - b0);
         // the stage's previous compute + D2H must be finished before its input buffer is overwritten
-        CUDA_TRY(cudaStreamWaitEvent(pl->s_copy, pl->ev_done[stage], 0));
-        CUDA_TRY(cudaMemcpyAsync(pl->d_stage_vol[stage], h_vol + (size_t)b0 * N3, (size_t)nb * N3 * sizeof(float),
+        HOST_TRY(cudaStreamWaitEvent(pl->s_copy, pl->ev_done[stage], 0));
+        HOST_TRY(cudaMemcpyAsync(pl->d_stage_vol[stage], h_vol + (size_t)b0 * N3, (size_t)nb * N3 * sizeof(float),
                                  cudaMemcpyHostToDevice, pl->s_copy));
-        CUDA_TRY(cudaEventRecord(pl->ev_in[stage], pl->s_copy));
-        CUDA_TRY(cudaStreamWaitEvent(pl->s_comp, pl->ev_in[stage], 0));
+        HOST_TRY(cudaEventRecord(pl->ev_in[stage], pl->s_copy));
+        HOST_TRY(cudaStreamWaitEvent(pl->s_comp, pl->ev_in[stage], 0));
         rc = z3d_decompose(pl, pl->d_stage_vol[stage], nb, 0, pl->H, pl->d_stage_mom[stage], pl->d_stage_ws[stage],
                            z3d_workspace_bytes(pl, gb), pl->s_comp);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(h_mom + (size_t)b0 * pl->nmom * 2, pl->d_stage_mom[stage],
+        if (rc) return host_call_fail(pl, rc);
+        HOST_TRY(cudaMemcpyAsync(h_mom + (size_t)b0 * pl->nmom * 2, pl->d_stage_mom[stage],
                                  (size_t)nb * pl->nmom * 2 * sizeof(float), cudaMemcpyDeviceToHost, pl->s_comp));
-        CUDA_TRY(cudaEventRecord(pl->ev_done[stage], pl->s_comp));
+        HOST_TRY(cudaEventRecord(pl->ev_done[stage], pl->s_comp));
     }
-    CUDA_TRY(cudaStreamSynchronize(pl->s_comp));
-    CUDA_TRY(cudaStreamSynchronize(pl->s_copy));
+    HOST_TRY(cudaStreamSynchronize(pl->s_comp));
+    HOST_TRY(cudaStreamSynchronize(pl->s_copy));
     return Z3D_OK;
 }
 
 extern "C" int z3d_reconstruct_host(z3d_plan *pl, const float *h_mom, int batch, float *h_vol) {
     if (!pl || !h_vol || !h_mom || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_reconstruct_host: bad arguments");
+    USE_DEVICE(pl->device);
     int rc = ensure_staging(pl);
     if (rc) return rc;
     const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
@@ -1272,20 +1700,20 @@ extern "C" int z3d_reconstruct_host(z3d_plan *pl, const float *h_mom, int batch,
     int stage = 0;
     for (int b0 = 0; b0 < batch; b0 += gb, stage ^= 1) {
         const int nb = std::min(gb, batch - b0);
-        CUDA_TRY(cudaStreamWaitEvent(pl->s_copy, pl->ev_done[stage], 0));
-        CUDA_TRY(cudaMemcpyAsync(pl->d_stage_mom[stage], h_mom + (size_t)b0 * pl->nmom * 2,
+        HOST_TRY(cudaStreamWaitEvent(pl->s_copy, pl->ev_done[stage], 0));
+        HOST_TRY(cudaMemcpyAsync(pl->d_stage_mom[stage], h_mom + (size_t)b0 * pl->nmom * 2,
                                  (size_t)nb * pl->nmom * 2 * sizeof(float), cudaMemcpyHostToDevice, pl->s_copy));
-        CUDA_TRY(cudaEventRecord(pl->ev_in[stage], pl->s_copy));
-        CUDA_TRY(cudaStreamWaitEvent(pl->s_comp, pl->ev_in[stage], 0));
+        HOST_TRY(cudaEventRecord(pl->ev_in[stage], pl->s_copy));
+        HOST_TRY(cudaStreamWaitEvent(pl->s_comp, pl->ev_in[stage], 0));
         rc = z3d_reconstruct(pl, pl->d_stage_mom[stage], nb, 0, pl->H, pl->d_stage_vol[stage], pl->d_stage_ws[stage],
                              z3d_workspace_bytes(pl, gb), pl->s_comp);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(h_vol + (size_t)b0 * N3, pl->d_stage_vol[stage], (size_t)nb * N3 * sizeof(float),
+        if (rc) return host_call_fail(pl, rc);
+        HOST_TRY(cudaMemcpyAsync(h_vol + (size_t)b0 * N3, pl->d_stage_vol[stage], (size_t)nb * N3 * sizeof(float),
                                  cudaMemcpyDeviceToHost, pl->s_comp));
-        CUDA_TRY(cudaEventRecord(pl->ev_done[stage], pl->s_comp));
+        HOST_TRY(cudaEventRecord(pl->ev_done[stage], pl->s_comp));
     }
-    CUDA_TRY(cudaStreamSynchronize(pl->s_comp));
-    CUDA_TRY(cudaStreamSynchronize(pl->s_copy));
+    HOST_TRY(cudaStreamSynchronize(pl->s_comp));
+    HOST_TRY(cudaStreamSynchronize(pl->s_copy));
     return Z3D_OK;
 }
 
@@ -1296,7 +1724,7 @@ extern "C" int z3d_fma_peak(int device, int variant, int iters, double *tflops) 
         cudaGetLastError();
         return fail(Z3D_ERR_NODEVICE, "z3d_fma_peak: no such CUDA device");
     }
-    CUDA_TRY(cudaSetDevice(device));
+    USE_DEVICE(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     const int blocks = prop.multiProcessorCount * 4, threads = 512;
@@ -1320,6 +1748,37 @@ extern "C" int z3d_fma_peak(int device, int variant, int iters, double *tflops) 
     cudaFree(d_out);
     return Z3D_OK;
 }
+
+#ifdef Z3D_GEN_DEBUG
+// developer aid: mapped host memory the kernel's bounded waits report into (survives a trapped context)
+static int *g_trap_host = nullptr;
+extern "C" int z3d_debug_trap_arm(void) {
+    if (!g_trap_host) {
+        if (cudaHostAlloc((void **)&g_trap_host, 4096, cudaHostAllocMapped) != cudaSuccess) return -1;
+        memset(g_trap_host, 0, 4096);
+        int *d = nullptr;
+        if (cudaHostGetDevicePointer((void **)&d, g_trap_host, 0) != cudaSuccess) return -2;
+        if (cudaMemcpyToSymbol(z3d::g_gen_trap, &d, sizeof d) != cudaSuccess) return -3;
+    }
+    return 0;
+}
+extern "C" int z3d_debug_trap_read(int *out, int n) {
+    if (!g_trap_host) return -1;
+    for (int i = 0; i < n && i < 1024; ++i) out[i] = g_trap_host[i];
+    return 0;
+}
+#endif
+#ifdef Z3D_GEN_TIMING
+extern "C" int z3d_debug_gen(long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, z3d::g_gdbg, sizeof(long long) * 32);
+    if (reset) {
+        long long z[32] = {0};
+        cudaMemcpyToSymbol(z3d::g_gdbg, z, sizeof z);
+    }
+    return 0;
+}
+#endif
 
 #ifdef Z3D_DEBUG_TIMING
 extern "C" int z3d_debug_dump(long long *out, int reset) {
@@ -1349,7 +1808,7 @@ struct z3d_comm {
 
 extern "C" int z3d_comm_create(const z3d_plan *pl, int batch_max, z3d_comm **out, unsigned char *handle64) {
     if (!pl || !out || !handle64 || batch_max < 1) return fail(Z3D_ERR_INVALID, "z3d_comm_create: bad arguments");
-    CUDA_TRY(cudaSetDevice(pl->device));
+    USE_DEVICE(pl->device);
     z3d_comm *c = new z3d_comm();
     c->device = pl->device;
     c->max_elems = (size_t)batch_max * 2 * pl->nmom;
@@ -1372,7 +1831,7 @@ extern "C" int z3d_comm_create(const z3d_plan *pl, int batch_max, z3d_comm **out
 extern "C" int z3d_comm_connect(z3d_comm *c, int rank, int world, const unsigned char *handles /* [world][64] */) {
     if (!c || !handles || world < 1 || world > MAX_RANKS || rank < 0 || rank >= world)
         return fail(Z3D_ERR_INVALID, "z3d_comm_connect: bad arguments (world <= %d)", MAX_RANKS);
-    CUDA_TRY(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     c->rank = rank;
     c->world = world;
     for (int r = 0; r < world; ++r) {
@@ -1392,7 +1851,7 @@ extern "C" int z3d_comm_connect(z3d_comm *c, int rank, int world, const unsigned
 
 extern "C" int z3d_comm_destroy(z3d_comm *c) {
     if (!c) return Z3D_OK;
-    cudaSetDevice(c->device);
+    DeviceGuard _guard(c->device);
     cudaDeviceSynchronize();
     for (int r = 0; r < MAX_RANKS; ++r)
         if (c->opened[r]) cudaIpcCloseMemHandle(c->peers.data[r]);
@@ -1407,36 +1866,47 @@ extern "C" int z3d_decompose_allreduce(const z3d_plan *pl, z3d_comm *c, const fl
                                        void *d_ws, size_t ws_bytes, void *stream) {
     if (!pl || !c || c->rank < 0) return fail(Z3D_ERR_INVALID, "z3d_decompose_allreduce: communicator not connected");
     if (!d_vol || !d_moments || !d_ws || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_decompose_allreduce: bad arguments");
-    if ((size_t)batch * 2 * pl->nmom > c->max_elems) return fail(Z3D_ERR_INVALID, "z3d_decompose_allreduce: batch exceeds communicator");
-    if (ws_bytes < ws_decompose(pl, batch)) return fail(Z3D_ERR_WORKSPACE, "z3d_decompose_allreduce: workspace too small");
-    CUDA_TRY(cudaSetDevice(pl->device));
+    // the per-CTA partials of the analysis kernel cover decompose_group(pl) volumes (workspace contract of z3d_workspace_bytes):
+    // a larger batch runs group by group, one exchange (epoch) per group
+    const int grp = decompose_group(pl);
+    if ((size_t)std::min(batch, grp) * 2 * pl->nmom > c->max_elems)
+        return fail(Z3D_ERR_INVALID, "z3d_decompose_allreduce: communicator created for fewer volumes per exchange (batch_max)");
+    if (ws_bytes < (size_t)std::min(batch, grp) * pl->npass * pl->nsplit * SLOT_WORDS * sizeof(float))
+        return fail(Z3D_ERR_WORKSPACE, "z3d_decompose_allreduce: workspace too small");
+    USE_DEVICE(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
     float *partial = (float *)d_ws;
-    dim3 g((2 * pl->nmom + 255) / 256, batch);
-    // every block of the exchange kernel waits for the peers, so all of them must be co-resident
-    if ((int)(g.x * g.y) > pl->num_sms * 4)
-        return fail(Z3D_ERR_UNSUPPORTED, "z3d_decompose_allreduce: batch %d too large for the one-shot exchange (use "
-                                         "z3d_decompose_part + a library all-reduce)", batch);
+    const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
     const_cast<z3d_plan *>(pl)->last_was_decompose = false;
-    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
-    if (pl->npass == 2)
-        k_decompose<1><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, 0, pl->H, c->rank, c->world, partial);
-    else
-        k_decompose<0><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, d_vol, batch, 0, pl->H, c->rank, c->world, partial);
-    CUDA_TRY(cudaGetLastError());
-    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev_k1, st));
-    c->epoch += 1;
-    k_reduce_allreduce_p2p<<<g, 256, 0, st>>>(partial, pl->d_src, pl->d_scale, pl->nmom, pl->npass, pl->nsplit, batch, c->peers,
-                                              c->rank, c->world, c->max_elems, c->epoch, c->d_done, c->d_err, d_moments);
-    CUDA_TRY(cudaGetLastError());
-    g_launches += 2;
+    for (int b0 = 0; b0 < batch; b0 += grp) {
+        const int nb = std::min(grp, batch - b0);
+        dim3 g((2 * pl->nmom + 255) / 256, nb);
+        // every block of the exchange kernel waits for the peers, so all of them must be co-resident
+        if ((int)(g.x * g.y) > pl->num_sms * 4)
+            return fail(Z3D_ERR_UNSUPPORTED, "z3d_decompose_allreduce: order %d too large for the one-shot exchange (use "
+                                             "z3d_decompose_part + a library all-reduce)", pl->order);
+        const float *vol = d_vol + (size_t)b0 * N3;
+        if (pl->profiling && b0 == 0) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
+        if (pl->npass == 2)
+            k_decompose<1><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, vol, nb, 0, pl->H, c->rank, c->world, partial);
+        else
+            k_decompose<0><<<pl->npass * pl->nsplit, NT, pl->smem_bytes, st>>>(pl->dev, vol, nb, 0, pl->H, c->rank, c->world, partial);
+        CUDA_TRY(cudaGetLastError());
+        if (pl->profiling && b0 == 0) CUDA_TRY(cudaEventRecord(pl->ev_k1, st));
+        c->epoch += 1;
+        k_reduce_allreduce_p2p<<<g, 256, 0, st>>>(partial, pl->d_src, pl->d_scale, pl->nmom, pl->npass, pl->nsplit, nb, c->peers,
+                                                  c->rank, c->world, c->max_elems, c->epoch, c->d_done, c->d_err,
+                                                  d_moments + (size_t)b0 * 2 * pl->nmom);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 2;
+    }
     return Z3D_OK;
 }
 
 extern "C" int z3d_comm_error(z3d_comm *c) {  // 1 after an exchange timed out (results were set to NaN)
     if (!c) return -1;
     int e = 0;
-    cudaSetDevice(c->device);
+    DeviceGuard _guard(c->device);
     cudaMemcpy(&e, c->d_err, sizeof(int), cudaMemcpyDeviceToHost);
     return e;
 }

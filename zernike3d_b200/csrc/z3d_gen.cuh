@@ -1,0 +1,585 @@
+// zernike3d_b200 - batched analysis, TABLE-FREE tensor-core variant (the default for batches): nothing volume-independent is
+// read from memory - the operand T = R_nl * Q_lm is generated inside the kernel by the reference's recurrences.
+//
+// Same contraction as z3d_stream.cuh, per (m, pz = (l + m) & 1) a real GEMM over the folded voxel axis,
+//     D[(re/im, b)][(n,l,m)] += a[(m,pz)][(re/im, b)][k] * T[(n,l,m)][k],   a = F_A,b trig_A + F_B,b trig_B,
+// on tcgen05.mma kind::tf32 (M = 128 = re/im x 64 volumes, N = moment rows of one (m, pz) padded to 16, K = 8 folded voxels =
+// one chunk), 3xTF32 (hi.lo + lo.hi + hi.hi), accumulators in tensor memory.  What is new:
+//   * T is produced by the CTA itself, in registers, straight into the K-major core-matrix layout the shared-memory
+//     descriptors describe.  A chain (l, m) of T over n obeys the radial recurrence of zm:1991-2000 because that recurrence is
+//     linear in R:  T_n = (K1 r^2 + K2) T_{n-2} + K3 T_{n-4},  seeded with  S_lm = r^l Q_lm.  The seeds obey the Legendre
+//     recurrence of zm:2021-2026 (monic, parity-decoupled, times r^l):  S_{l+2} = (4 z^2 - gamma_l r^2) S_l - delta_l r^4 S_{l-2},
+//     S_mm = rho^m, S_{m+1,m} = 2 z rho^m - polynomial in the voxel coordinates, no division and no square root per voxel.
+//     No R / Q / T table exists anywhere (the streamed-T kernel reads 13.7 GB per tile at 128^3 / order 50).
+//   * the a panels (A operand) live in TENSOR memory: the a-panel teams write them with tcgen05.st and the MMAs take A from
+//     tensor memory, so neither the producers' stores nor the tensor core's A fetch touch shared memory, which is left to the
+//     T ring (64 B written + 96 B fetched per moment row and chunk).
+//   * the folds come straight from global memory into registers (prefetched one round ahead): no fold staging.
+//   * MMAs are issued by ONE converged warp through elect.sync (back-to-back UTCHMMA on uniform registers: 23 clk or the tensor
+//     pipe's N / 2 per instruction; an `if (lane == 0)` region costs 64-72 clk per MMA - scripts/experiments/tc_probe4.cu).
+//
+// Roles (28 warps, no block barrier in the loop):
+//   warp 0        issues the MMAs of chunk t when its T block (tfull) and a panels (afull) are ready; commits -> tfree, afree
+//   warps 1-3     seed warps (chunks t = w-1 mod 3): per chunk the float64 geometry (z, rho^2), the row trig of the set's m
+//                 (float64 complex powering like exp(1j m phi), zm:2297) and the seeds S_lm of every (panel, l, voxel) -> G ring
+//   warps 4-11    two a-panel teams (chunk t -> team t & 1 -> tensor-memory slot t & 1); a thread owns one row (re/im, volume)
+//   warps 12-27   four T teams (chunk t -> team t & 3); a thread owns up to two (chain, k half) tasks, 4 voxels each
+// All 24 producer warps read the accumulators back every BFLUSH_CHUNKS chunks (see z3d_batched.cuh for why).
+#pragma once
+#include "z3d_stream.cuh"
+
+namespace z3d {
+
+constexpr int G_PANELS = 8;        // a panels ((m, pz) pieces) per column set at most
+constexpr int G_SEGS = 8;          // MMA segments (<= 256 columns each) per column set at most
+constexpr int G_TASKS = 256;       // T chain tasks (chain, k half) per column set at most: two passes of a 128-thread team
+#ifndef G_NSEEDW_
+#define G_NSEEDW_ 3
+#endif
+#ifndef G_DG_
+#define G_DG_ 12
+#endif
+constexpr int G_NSEEDW = G_NSEEDW_;        // seed warps
+constexpr int G_NAT = 2;           // a-panel teams = a-panel slots in tensor memory
+constexpr int G_NTT = 4;           // T teams
+constexpr int G_DG = G_DG_;            // depth of the geometry / seed ring
+constexpr int G_NS_MAX = 8;        // depth of the T ring at most
+// A parity wait is only meaningful when the waiter knows the barrier is at most one phase behind: the previous user of a ring
+// slot must be the SAME agent (warp / team), whose own progress then proves the earlier phase complete.  Chunk t is handled by
+// seed warp t % G_NSEEDW, a-panel team t % G_NAT and T team t % G_NTT and uses geometry slot t % G_DG, so G_DG must be a common
+// multiple of the three (with G_DG = 6 a T team could pass gfull one phase early whenever the seed warps were the bottleneck:
+// sporadic wrong moments, lost arrivals).  The T ring is safe for any depth >= G_NTT because the tensor core retires chunks in order.
+static_assert(G_DG % G_NSEEDW == 0 && G_DG % G_NAT == 0 && G_DG % G_NTT == 0, "geometry ring depth vs. agent strides");
+constexpr int G_WARP_SEED0 = 1;
+constexpr int G_WARP_A0 = 4;
+constexpr int G_WARP_T0 = G_WARP_A0 + 4 * G_NAT;
+constexpr int G_NWARP = G_WARP_T0 + 4 * G_NTT;     // 28
+constexpr int GNT = G_NWARP * 32;                  // 896 threads
+static_assert(G_WARP_A0 == S_WARP_PROD0 && G_NWARP - G_WARP_A0 == S_NPW, "s_flush deals the read-back units over warps 4..27");
+constexpr int G_OFF_TABS = 0;      // GenTabs
+constexpr int G_OFF_BAR = 512;     // mbarriers, tensor-memory base
+constexpr int G_OFF_GD = 1024;     // seed recurrence coefficients of the set's panels, then the radial table, the G ring, the T ring
+
+struct GenTabs {                   // per column set
+    int ncols, nseg, npanel, kind;
+    int ntask, nseedrows, acol0, lpar;      // acol0: first tensor-memory column of the a-panel slots; lpar: parity of the set's l
+    int seg_cols[G_SEGS], seg_off[G_SEGS], seg_panel[G_SEGS];
+    int panel_m[G_PANELS], panel_pz[G_PANELS], panel_nl[G_PANELS], panel_soff[G_PANELS], panel_gd[G_PANELS];
+};
+static_assert(sizeof(GenTabs) <= G_OFF_BAR, "tables");
+
+struct DevPlanG {
+    int order, dim, H;
+    int nsets, nsplits, nslots;    // T ring depth
+    int tslot_bytes;               // T block of the widest set: 64 B per column
+    int gslot_bytes;               // seeds of the set with the most (panel, l) rows + r^2 + trig
+    int gd_bytes, rk_bytes;        // shared-memory copies of the coefficient tables
+    int off_rk, off_g, off_t;      // byte offsets in dynamic shared memory
+    int dbg;                       // developer switches (-DZ3D_GEN_DEBUG builds only)
+    const GenTabs *tabs;           // [nsets]
+    const int4 *tasks;             // [nsets][G_TASKS]  (first column, length, index in the radial table, seed row | k half << 16)
+    const float2 *gd;              // [nsets][gd_bytes / 8]   (gamma_l, -delta_l) per panel and step
+    const float4 *rk;              // [2][rk_bytes / 16]      (K1, K2, K3, 0) of the l of one parity, l-major
+    const double *side;            // [dim]
+};
+
+#ifdef Z3D_GEN_TIMING
+// developer instrumentation: clocks spent per role and wait reason, CTA 0 only (z3d_debug_gen)
+__device__ long long g_gdbg[32];
+#define GT_T(var) const long long var = clock64()
+#define GT_ADD(slot, t0, t1) do { if (blockIdx.x == GT_BLOCK && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&g_gdbg[slot], (unsigned long long)((t1) - (t0))); } while (0)
+#ifndef GT_BLOCK
+#define GT_BLOCK 0
+#endif
+#else
+#define GT_T(var)
+#define GT_ADD(slot, t0, t1)
+#endif
+
+#ifdef Z3D_GEN_DEBUG
+// developer aid: hazard probes.  GD_SLEEP(bit) delays one role at one point when the bit is set in P.dbg (a race that
+// disappears under a delay names its hazard); bounded waits report the barrier that never completed through mapped host memory.
+__device__ int *g_gen_trap;
+#define GD_SLEEP(bit) do { if (P.dbg & (bit)) __nanosleep(3000); } while (0)
+__device__ __forceinline__ void g_wait_dbg(unsigned mbar, unsigned parity, int id, int t) {
+#pragma unroll 1
+    for (int it = 0; it < (1 << 21); ++it) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    if ((threadIdx.x & 31) == 0 && g_gen_trap && atomicAdd(g_gen_trap, 1) < 60) {
+        int *r = g_gen_trap + 8 + 8 * (atomicAdd(g_gen_trap + 1, 1) % 60);
+        r[0] = id; r[1] = blockIdx.x; r[2] = threadIdx.x >> 5; r[3] = (int)parity; r[4] = t;
+        __threadfence_system();
+    }
+    __nanosleep(1000000);
+    __trap();
+}
+#define GD_FLUSHSLEEP ((P.dbg & 512) != 0)
+#define GW(bar, par, id, t) g_wait_dbg(bar, par, id, t)
+#define GWR(bar, par, id, t) g_wait_dbg(bar, par, id, t)
+#else
+#define GD_SLEEP(bit)
+#define GD_FLUSHSLEEP false
+#define GW(bar, par, id, t) mbar_wait(bar, par)
+#define GWR(bar, par, id, t) mbar_wait_relaxed(bar, par)
+#endif
+
+// ---- tensor-memory helpers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_tf32_ts(unsigned d_tmem, unsigned a_tmem, unsigned long long b, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                   "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+// x = hi + lo, hi = x rounded to TF32 (nearest, ties away: what cvt.rna.tf32.f32 computes, which ptxas expands into four
+// instructions per value - FSETP / VIADD / SEL / LOP3 - for the infinity case; the operands here are finite): add half an ulp of
+// the 13 dropped bits to the magnitude, clear them
+__device__ __forceinline__ void split_fast(float x, float &hi, float &lo) {
+#ifdef G_OLDSPLIT
+    split_tf32(x, hi, lo);
+#else
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = x - hi;
+#endif
+}
+__device__ __forceinline__ void split4_fast(const float4 &x, float4 &hi, float4 &lo) {
+    split_fast(x.x, hi.x, lo.x);
+    split_fast(x.y, hi.y, lo.y);
+    split_fast(x.z, hi.z, lo.z);
+    split_fast(x.w, hi.w, lo.w);
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Folds of a tile by kind, as k_fold_tile_kind but without the k-half swizzle (the a-panel threads read them from global memory):
+// F[chunk][kind][set A|B][re|im][volume][k]
+__global__ void __launch_bounds__(2 * SNV * KC) k_fold_tile_gen(const float *__restrict__ vol, int nvol, int N, int H,
+                                                                float *__restrict__ Ft) {
+    const int CPR = (H + KC - 1) / KC;
+    const long long chunk = blockIdx.x;
+    ChunkPos p;
+    chunk_pos(chunk, CPR, H, p);
+    const int tid = threadIdx.x;
+    const int k = tid % KC, b = (tid / KC) % SNV, set = tid / (KC * SNV);
+    const int kk = p.kc * KC + k, k2 = N - 1 - kk;
+    const int ri = set ? p.jp : p.ip, rj = set ? p.ip : p.jp;
+    const int i2 = N - 1 - ri, j2 = N - 1 - rj;
+    const bool live = b < nvol && kk < H && (set == 0 || p.paired);
+    const float *vb = vol + (size_t)b * N * N * N;
+    float v[8];
+#pragma unroll
+    for (int img = 0; img < 8; ++img) {
+        const bool sy = img & 4, sx = img & 2, sz = img & 1;
+        const bool dup = (sy && i2 == ri) || (sx && j2 == rj) || (sz && k2 == kk);
+        v[img] = (live && !dup) ? __ldg(vb + ((size_t)(sy ? i2 : ri) * N + (sx ? j2 : rj)) * N + (sz ? k2 : kk)) : 0.0f;
+    }
+    wht8(v);
+    float *dst = Ft + (size_t)chunk * (4 * S_FK_BYTES / 4);
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {  // class c8 = (y parity = re/im) << 2 | (x parity) << 1 | z parity
+        const int reim = c8 >> 2, kind = ((((c8 >> 1) & 1) ^ reim) << 1) | (c8 & 1);
+        dst[(((kind * 2 + set) * 2 + reim) * SNV + b) * KC + k] = v[c8];
+    }
+}
+
+__device__ __forceinline__ float4 ldg_stream4(const float *p) {  // read-once data: do not allocate in L1
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// one read-back event of a producer warp (see s_flush)
+__device__ __forceinline__ void g_flush_event(unsigned tmem, int ncols, float *out, bool &had, unsigned drained, unsigned flushed, int &nev,
+                                              bool last, bool dbg_sleep = false) {
+    s_flush(tmem, ncols, out, had, drained, nev & 1, dbg_sleep);
+    had = true;
+    if (!last) {
+        tc_fence_before();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(flushed);
+    }
+    ++nev;
+}
+
+__global__ void __launch_bounds__(GNT, 1)
+k_decompose_gen(const DevPlanG P, const float *__restrict__ Ft, int part, int nparts, float *__restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int set = blockIdx.x / P.nsplits, split = blockIdx.x % P.nsplits;
+    GenTabs &T = *reinterpret_cast<GenTabs *>(smem + G_OFF_TABS);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + G_OFF_BAR);
+    float2 *gds = reinterpret_cast<float2 *>(smem + G_OFF_GD);
+    float4 *rks = reinterpret_cast<float4 *>(smem + P.off_rk);
+    unsigned char *gring = smem + P.off_g, *tring = smem + P.off_t;
+    const int NS = P.nslots;
+    // barriers: gfull[DG] gfree[DG] tfull[NS_MAX] tfree[NS_MAX] afull[2] afree[2] drained flushed
+    const unsigned gfull0 = smem_u32(bars), gfree0 = gfull0 + 8 * G_DG, tfull0 = gfree0 + 8 * G_DG, tfree0 = tfull0 + 8 * G_NS_MAX,
+                   afull0 = tfree0 + 8 * G_NS_MAX, afree0 = afull0 + 8 * G_NAT, drained = afree0 + 8 * G_NAT, flushed = drained + 8;
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + G_OFF_BAR + 8 * (2 * G_DG + 2 * G_NS_MAX + 2 * G_NAT + 2));
+    for (int i = tid; i < (int)(sizeof(GenTabs) / 4); i += GNT)
+        reinterpret_cast<int *>(smem + G_OFF_TABS)[i] = reinterpret_cast<const int *>(P.tabs + set)[i];
+    for (int i = tid; i < P.gd_bytes / 8; i += GNT) gds[i] = P.gd[(size_t)set * (P.gd_bytes / 8) + i];
+    __syncthreads();
+    const int ncols = T.ncols, nseg = T.nseg, npanel = T.npanel;
+    for (int i = tid; i < P.rk_bytes / 16; i += GNT) rks[i] = P.rk[(size_t)T.lpar * (P.rk_bytes / 16) + i];
+    if (tid == 0) {
+        for (int i = 0; i < G_DG; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gfull0 + 8 * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(gfree0 + 8 * i));   // 4 warps of a T team + 4 of an a-panel team
+        }
+        for (int i = 0; i < G_NS_MAX; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(tfull0 + 8 * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tfree0 + 8 * i));
+        }
+        for (int i = 0; i < G_NAT; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(afull0 + 8 * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(afree0 + 8 * i));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(drained));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(flushed), "r"(S_NPW));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *tmem_slot;
+
+    const int CPR = (P.H + KC - 1) / KC;
+    const long long total = (long long)analysis_items(0, P.H, P.H) * CPR;
+    const long long gbeg = total * part / nparts, glen = total * (part + 1) / nparts - gbeg;
+    const long long cbeg = gbeg + glen * split / P.nsplits, cend = gbeg + glen * (split + 1) / P.nsplits;
+    const int nchunk = (int)(cend - cbeg);
+    float *out = partial + (size_t)blockIdx.x * BSLOT_WORDS;
+#ifdef Z3D_GEN_DEBUG
+    const int ev0 = (P.dbg & 1) ? (1 << 28) : s_first_event();
+#else
+    const int ev0 = s_first_event();
+#endif
+    const int nregular = nchunk > ev0 ? (nchunk - 1 - ev0) / BFLUSH_CHUNKS + 1 : 0;  // events in front of chunks ev0 + k BFLUSH_CHUNKS < nchunk
+    const int np16 = npanel * 16;
+
+    if (nchunk == 0) {
+        for (int i = tid; i < ncols * BTM; i += GNT) out[i] = 0.0f;  // the reduction reads every split
+    } else if (warp == 0) {
+        // ---- issuing warp
+        int4 sg[G_SEGS];   // instruction descriptor, a-panel column offset, T row offset (16 B units), accumulator column
+#pragma unroll
+        for (int g = 0; g < G_SEGS; ++g) {
+            const int n = g < nseg ? T.seg_cols[g] : 16;
+            sg[g] = make_int4((int)((1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(SM_ROWS >> 4) << 24)),
+                              g < nseg ? T.seg_panel[g] * 16 : 0, g < nseg ? T.seg_off[g] : 0, g < nseg ? T.seg_off[g] : -1);
+        }
+        const unsigned long long dT0 = umma_desc(smem_u32(tring), ncols * 16, 128);
+        const unsigned long long lo_t = (unsigned long long)(2 * ncols), step = (unsigned long long)(P.tslot_bytes >> 4);
+        const unsigned a0 = tmem + (unsigned)T.acol0;
+        unsigned long long dT = dT0;
+        int ts = 0, since = 0, to_event = ev0;
+        unsigned tuse = 0, nev = 0;
+        for (int t = 0; t < nchunk; ++t) {
+            GT_T(i0);
+            if (to_event == 0) {  // the accumulators have been read back -> overwrite
+                GW(flushed, nev & 1, 1, t);
+                GD_SLEEP(2);
+                since = 0;
+                ++nev;
+                to_event = BFLUSH_CHUNKS;
+            }
+            GT_T(i1);
+            const int as = t & 1;
+            GW(tfull0 + 8 * ts, tuse & 1, 2, t);
+            GT_T(i2);
+            GW(afull0 + 8 * as, (unsigned)(t >> 1) & 1, 3, t);
+            GD_SLEEP(4);
+            GT_T(i3);
+            GT_ADD(0, i0, i1); GT_ADD(1, i1, i2); GT_ADD(2, i2, i3);
+            tc_fence_after();
+            if (elect_one()) {
+                const unsigned a = a0 + (unsigned)(as * np16);
+#pragma unroll
+                for (int g = 0; g < G_SEGS; ++g) {
+                    if (sg[g].w >= 0) {
+                        const unsigned long long b = dT + (unsigned long long)sg[g].z;
+                        const unsigned d = tmem + (unsigned)sg[g].w, ah = a + (unsigned)sg[g].y;
+                        umma_tf32_ts(d, ah, b + lo_t, (unsigned)sg[g].x, since > 0 ? 1u : 0u);  // small terms first
+                        umma_tf32_ts(d, ah + 8, b, (unsigned)sg[g].x, 1u);
+                        umma_tf32_ts(d, ah, b, (unsigned)sg[g].x, 1u);
+                    }
+                }
+                umma_commit(tfree0 + 8 * ts);
+                umma_commit(afree0 + 8 * as);
+                if (to_event == 1 || t == nchunk - 1) umma_commit(drained);  // a read-back follows this chunk
+            }
+            __syncwarp();
+            GT_T(i4);
+            GT_ADD(3, i3, i4);
+            ++since;
+            --to_event;
+            dT += step;
+            if (++ts == NS) { ts = 0; ++tuse; dT = dT0; }
+        }
+    } else if (warp < G_WARP_SEED0 + G_NSEEDW) {
+        // ---- seed warps: lane = (panel j = lane / 8 (+ 4 in the second pass), voxel k = lane % 8)
+        const int sw = warp - G_WARP_SEED0, k = lane & 7;
+        int pm[2], ppz[2], pnl[2], psoff[2], pgd[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int j = (lane >> 3) + 4 * q;
+            const bool v = j < npanel;
+            pm[q] = v ? T.panel_m[j] : 0;
+            ppz[q] = v ? T.panel_pz[j] : 0;
+            pnl[q] = v ? T.panel_nl[j] : 0;
+            psoff[q] = v ? T.panel_soff[j] : 0;
+            pgd[q] = v ? T.panel_gd[j] : 0;
+        }
+        const int npass = npanel > 4 ? 2 : 1;
+        int maxnl = 0;
+        for (int j = 0; j < npanel; ++j) maxnl = max(maxnl, T.panel_nl[j]);
+        int item_have = -1;
+        double rho2 = 0.0, rhom[2] = {0.0, 0.0};
+        float tr[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        for (int t = sw; t < nchunk; t += G_NSEEDW) {
+            const long long cc = cbeg + t;
+            const int item = (int)(cc / CPR), kc = (int)(cc % CPR);
+            if (item != item_have) {  // row group changed: rho, rho^m and the row trig of this lane's panels (float64)
+                item_have = item;
+                int ip, jp;
+                bool paired;
+                decode_item(item, 0, P.H, P.H, ip, jp, paired);
+                const double y0 = P.side[ip], x0 = P.side[jp];
+                rho2 = x0 * x0 + y0 * y0;
+                const double rho = sqrt(rho2);
+                double ur = 1.0, ui = 0.0;
+                if (rho > 0.0) {
+                    ur = x0 / rho;
+                    ui = y0 / rho;
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int m = pm[q];
+                    double br = ur, bi = ui, cr = 1.0, ci = 0.0, pw = 1.0, pb = rho;
+                    for (int e = m; e; e >>= 1) {  // (cos, sin)(m phi) by complex powering, rho^m by real powering
+                        if (e & 1) {
+                            const double tt = cr * br - ci * bi;
+                            ci = cr * bi + ci * br;
+                            cr = tt;
+                            pw *= pb;
+                        }
+                        const double tt = br * br - bi * bi;
+                        bi = 2.0 * br * bi;
+                        br = tt;
+                        pb *= pb;
+                    }
+                    rhom[q] = pw;
+                    const int mq = m & 3;  // transpose: phi' = atan2(x0, y0) = pi/2 - phi (mod 2 pi)
+                    tr[q][0] = (float)cr;
+                    tr[q][1] = (float)ci;
+                    tr[q][2] = (float)((mq == 0) ? cr : (mq == 1) ? ci : (mq == 2) ? -cr : -ci);
+                    tr[q][3] = (float)((mq == 0) ? -ci : (mq == 1) ? cr : (mq == 2) ? ci : -cr);
+                }
+            }
+            const int kk = kc * KC + k;
+            const double z = (kk < P.H) ? P.side[kk] : 0.0;
+            const double zz = z * z;
+            const float r2 = (float)(rho2 + zz), z4 = (float)(4.0 * zz), r4 = r2 * r2;
+            const int gs = t % G_DG;
+            GT_T(s0);
+            if (t >= G_DG) GW(gfree0 + 8 * gs, (unsigned)(t / G_DG - 1) & 1, 4, t);
+            GD_SLEEP(8);
+            GT_T(s1);
+            float *slot = reinterpret_cast<float *>(gring + (size_t)gs * P.gslot_bytes);
+            float *seeds = slot + 40;  // [0..7] r^2, [8..39] trig of the panels, then the seeds [row][8]
+            if (lane < 8) slot[lane] = r2;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (q < npass) {
+                    const int j = (lane >> 3) + 4 * q;
+                    const float tv = k == 0 ? tr[q][0] : k == 1 ? tr[q][1] : k == 2 ? tr[q][2] : tr[q][3];
+                    if (k < 4 && j < npanel) slot[8 + j * 4 + k] = tv;
+                    // S_{l0}: l0 = m (pz = 0): rho^m;  l0 = m + 1: 2 z rho^m   (Q_mm = sin^m, Q_{m+1,m} = 2c Q_mm, zm:2012-2020 / kappa)
+                    float S1 = (float)(ppz[q] ? 2.0 * z * rhom[q] : rhom[q]), S2 = 0.0f;
+                    float *sp = seeds + psoff[q] * 8 + k;
+                    const float2 *gp = gds + pgd[q];
+                    const int nl = pnl[q];
+                    if (nl > 0) sp[0] = S1;
+                    // coefficients in blocks of 8, loaded before the block's stores (loads cannot be hoisted over shared-memory
+                    // stores by the compiler; one load per step in front of a dependent store is 50 clocks per step)
+#ifdef G_OLDSEED
+                    for (int i = 1; i < maxnl; ++i) {
+                        const float2 g = gp[i - 1];
+                        const float S = fmaf(fmaf(-g.x, r2, z4), S1, (g.y * r4) * S2);
+                        S2 = S1;
+                        S1 = S;
+                        if (i < nl) sp[i * 8] = S;
+                    }
+#else
+                    for (int i0 = 1; i0 < maxnl; i0 += 8) {
+                        float2 g[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) g[e] = gp[i0 - 1 + e];  // tables are padded: reads past a chain are throw-away
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float S = fmaf(fmaf(-g[e].x, r2, z4), S1, (g[e].y * r4) * S2);
+                            S2 = S1;
+                            S1 = S;
+                            if (i0 + e < nl) sp[(i0 + e) * 8] = S;
+                        }
+                    }
+#endif
+                }
+            }
+            GD_SLEEP(16);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gfull0 + 8 * gs);
+            GT_T(s2);
+            if (sw == 0) { GT_ADD(4, s0, s1); GT_ADD(5, s1, s2); }
+        }
+    } else if (warp < G_WARP_A0) {
+        // (a special warp without a role)
+    } else if (warp < G_WARP_T0) {
+        // ---- a-panel teams: thread = row (re/im, volume b) of the MMA's M dimension = tensor-memory lane
+        const int team = (warp - G_WARP_A0) >> 2, quarter = warp & 3;
+        const int row = quarter * 32 + lane, reim = row >> 6, b = row & 63;
+        const float sign = reim ? -1.0f : 1.0f;  // im rows are negated
+        const unsigned arow = tmem + ((unsigned)(32 * quarter) << 16) + (unsigned)T.acol0 + (unsigned)(team * np16);
+        const float *fbase = Ft + (size_t)T.kind * (S_FK_BYTES / 4) + (size_t)(reim * SNV + b) * KC;
+        bool had = false;
+        int nev = 0;
+        float4 fa0, fa1, fb0, fb1;
+        if (team < nchunk) {
+            const float *f = fbase + (size_t)(cbeg + team) * (4 * S_FK_BYTES / 4);
+            fa0 = ldg_stream4(f); fa1 = ldg_stream4(f + 4);
+            fb0 = ldg_stream4(f + 2 * SNV * KC); fb1 = ldg_stream4(f + 2 * SNV * KC + 4);
+        }
+        for (int t = team; t < nchunk; t += G_NAT) {
+            float4 na0 = fa0, na1 = fa1, nb0 = fb0, nb1 = fb1;
+            if (t + G_NAT < nchunk) {  // folds of the team's next chunk: in flight while this chunk's panels are built
+                const float *f = fbase + (size_t)(cbeg + t + G_NAT) * (4 * S_FK_BYTES / 4);
+                na0 = ldg_stream4(f); na1 = ldg_stream4(f + 4);
+                nb0 = ldg_stream4(f + 2 * SNV * KC); nb1 = ldg_stream4(f + 2 * SNV * KC + 4);
+            }
+            int pos, len;
+            s_interval(t, ev0, nchunk, pos, len);
+            const float sg = sign * (1.0f + BTRUNC_PER_MMA * (float)(3 * (len - 1 - pos) + 1));  // truncation pre-compensation
+            const int gs = t % G_DG;
+            const float *slot = reinterpret_cast<const float *>(gring + (size_t)gs * P.gslot_bytes);
+            GT_T(a0);
+            GWR(gfull0 + 8 * gs, (unsigned)(t / G_DG) & 1, 5, t);
+            GT_T(a1);
+            if (t >= G_NAT) GWR(afree0 + 8 * team, (unsigned)(t / G_NAT - 1) & 1, 6, t);  // the slot's previous MMAs retired
+            GD_SLEEP(32);
+            GT_T(a2);
+            tc_fence_after();
+            const float fa[8] = {fa0.x, fa0.y, fa0.z, fa0.w, fa1.x, fa1.y, fa1.z, fa1.w};
+            const float fb[8] = {fb0.x, fb0.y, fb0.z, fb0.w, fb1.x, fb1.y, fb1.z, fb1.w};
+            for (int j = 0; j < npanel; ++j) {
+                const float tA = slot[8 + j * 4 + reim] * sg, tB = slot[8 + j * 4 + 2 + reim] * sg;
+                float hi[8], lo[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) split_fast(fmaf(fa[q], tA, fb[q] * tB), hi[q], lo[q]);
+                tmem_st8(arow + (unsigned)(j * 16), hi);
+                tmem_st8(arow + (unsigned)(j * 16 + 8), lo);
+            }
+            tmem_st_wait();
+            GD_SLEEP(64);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(afull0 + 8 * team);
+                mbar_arrive(gfree0 + 8 * gs);
+            }
+            GT_T(a3);
+            while (nev < nregular && ev0 + nev * BFLUSH_CHUNKS <= t) g_flush_event(tmem, ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
+            GT_T(a4);
+            if (warp == G_WARP_A0) { GT_ADD(6, a0, a1); GT_ADD(7, a1, a2); GT_ADD(8, a2, a3); GT_ADD(9, a3, a4); }
+            fa0 = na0; fa1 = na1; fb0 = nb0; fb1 = nb1;
+        }
+        while (nev < nregular) g_flush_event(tmem, ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
+        g_flush_event(tmem, ncols, out, had, drained, flushed, nev, true, GD_FLUSHSLEEP);
+    } else {
+        // ---- T teams: thread u of a team owns tasks u and u + 128: (chain (l, m), k half) -> 4 voxels of every n of the chain
+        // the tasks are sorted by chain length, so a team's first logical warp is its busiest: rotate the logical warps over the
+        // physical ones by team, or the four teams' busiest warps all sit on scheduler 0 next to the issuing warp
+#ifdef G_NOROT
+        const int team = (warp - G_WARP_T0) >> 2, u = ((warp - G_WARP_T0) & 3) * 32 + lane;
+#else
+        const int team = (warp - G_WARP_T0) >> 2, u = ((warp - team + 1) & 3) * 32 + lane;
+#endif
+        int4 task[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = u + 128 * q;
+            task[q] = i < T.ntask ? P.tasks[(size_t)set * G_TASKS + i] : make_int4(0, 0, 0, 0);
+        }
+        bool had = false;
+        int nev = 0;
+        for (int t = team; t < nchunk; t += G_NTT) {
+            const int ts = t % NS;
+            const unsigned tuse = (unsigned)(t / NS);  // how often the slot has been filled before
+            const int gs = t % G_DG;
+            const float *slot = reinterpret_cast<const float *>(gring + (size_t)gs * P.gslot_bytes);
+            float *tb = reinterpret_cast<float *>(tring + (size_t)ts * P.tslot_bytes);
+            GT_T(t0);
+            GWR(gfull0 + 8 * gs, (unsigned)(t / G_DG) & 1, 7, t);
+            GT_T(t1);
+            if (tuse) GWR(tfree0 + 8 * ts, (tuse - 1) & 1, 8, t);  // the slot's previous MMAs retired
+            GD_SLEEP(128);
+            GT_T(t2);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int len = task[q].y;
+                if (len > 0) {
+                    const int kh = task[q].w >> 16, srow = task[q].w & 0xffff;
+                    const float4 s4 = *reinterpret_cast<const float4 *>(slot + 40 + srow * 8 + 4 * kh);
+                    const float4 r2 = *reinterpret_cast<const float4 *>(slot + 4 * kh);
+                    const float4 *K = rks + task[q].z;
+                    float *hi = tb + (size_t)(kh * ncols + task[q].x) * 4, *lo = hi + (size_t)2 * ncols * 4;
+                    float4 T1 = make_float4(0.f, 0.f, 0.f, 0.f), T2 = s4;
+                    float4 kc4 = K[0];
+#pragma unroll 2
+                    for (int i = 0; i < len; ++i) {
+                        const float4 kn = K[i + 1];  // prefetch (the table is padded)
+                        float4 Tn, h, l;
+                        Tn.x = fmaf(fmaf(kc4.x, r2.x, kc4.y), T1.x, kc4.z * T2.x);
+                        Tn.y = fmaf(fmaf(kc4.x, r2.y, kc4.y), T1.y, kc4.z * T2.y);
+                        Tn.z = fmaf(fmaf(kc4.x, r2.z, kc4.y), T1.z, kc4.z * T2.z);
+                        Tn.w = fmaf(fmaf(kc4.x, r2.w, kc4.y), T1.w, kc4.z * T2.w);
+                        split4_fast(Tn, h, l);
+                        *reinterpret_cast<float4 *>(hi + i * 4) = h;
+                        *reinterpret_cast<float4 *>(lo + i * 4) = l;
+                        T2 = T1;
+                        T1 = Tn;
+                        kc4 = kn;
+                    }
+                }
+            }
+            fence_async_smem();  // generic-proxy T writes -> visible to the tensor core's async-proxy reads
+            GD_SLEEP(256);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(tfull0 + 8 * ts);
+                mbar_arrive(gfree0 + 8 * gs);
+            }
+            GT_T(t3);
+            while (nev < nregular && ev0 + nev * BFLUSH_CHUNKS <= t) g_flush_event(tmem, ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
+            GT_T(t4);
+            if (u < 32 && team == 0) { GT_ADD(10, t0, t1); GT_ADD(11, t1, t2); GT_ADD(12, t2, t3); GT_ADD(13, t3, t4); }
+        }
+        while (nev < nregular) g_flush_event(tmem, ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
+        g_flush_event(tmem, ncols, out, had, drained, flushed, nev, true, GD_FLUSHSLEEP);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+}  // namespace z3d

@@ -195,10 +195,11 @@ __device__ __forceinline__ void st_hint(float *p, float v, unsigned long long po
 // (tcgen05.ld, 32 loads, add, 32 stores) of 2 000 - 3 500 clk while the T stream saturates the memory system (measured with
 // clock64 stamps), and the tensor core idles until the slowest warp is through: the units are dealt out evenly (at most 3 per
 // warp for 512 columns) and the partial sums are kept L2-resident (evict-last; the folds, 537 MB per tile, are evict-normal).
-__device__ __forceinline__ void s_flush(unsigned tmem, int ncols, float *out, bool add, unsigned drained_bar, unsigned parity) {
+__device__ __forceinline__ void s_flush(unsigned tmem, int ncols, float *out, bool add, unsigned drained_bar, unsigned parity, bool dbg_sleep = false) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3;
     const unsigned long long pol = l2_policy_evict_last();
     mbar_wait(drained_bar, parity);  // every MMA issued so far has retired
+    if (dbg_sleep) __nanosleep(3000);
     tc_fence_after();
 #pragma unroll 1
     for (int c32 = 32 * ((warp - S_WARP_PROD0) >> 2); c32 < ncols; c32 += 32 * (S_NPW / 4)) {
@@ -387,7 +388,7 @@ k_decompose_stream(const DevPlanS P, const float *__restrict__ Ft, int part, int
         for (int j = 0; j < S_PANELS; ++j) tofs[j] = reim * (LMAX + 1) + (T.panel_code[j < npanel ? j : 0] & 0xffff);
         const float *Fs = reinterpret_cast<const float *>(slot0 + (size_t)team * slot_bytes + t_bytes_max);
         float *abuf = reinterpret_cast<float *>(slot0 + (size_t)team * slot_bytes + t_bytes_max + S_FK_BYTES);
-        const unsigned my_fready = fready0 + 8 * team, my_ready = ready0 + 8 * team, my_done = done0 + 8 * team;
+        const unsigned my_fready = fready0 + 8 * team, my_ready = ready0 + 8 * team;
         unsigned use = 0;
         int kc = (int)((cbeg + team) % CPR);
         const float *trig = P.trig + (size_t)((cbeg + team) / CPR) * 4 * (LMAX + 1);

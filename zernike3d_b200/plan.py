@@ -24,7 +24,7 @@ class Plan:
                  "voxels_per_chunk", "sms", "useful_accumulators", "padded_accumulators",
                  "batched_min", "batched_row_groups", "batched_row_groups_wide", "batched_wide_min", "batched_rounds",
                  "batched_rounds_wide", "stream_state", "stream_sets", "stream_splits", "stream_rows16", "stream_table_mib",
-                 "chunks")
+                 "chunks", "gen", "gen_sets", "gen_splits", "gen_cols", "gen_slots", "gen_min", "tables_level", "gen_maxcols")
 
     def __init__(self, order: int, dim: int, device: int | None = None):
         if not torch.cuda.is_available():
@@ -50,24 +50,49 @@ class Plan:
 
     # ------------------------------------------------------------------ helpers
     def info(self) -> dict:
-        arr = (ctypes.c_int * 24)()
-        _lib.check(self._L.z3d_plan_info(self._h, arr, 24))
+        arr = (ctypes.c_int * 32)()
+        _lib.check(self._L.z3d_plan_info(self._h, arr, 32))
         return dict(zip(self.INFO_KEYS, list(arr)))
+
+    def prepare_tables(self, level: int, max_bytes: int = 0) -> int:
+        """Opt in to the table-fed batched kernels (``z3d_plan_prepare_tables``): 1 = R / Q factor tables, 2 = + the streamed T
+        table, 0 = back to the table-free default.  Returns the level reached."""
+        got = ctypes.c_int()
+        _lib.check(self._L.z3d_plan_prepare_tables(self._h, int(level), int(max_bytes), ctypes.byref(got)))
+        self._ws = None
+        return int(got.value)
 
     def workspace_bytes(self, batch: int) -> int:
         return int(self._L.z3d_workspace_bytes(self._h, int(batch)))
 
-    def _workspace(self, batch: int) -> torch.Tensor:
+    def _workspace(self, batch: int, stream=None) -> torch.Tensor:
+        """Scratch owned by the plan.  It is allocated on torch's current stream of the plan's device; when a call runs on
+        another stream the caching allocator is told (``record_stream``), so that neither a later growth (which drops the old
+        buffer) nor the allocator's reuse can hand the memory out while that stream still works on it."""
         need = self.workspace_bytes(batch)
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
+        if stream is not None:
+            self._ws.record_stream(stream)
         return self._ws
 
-    @staticmethod
-    def _stream(stream) -> ctypes.c_void_p:
-        s = torch.cuda.current_stream() if stream is None else stream
+    def _stream(self, stream) -> ctypes.c_void_p:
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
         return ctypes.c_void_p(s.cuda_stream)
+
+    def _check_moments(self, m: torch.Tensor, what: str) -> torch.Tensor:
+        if m.dtype != torch.complex64 or not m.is_cuda or m.dim() != 2 or m.shape[1] != self.num_moments or m.device.index != self.device:
+            raise ValueError(f"{what}: expected complex64 [B,{self.num_moments}] on cuda:{self.device}, got {m.dtype} "
+                             f"{tuple(m.shape)} on {m.device}")
+        return m.contiguous()
+
+    def _check_volumes(self, v: torch.Tensor, what: str) -> torch.Tensor:
+        N = self.dim
+        if v.dtype != torch.float32 or not v.is_cuda or tuple(v.shape[1:]) != (N, N, N) or v.device.index != self.device:
+            raise ValueError(f"{what}: expected a float32 tensor [B,{N},{N},{N}] on cuda:{self.device}, got {v.dtype} "
+                             f"{tuple(v.shape)} on {v.device}")
+        return v.contiguous()
 
     def _pairs(self, pairs):
         lo, hi = (0, self.half) if pairs is None else pairs
@@ -93,14 +118,13 @@ class Plan:
         (balanced multi-GPU sharding of one replicated volume); the default is the whole volume."""
         single = vol.dim() == 3
         v = vol.unsqueeze(0) if single else vol
-        N = self.dim
-        if v.dtype != torch.float32 or not v.is_cuda or tuple(v.shape[1:]) != (N, N, N):
-            raise ValueError(f"expected a float32 CUDA tensor [B,{N},{N},{N}], got {v.dtype} {tuple(v.shape)} on {v.device}")
-        v = v.contiguous()
+        v = self._check_volumes(v, "decompose")
         B = v.shape[0]
         if out is None:
             out = torch.empty((B, self.num_moments), dtype=torch.complex64, device=v.device)
-        ws = self._workspace(B)
+        elif stream is not None:
+            out.record_stream(stream)
+        ws = self._workspace(B, stream)
         if part is not None:
             if pairs is not None:
                 raise ValueError("give either pairs= or part=, not both")
@@ -116,11 +140,11 @@ class Plan:
         """Work-sharded analysis of replicated volume(s) fused with a one-shot all-reduce over NVLink peer memory
         (``z3d_decompose_allreduce``): every rank returns the full, bit-identical moments."""
         single = vol.dim() == 3
-        v = (vol.unsqueeze(0) if single else vol).contiguous()
+        v = self._check_volumes(vol.unsqueeze(0) if single else vol, "decompose_allreduce")
         B = v.shape[0]
         if out is None:
             out = torch.empty((B, self.num_moments), dtype=torch.complex64, device=v.device)
-        ws = self._workspace(B)
+        ws = self._workspace(B, stream)
         _lib.check(self._L.z3d_decompose_allreduce(self._h, comm._c, _ptr(v), B, _ptr(out), _ptr(ws), ws.numel(),
                                                    self._stream(stream)))
         return out[0] if single else out
@@ -129,13 +153,11 @@ class Plan:
         """complex64 CUDA ``[B, num_moments]`` -> float32 ``[B, N, N, N]`` (planes outside ``pairs`` untouched)."""
         single = moments.dim() == 1
         m = moments.unsqueeze(0) if single else moments
-        if m.dtype != torch.complex64 or not m.is_cuda or m.shape[1] != self.num_moments:
-            raise ValueError(f"expected complex64 CUDA [B,{self.num_moments}], got {m.dtype} {tuple(m.shape)}")
-        m = m.contiguous()
+        m = self._check_moments(m, "reconstruct")
         B, N = m.shape[0], self.dim
         if out is None:
             out = torch.zeros((B, N, N, N), dtype=torch.float32, device=m.device)
-        ws = self._workspace(B)
+        ws = self._workspace(B, stream)
         lo, hi = self._pairs(pairs)
         _lib.check(self._L.z3d_reconstruct(self._h, _ptr(m), B, lo, hi, _ptr(out), _ptr(ws), ws.numel(),
                                            self._stream(stream)))
@@ -158,7 +180,7 @@ class Plan:
 
     def invariants(self, moments: torch.Tensor, stream=None) -> torch.Tensor:
         single = moments.dim() == 1
-        m = (moments.unsqueeze(0) if single else moments).contiguous()
+        m = self._check_moments(moments.unsqueeze(0) if single else moments, "invariants")
         out = torch.empty((m.shape[0], self.num_radial), dtype=torch.float32, device=m.device)
         _lib.check(self._L.z3d_invariants(self._h, _ptr(m), m.shape[0], _ptr(out), self._stream(stream)))
         return out[0] if single else out
@@ -167,9 +189,9 @@ class Plan:
         """Per-order correlation curve(s) of two moment sets on the device (``Z_3DVA.calc_ZCC``, moment_analysis_3dva.py:402-422):
         ``[num_moments]`` or ``[B, num_moments]`` complex64 each -> ``[order + 1]`` or ``[B, order + 1]`` float32."""
         single = moments_a.dim() == 1
-        a = (moments_a.unsqueeze(0) if single else moments_a).contiguous()
-        b = (moments_b.unsqueeze(0) if single else moments_b).contiguous()
-        if a.shape != b.shape or a.shape[1] != self.num_moments:
+        a = self._check_moments(moments_a.unsqueeze(0) if single else moments_a, "zcc")
+        b = self._check_moments(moments_b.unsqueeze(0) if single else moments_b, "zcc")
+        if a.shape != b.shape:
             raise ValueError("zcc: moment sets of different shapes")
         out = torch.empty((a.shape[0], self.order + 1), dtype=torch.float32, device=a.device)
         _lib.check(self._L.z3d_zcc(self._h, _ptr(a), _ptr(b), a.shape[0], _ptr(out), self._stream(stream)))
@@ -249,7 +271,7 @@ def crop_bin(volumes: torch.Tensor, crop_to: int | None = None, bin: float | Non
     n_out = box if bin is None else int(round(box * (1 / bin)))
     cz, cy, cx = (n_in // 2,) * 3 if center is None else (int(c) for c in center)
     out = torch.empty((v.shape[0], n_out, n_out, n_out), dtype=torch.float32, device=v.device)
-    s = torch.cuda.current_stream() if stream is None else stream
+    s = torch.cuda.current_stream(v.device) if stream is None else stream
     _lib.check(_lib.lib().z3d_crop_bin(_ptr(v), v.shape[0], n_in, cz, cy, cx, crop, n_out, _ptr(out), ctypes.c_void_p(s.cuda_stream)))
     return out[0] if single else out
 
