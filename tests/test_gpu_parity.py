@@ -18,8 +18,8 @@ pytestmark = pytest.mark.gpu
 
 TOL_MOM, TOL_MAP, TOL_INV = 1e-5, 1e-5, 1e-6
 TOL_EXACT = 1.5e-6
-# batches take the tensor-core path (3xTF32 products, TMEM accumulators, basis / T tables): T = R*Q is rounded to float32
-# before the contraction, which costs a little against the float64 oracle (1.0e-6 at order 50, 1.4e-6 at order 60)
+# batches take the tensor-core path (3xTF32 products, TMEM accumulators): T = R*Q is a float32 recurrence before the
+# contraction, which costs a little against the float64 oracle (1.0e-6 at order 50, 1.4e-6 at order 60)
 TOL_EXACT_BATCHED = 2.0e-6
 
 
@@ -53,11 +53,18 @@ def test_decompose_vs_reference_golden(plans, oracle_mod, name):
         assert mom.dtype == np.complex64 and mom.shape == (P.num_moments,)
         assert rel_l2(mom, g["moments"][si]) < TOL_MOM
         inv = P.invariants(dev(mom)).cpu().numpy()
-        # the 1e-6 bar on invariants holds against the exact oracle everywhere; against the reference's own
-        # float32-BLAS numbers it holds up to 64^3 and is 1.0e-6 at 96^3 / 2.3e-6 at 128^3 - that is the reference's
-        # summation noise (its moments are 3.3e-6 / 5.4e-6 from the float64 evaluation there), see DESIGN.md
+        # the 1e-6 bar on invariants holds against the exact oracle everywhere and against the reference's own float32-BLAS
+        # numbers up to 64^3.  At 96^3 / 128^3 the reference does not reproduce ITSELF to 1e-6: tests/golden/ref_selfnoise.npz
+        # (oracle/make_selfnoise.py) holds the difference between two runs of the unmodified reference that only differ in the
+        # order of its float32 summation (zm:2210) - invariants 1.5e-6 / 3.4e-6, moments 5.2e-6 / 7.6e-6.  The bar against the
+        # reference there is that measured self-noise (x 1.5), not a number picked to make the test pass.
         assert rel_l2(inv, oracle_mod.invariants(mom, order)) < 2e-7
-        assert rel_l2(inv, g["invariants"][si]) < (TOL_INV if dim <= 64 else 5e-6)
+        tol_inv_ref = TOL_INV
+        if dim > 64:
+            noise = golden("selfnoise")
+            tol_inv_ref = max(TOL_INV, 1.5 * float(noise[f"{name}/invariants_fwd_vs_rev"]))
+            assert float(noise[f"{name}/invariants_fwd_vs_exact"]) > 0.9 * TOL_INV      # the reference itself is >= 1e-6 from exact
+        assert rel_l2(inv, g["invariants"][si]) < tol_inv_ref
         if dim <= 64:
             exact = oracle_mod.decompose(v, order, oracle_mod.EXACT)
             assert rel_l2(mom, exact) < TOL_EXACT
@@ -120,29 +127,30 @@ BATCHED = [("d16_o10", 13), ("d15_o8", 12), ("d32_o20", 35), ("d20_o25", 45), ("
 
 @pytest.mark.parametrize("name,count", BATCHED)
 def test_batched_tensor_core_path(plans, oracle_mod, name, count):
-    """Batches of >= info['batched_min'] volumes: basis / T tables + k_fold_tile_kind + k_decompose_stream (tcgen05, T streamed
-    from HBM) + k_reduce_stream; k_decompose_batched when the T table is disabled or does not fit."""
+    """Batches of >= info['gen_min'] volumes take the TABLE-FREE tensor-core kernel: k_fold_tile_gen + k_decompose_gen (tcgen05,
+    T = R Q generated in the kernel by the recurrences of zm:1991-2000 / zm:2021-2026, nothing materialised) + k_reduce_stream."""
     from zernike3d_b200.plan import launch_count
 
     g = golden(name)
     order, dim = int(g["order"]), int(g["dim"])
     P = plans(order, dim)
     info = P.info()
-    assert 0 < info["batched_min"] <= count
+    assert info["gen"] == 1 and info["tables_level"] == 0 and 0 < info["gen_min"] <= count
     seed0 = int(g["seeds"][0])
     vols = np.stack([volume(seed0 + i, dim) for i in range(count)])
     dv = dev(vols)
-    P.decompose(dv)                                           # first call also builds the basis tables
+    P.decompose(dv)                                           # (allocates the plan's torch-owned scratch)
+    free0 = torch.cuda.mem_get_info()[0]
     l0 = launch_count()
     mb = P.decompose(dv)
-    stream = P.info()["stream_state"] == 2                    # streamed-T kernel (its table is resident after the first call)
-    assert stream or os.environ.get("Z3D_STREAM") == "0" or dim > 128
-    tiles, left, covered = 0, count, 0                        # the C side's tiling: streamed-T: 64-volume tiles; else 64-volume
-    while left >= info["batched_min"]:                        # tiles while >= wide_min are left, then 32-volume tiles; the rest
-        take = min(64 if (stream or left >= info["batched_wide_min"]) else 32, left)   # goes through the per-volume kernel
+    assert P.info()["stream_state"] != 2 and P.info()["tables_level"] == 0       # no basis table appeared behind the caller's back
+    assert free0 - torch.cuda.mem_get_info()[0] < (8 << 20)
+    tiles, left, covered = 0, count, 0                        # the C side's tiling: 64-volume tiles while >= gen_min volumes are
+    while left >= info["gen_min"]:                            # left; the rest goes through the per-volume kernel
+        take = min(64, left)
         tiles, left, covered = tiles + 1, left - take, covered + take
     tail = left
-    assert launch_count() - l0 >= 3 * tiles + (2 if tail else 0)  # fold + contraction round(s) + reduction per tile, then the tail
+    assert launch_count() - l0 >= 3 * tiles + (2 if tail else 0)  # fold + contraction + reduction per tile, then the tail
     assert mb.shape == (count, P.num_moments) and mb.dtype == torch.complex64
     assert torch.equal(torch.view_as_real(mb), torch.view_as_real(P.decompose(dv)))     # run-to-run bitwise
     mb = mb.cpu().numpy()
@@ -165,32 +173,32 @@ def test_batched_tensor_core_path(plans, oracle_mod, name, count):
 
 
 @pytest.mark.parametrize("name,count", [("d32_o20", 35), ("c1_d64_o50", 70)])
-def test_batched_path_without_the_T_table(oracle_mod, monkeypatch, name, count):
-    """Z3D_STREAM=0 (or a T table that does not fit in device memory): the R / Q table kernel k_decompose_batched, 32- and
-    64-volume tiles; same results as the streamed-T kernel to the batched tolerance."""
+def test_opt_in_table_fed_kernels(oracle_mod, name, count):
+    """z3d_plan_prepare_tables: level 1 = R / Q factor tables (k_decompose_batched, 32- and 64-volume tiles), level 2 = + the
+    streamed product table (k_decompose_stream).  Same results as the table-free default to the batched tolerance; a T table
+    over the byte cap leaves the plan at level 1; level 0 frees everything and returns to the default kernel bit for bit."""
     from zernike3d_b200.plan import Plan
 
     g = golden(name)
     order, dim = int(g["order"]), int(g["dim"])
     vols = np.stack([volume(int(g["seeds"][0]) + i, dim) for i in range(count)])
     dv = dev(vols)
-    monkeypatch.setenv("Z3D_STREAM", "0")
-    old = Plan(order, dim)
-    monkeypatch.delenv("Z3D_STREAM")
-    new = Plan(order, dim)
-    mo, mn = old.decompose(dv).cpu().numpy(), new.decompose(dv).cpu().numpy()
-    assert old.info()["stream_state"] == 0 and new.info()["stream_state"] == 2
-    assert rel_l2(mo[0], g["moments"][0]) < TOL_MOM and rel_l2(mn[0], g["moments"][0]) < TOL_MOM
-    assert rel_l2(mo, mn) < 2 * TOL_EXACT_BATCHED
-    for i in (0, count - 1):
-        exact = oracle_mod.decompose(vols[i], order, oracle_mod.EXACT)
-        assert rel_l2(mo[i], exact) < TOL_EXACT_BATCHED and rel_l2(mn[i], exact) < TOL_EXACT_BATCHED
-    # a T table that is refused for lack of memory (here: by the cap) silently leaves the plan on the R / Q table kernel
-    monkeypatch.setenv("Z3D_STREAM_MAX_GB", "0.000001")
-    capped = Plan(order, dim)
-    assert capped.info()["stream_state"] == 1
-    mc = capped.decompose(dv).cpu().numpy()
-    assert capped.info()["stream_state"] == 0 and np.array_equal(mc, mo)
+    P = Plan(order, dim)
+    m_gen = P.decompose(dv).cpu().numpy()
+    assert P.prepare_tables(2, max_bytes=1) == 1 and P.info()["stream_state"] != 2   # capped: factor tables only
+    m_rq = P.decompose(dv).cpu().numpy()
+    assert P.prepare_tables(2) == 2 and P.info()["stream_state"] == 2
+    m_t = P.decompose(dv).cpu().numpy()
+    for m in (m_gen, m_rq, m_t):
+        assert rel_l2(m[0], g["moments"][0]) < TOL_MOM
+        for i in (0, count - 1):
+            assert rel_l2(m[i], oracle_mod.decompose(vols[i], order, oracle_mod.EXACT)) < TOL_EXACT_BATCHED
+    assert rel_l2(m_rq, m_t) < 2 * TOL_EXACT_BATCHED and rel_l2(m_gen, m_t) < 2 * TOL_EXACT_BATCHED
+    assert not np.array_equal(m_rq, m_gen) and not np.array_equal(m_t, m_gen)        # three different kernels really ran
+    assert P.prepare_tables(1) == 1
+    assert np.array_equal(P.decompose(dv).cpu().numpy(), m_rq)
+    assert P.prepare_tables(0) == 0 and P.info()["tables_level"] == 0
+    assert np.array_equal(P.decompose(dv).cpu().numpy(), m_gen)
 
 
 def test_batched_128_order50_headline(plans, oracle_mod):

@@ -104,7 +104,7 @@ struct z3d_plan {
     int tables_level = 0;        // 0: no basis tables (default), 1: R / Q tables, 2: R / Q + T tables (z3d_plan_prepare_tables)
     // table-free tensor-core variant (z3d_gen.cuh): the default for batches
     bool gen = false;
-    int gen_min = 4;             // smallest (remaining) batch routed to it
+    int gen_min = 8;             // smallest (remaining) batch routed to it: a tile costs the same whatever it holds (6.4 per-volume launches at 128^3 / order 50)
     DevPlanG devg{};
     int g_smem = 0, g_ncols_all = 0, g_maxcols = 0;
     int2 *d_gcolmap = nullptr;
