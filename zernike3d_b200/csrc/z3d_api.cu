@@ -107,6 +107,7 @@ struct z3d_plan {
     int gen_min = 8;             // smallest (remaining) batch routed to it: a tile costs the same whatever it holds (6.4 per-volume launches at 128^3 / order 50)
     DevPlanG devg{};
     int g_smem = 0, g_ncols_all = 0, g_maxcols = 0;
+    GenIssue g_issue{};          // per-set MMA issue table, passed in the kernel parameters
     int2 *d_gcolmap = nullptr;
     // reduce / prepare tables
     int *d_src = nullptr;        // [2*nmom]  pass*SLOT_WORDS + word
@@ -841,11 +842,33 @@ void build_gen_plan(int L, int num_sms, const HostPlan &hp, HostPlanG &hg, int f
         // tasks: chains sorted by length (longest first), in blocks of 16 chains: 16 x k half 0, then 16 x k half 1 (a quarter
         // warp's 16-byte stores then belong to 8 different chains)
         std::stable_sort(chains.begin(), chains.end(), [](const TaskC &a, const TaskC &b) { return a.len > b.len; });
+        // Within a warp's 16 chains, lanes 0-7 and 8-15 (and their k-half twins 16-23, 24-31) are the quarter-warps of the 16-byte
+        // stores: a quarter-warp is conflict free when its 8 rows differ mod 8 (a row is 16 B, 8 rows span the 32 banks), and all
+        // its lanes advance their rows in step.  Deal the block's chains into the two groups by row residue (ncu: 57 % of the T
+        // stores' shared-memory wavefronts were conflict replays with the chains in plain length order).
         int nt = 0;
-        for (size_t c0 = 0; c0 < chains.size(); c0 += 16)
+        for (size_t c0 = 0; c0 < chains.size(); c0 += 16) {
+            const size_t n = std::min<size_t>(16, chains.size() - c0);
+            std::vector<TaskC> grp[2], rest;
+            bool used[2][8] = {{false}};
+            for (size_t c = c0; c < c0 + n; ++c) {
+                const int r = chains[c].row0 & 7;
+                if (!used[0][r] && grp[0].size() < 8) { used[0][r] = true; grp[0].push_back(chains[c]); }
+                else if (!used[1][r] && grp[1].size() < 8) { used[1][r] = true; grp[1].push_back(chains[c]); }
+                else rest.push_back(chains[c]);
+            }
+            for (const TaskC &x : rest) (grp[0].size() < 8 && (grp[0].size() <= grp[1].size() || grp[1].size() >= 8) ? grp[0] : grp[1]).push_back(x);
+            // a warp's 32 lanes: [group 0 | group 1] x k half 0, then the same x k half 1; a short last block keeps the quarter-warp
+            // alignment with empty tasks (length 0: the lane idles)
+            const TaskC none{0, 0, 0, 0};
             for (int kh = 0; kh < 2; ++kh)
-                for (size_t c = c0; c < std::min(chains.size(), c0 + 16); ++c)
-                    hg.tasks[(size_t)si * G_TASKS + nt++] = make_int4(chains[c].row0, chains[c].len, chains[c].rk, chains[c].srow | (kh << 16));
+                for (int g2 = 0; g2 < 2; ++g2)
+                    for (size_t i = 0; i < 8; ++i) {
+                        const TaskC &x = i < grp[g2].size() ? grp[g2][i] : none;
+                        if (nt < G_TASKS) hg.tasks[(size_t)si * G_TASKS + nt] = make_int4(x.row0, x.len, x.rk, x.srow | (kh << 16));
+                        ++nt;
+                    }
+        }
         T.ntask = nt;
         if (nt > G_TASKS || T.nseg > G_SEGS || T.ncols + 32 * T.npanel > 512) return;
     }
@@ -1047,13 +1070,23 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
             if (const char *e = getenv("Z3D_GEN_DBG")) g.dbg = atoi(e);
             g.nslots = std::min(G_NS_MAX, ((int)prop.sharedMemPerBlockOptin - g.off_t) / g.tslot_bytes);
             if (const char *e = getenv("Z3D_GEN_SLOTS")) g.nslots = std::max(2, std::min(g.nslots, atoi(e)));
-            if (g.nslots >= G_NTT) {   // a T team's first chunk behind a read-back must find a free slot (see z3d_gen.cuh)
+            if (g.nslots >= G_NTT && hg.nsets <= G_MAXSETS) {   // a T team's first chunk behind a read-back must find a free slot (see z3d_gen.cuh)
                 GenTabs *d_tabs; int4 *d_tasks; float2 *d_ggd; float4 *d_grk;
                 UP(hg.tabs, d_tabs) UP(hg.tasks, d_tasks) UP(hg.gd, d_ggd) UP(hg.rk, d_grk) UP(hg.colmap, pl->d_gcolmap)
                 g.tabs = d_tabs; g.tasks = d_tasks; g.gd = d_ggd; g.rk = d_grk; g.side = d_side;
                 pl->g_smem = g.off_t + g.nslots * g.tslot_bytes;
                 pl->g_ncols_all = hg.ncols_all;
                 pl->g_maxcols = hg.maxcols;
+                for (int i = 0; i < hg.nsets; ++i) {
+                    const GenTabs &T = hg.tabs[i];
+                    pl->g_issue.hdr[i] = make_int4(T.ncols, T.nseg, T.npanel, T.acol0);
+                    for (int s2 = 0; s2 < G_SEGS; ++s2) {
+                        const bool v = s2 < T.nseg;
+                        const int n = v ? T.seg_cols[s2] : 16;
+                        pl->g_issue.seg[i][s2] = make_int4((int)((1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(SM_ROWS >> 4) << 24)),
+                                                          v ? T.seg_panel[s2] * 16 : 0, v ? T.seg_off[s2] : 0, v ? 0 : -1);
+                    }
+                }
                 pl->b_chunks = (long long)analysis_items(0, pl->H, pl->H) * ((pl->H + KC - 1) / KC);
                 pl->gen = true;
             }
@@ -1158,6 +1191,7 @@ extern "C" int z3d_gen_layout(int order, int num_sms, int *out, int n_out) {
             std::vector<char> covered(T.ncols, 0);   // every chain task writes its own rows, twice (two k halves)
             for (int t = 0; t < T.ntask; ++t) {
                 const int4 tk = hg.tasks[(size_t)i * G_TASKS + t];
+                if (tk.y == 0) continue;   // filler lane of a short block
                 if (tk.y < 1 || tk.x < 0 || tk.x + tk.y > T.ncols || (tk.w & 0xffff) >= T.nseedrows || tk.z < 0 || tk.z + tk.y > hg.rk_entries) { ++bad; continue; }
                 for (int r = 0; r < tk.y; ++r) covered[tk.x + r] += 1;
             }
@@ -1389,7 +1423,7 @@ static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int
         CUDA_TRY(cudaGetLastError());
         const bool timed = pl->profiling && mpl->n_timed < z3d_plan::MAX_TIMED;
         if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t0[mpl->n_timed], st));
-        k_decompose_gen<<<dp.nsets * dp.nsplits, GNT, pl->g_smem, st>>>(dp, folds, part, nparts, partial);
+        k_decompose_gen<<<dim3(dp.nsplits, dp.nsets), GNT, pl->g_smem, st>>>(dp, pl->g_issue, folds, part, nparts, partial);
         CUDA_TRY(cudaGetLastError());
         if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t1[mpl->n_timed++], st));
         k_reduce_stream<<<(pl->nmom * SM_ROWS + 255) / 256, 256, 0, st>>>(partial, pl->d_gcolmap, pl->d_scale, pl->nmom, dp.nsplits, nb, mom);

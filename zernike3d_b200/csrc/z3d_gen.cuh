@@ -18,13 +18,13 @@
 //   * MMAs are issued by ONE converged warp through elect.sync (back-to-back UTCHMMA on uniform registers: 23 clk or the tensor
 //     pipe's N / 2 per instruction; an `if (lane == 0)` region costs 64-72 clk per MMA - scripts/experiments/tc_probe4.cu).
 //
-// Roles (28 warps, no block barrier in the loop):
-//   warp 0        issues the MMAs of chunk t when its T block (tfull) and a panels (afull) are ready; commits -> tfree, afree
-//   warps 1-3     seed warps (chunks t = w-1 mod 3): per chunk the float64 geometry (z, rho^2), the row trig of the set's m
+// Roles (32 warps, no block barrier in the loop):
+//   warps 0-3     issue the MMAs of chunk t (segments g = w mod 4) when its T block (tfull) and a panels (afull) are ready; commit -> tfree, afree
+//   warps 4-6     seed warps (chunks t = w-4 mod 3): per chunk the float64 geometry (z, rho^2), the row trig of the set's m
 //                 (float64 complex powering like exp(1j m phi), zm:2297) and the seeds S_lm of every (panel, l, voxel) -> G ring
-//   warps 4-11    two a-panel teams (chunk t -> team t & 1 -> tensor-memory slot t & 1); a thread owns one row (re/im, volume)
-//   warps 12-27   four T teams (chunk t -> team t & 3); a thread owns up to two (chain, k half) tasks, 4 voxels each
-// All 24 producer warps read the accumulators back every BFLUSH_CHUNKS chunks (see z3d_batched.cuh for why).
+//   warps 8-15    two a-panel teams (chunk t -> team t & 1 -> tensor-memory slot t & 1); a thread owns one row (re/im, volume)
+//   warps 16-31   four T teams (chunk t -> team t & 3); a thread owns up to two (chain, k half) tasks, 4 voxels each
+// All 24 producer warps (8-31) read the accumulators back every BFLUSH_CHUNKS chunks (see z3d_batched.cuh for why).
 #pragma once
 #include "z3d_stream.cuh"
 
@@ -50,12 +50,17 @@ constexpr int G_NS_MAX = 8;        // depth of the T ring at most
 // multiple of the three (with G_DG = 6 a T team could pass gfull one phase early whenever the seed warps were the bottleneck:
 // sporadic wrong moments, lost arrivals).  The T ring is safe for any depth >= G_NTT because the tensor core retires chunks in order.
 static_assert(G_DG % G_NSEEDW == 0 && G_DG % G_NAT == 0 && G_DG % G_NTT == 0, "geometry ring depth vs. agent strides");
-constexpr int G_WARP_SEED0 = 1;
-constexpr int G_WARP_A0 = 4;
+#ifndef G_NISS_
+#define G_NISS_ 1
+#endif
+constexpr int G_NISS = G_NISS_;           // issuing warps, one per scheduler (SM sub-partition = warp % 4): warp w issues the segments g = w mod 4
+constexpr int G_WARP_SEED0 = G_NISS;
+constexpr int G_WARP_A0 = G_NISS == 1 ? 4 : 8;
 constexpr int G_WARP_T0 = G_WARP_A0 + 4 * G_NAT;
-constexpr int G_NWARP = G_WARP_T0 + 4 * G_NTT;     // 28
-constexpr int GNT = G_NWARP * 32;                  // 896 threads
-static_assert(G_WARP_A0 == S_WARP_PROD0 && G_NWARP - G_WARP_A0 == S_NPW, "s_flush deals the read-back units over warps 4..27");
+constexpr int G_NWARP = G_WARP_T0 + 4 * G_NTT;     // 32
+constexpr int GNT = G_NWARP * 32;                  // 1024 threads
+constexpr int G_SEG_PER_ISS = G_SEGS / G_NISS;
+static_assert(G_NWARP - G_WARP_A0 == S_NPW && G_WARP_A0 % 4 == 0 && G_SEGS % G_NISS == 0, "s_flush deals the read-back units over the 24 producer warps");
 constexpr int G_OFF_TABS = 0;      // GenTabs
 constexpr int G_OFF_BAR = 512;     // mbarriers, tensor-memory base
 constexpr int G_OFF_GD = 1024;     // seed recurrence coefficients of the set's panels, then the radial table, the G ring, the T ring
@@ -67,6 +72,17 @@ struct GenTabs {                   // per column set
     int panel_m[G_PANELS], panel_pz[G_PANELS], panel_nl[G_PANELS], panel_soff[G_PANELS], panel_gd[G_PANELS];
 };
 static_assert(sizeof(GenTabs) <= G_OFF_BAR, "tables");
+
+// What the issuing warp needs per column set, passed in the KERNEL PARAMETERS (constant bank): the values arrive in uniform
+// registers through ULDC, where UTCHMMA wants them.  Read from shared memory they sat in vector registers and every MMA cost a
+// chain of R2UR moves (19 instructions per segment, ~130 clk per segment on a scheduler shared with six producer warps - the
+// issuing warp's serial path was the whole kernel's period, whatever the producers and the tensor pipe had to do).
+constexpr int G_MAXSETS = 152;
+struct GenIssue {
+    int4 seg[G_MAXSETS][G_SEGS];   // instruction descriptor, a-panel column offset, T row offset (16 B units) = accumulator column, valid ? 0 : -1
+    int4 hdr[G_MAXSETS];           // ncols, nseg, npanel, acol0
+};
+static_assert(sizeof(GenIssue) < 24 * 1024, "kernel parameter space");
 
 struct DevPlanG {
     int order, dim, H;
@@ -87,7 +103,7 @@ struct DevPlanG {
 // developer instrumentation: clocks spent per role and wait reason, CTA 0 only (z3d_debug_gen)
 __device__ long long g_gdbg[32];
 #define GT_T(var) const long long var = clock64()
-#define GT_ADD(slot, t0, t1) do { if (blockIdx.x == GT_BLOCK && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&g_gdbg[slot], (unsigned long long)((t1) - (t0))); } while (0)
+#define GT_ADD(slot, t0, t1) do { if (blockIdx.y * gridDim.x + blockIdx.x == GT_BLOCK && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&g_gdbg[slot], (unsigned long long)((t1) - (t0))); } while (0)
 #ifndef GT_BLOCK
 #define GT_BLOCK 0
 #endif
@@ -111,7 +127,7 @@ __device__ __forceinline__ void g_wait_dbg(unsigned mbar, unsigned parity, int i
     }
     if ((threadIdx.x & 31) == 0 && g_gen_trap && atomicAdd(g_gen_trap, 1) < 60) {
         int *r = g_gen_trap + 8 + 8 * (atomicAdd(g_gen_trap + 1, 1) % 60);
-        r[0] = id; r[1] = blockIdx.x; r[2] = threadIdx.x >> 5; r[3] = (int)parity; r[4] = t;
+        r[0] = id; r[1] = blockIdx.y * gridDim.x + blockIdx.x; r[2] = threadIdx.x >> 5; r[3] = (int)parity; r[4] = t;
         __threadfence_system();
     }
     __nanosleep(1000000);
@@ -197,7 +213,7 @@ __device__ __forceinline__ float4 ldg_stream4(const float *p) {  // read-once da
 // one read-back event of a producer warp (see s_flush)
 __device__ __forceinline__ void g_flush_event(unsigned tmem, int ncols, float *out, bool &had, unsigned drained, unsigned flushed, int &nev,
                                               bool last, bool dbg_sleep = false) {
-    s_flush(tmem, ncols, out, had, drained, nev & 1, dbg_sleep);
+    s_flush<G_WARP_A0>(tmem, ncols, out, had, drained, nev & 1, dbg_sleep);
     had = true;
     if (!last) {
         tc_fence_before();
@@ -208,10 +224,11 @@ __device__ __forceinline__ void g_flush_event(unsigned tmem, int ncols, float *o
 }
 
 __global__ void __launch_bounds__(GNT, 1)
-k_decompose_gen(const DevPlanG P, const float *__restrict__ Ft, int part, int nparts, float *__restrict__ partial) {
+k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenIssue I, const float *__restrict__ Ft, int part, int nparts,
+                float *__restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int set = blockIdx.x / P.nsplits, split = blockIdx.x % P.nsplits;
+    const int set = blockIdx.y, split = blockIdx.x, bid = blockIdx.y * gridDim.x + blockIdx.x;   // grid = (splits, sets)
     GenTabs &T = *reinterpret_cast<GenTabs *>(smem + G_OFF_TABS);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + G_OFF_BAR);
     float2 *gds = reinterpret_cast<float2 *>(smem + G_OFF_GD);
@@ -227,6 +244,7 @@ k_decompose_gen(const DevPlanG P, const float *__restrict__ Ft, int part, int np
     for (int i = tid; i < P.gd_bytes / 8; i += GNT) gds[i] = P.gd[(size_t)set * (P.gd_bytes / 8) + i];
     __syncthreads();
     const int ncols = T.ncols, nseg = T.nseg, npanel = T.npanel;
+    const int nactive = min(nseg, G_NISS);   // issuing warps that own a segment
     for (int i = tid; i < P.rk_bytes / 16; i += GNT) rks[i] = P.rk[(size_t)T.lpar * (P.rk_bytes / 16) + i];
     if (tid == 0) {
         for (int i = 0; i < G_DG; ++i) {
@@ -235,13 +253,13 @@ k_decompose_gen(const DevPlanG P, const float *__restrict__ Ft, int part, int np
         }
         for (int i = 0; i < G_NS_MAX; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(tfull0 + 8 * i));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tfree0 + 8 * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tfree0 + 8 * i), "r"(nactive));
         }
         for (int i = 0; i < G_NAT; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(afull0 + 8 * i));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(afree0 + 8 * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(afree0 + 8 * i), "r"(nactive));
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(drained));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(drained), "r"(nactive));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(flushed), "r"(S_NPW));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -259,73 +277,83 @@ k_decompose_gen(const DevPlanG P, const float *__restrict__ Ft, int part, int np
     const long long gbeg = total * part / nparts, glen = total * (part + 1) / nparts - gbeg;
     const long long cbeg = gbeg + glen * split / P.nsplits, cend = gbeg + glen * (split + 1) / P.nsplits;
     const int nchunk = (int)(cend - cbeg);
-    float *out = partial + (size_t)blockIdx.x * BSLOT_WORDS;
+    float *out = partial + (size_t)bid * BSLOT_WORDS;
+    // first read-back event (chunks): staggered over the CTAs, which sweep the chunk list in lock step (see s_first_event)
 #ifdef Z3D_GEN_DEBUG
-    const int ev0 = (P.dbg & 1) ? (1 << 28) : s_first_event();
+    const int ev0 = (P.dbg & 1) ? (1 << 28) : (bid % 8 + 1) * (BFLUSH_CHUNKS / 8);
 #else
-    const int ev0 = s_first_event();
+    const int ev0 = (bid % 8 + 1) * (BFLUSH_CHUNKS / 8);
 #endif
     const int nregular = nchunk > ev0 ? (nchunk - 1 - ev0) / BFLUSH_CHUNKS + 1 : 0;  // events in front of chunks ev0 + k BFLUSH_CHUNKS < nchunk
     const int np16 = npanel * 16;
 
     if (nchunk == 0) {
         for (int i = tid; i < ncols * BTM; i += GNT) out[i] = 0.0f;  // the reduction reads every split
-    } else if (warp == 0) {
-        // ---- issuing warp
-        int4 sg[G_SEGS];   // instruction descriptor, a-panel column offset, T row offset (16 B units), accumulator column
+    } else if (warp < G_NISS) {
+        // ---- issuing warps: warp w owns the segments g = w, w + G_NISS, .. (different accumulator columns: no ordering between the
+        // warps' MMAs is needed); a warp without a segment has nothing to do.  The serial per-chunk path of an issuing warp (two
+        // waits, the operand set-up of its MMAs - every UTCHMMA operand has to be moved into uniform registers -, two commits) is
+        // what bounds the kernel's period: with one issuing warp for all segments it was ~50 clk per MMA, ~1000 clk per chunk.
+        const int wi = warp;
+        if (wi < nactive) {
+            int4 sg[G_SEG_PER_ISS];
 #pragma unroll
-        for (int g = 0; g < G_SEGS; ++g) {
-            const int n = g < nseg ? T.seg_cols[g] : 16;
-            sg[g] = make_int4((int)((1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(SM_ROWS >> 4) << 24)),
-                              g < nseg ? T.seg_panel[g] * 16 : 0, g < nseg ? T.seg_off[g] : 0, g < nseg ? T.seg_off[g] : -1);
-        }
-        const unsigned long long dT0 = umma_desc(smem_u32(tring), ncols * 16, 128);
-        const unsigned long long lo_t = (unsigned long long)(2 * ncols), step = (unsigned long long)(P.tslot_bytes >> 4);
-        const unsigned a0 = tmem + (unsigned)T.acol0;
-        unsigned long long dT = dT0;
-        int ts = 0, since = 0, to_event = ev0;
-        unsigned tuse = 0, nev = 0;
-        for (int t = 0; t < nchunk; ++t) {
-            GT_T(i0);
-            if (to_event == 0) {  // the accumulators have been read back -> overwrite
-                GW(flushed, nev & 1, 1, t);
-                GD_SLEEP(2);
-                since = 0;
-                ++nev;
-                to_event = BFLUSH_CHUNKS;
-            }
-            GT_T(i1);
-            const int as = t & 1;
-            GW(tfull0 + 8 * ts, tuse & 1, 2, t);
-            GT_T(i2);
-            GW(afull0 + 8 * as, (unsigned)(t >> 1) & 1, 3, t);
-            GD_SLEEP(4);
-            GT_T(i3);
-            GT_ADD(0, i0, i1); GT_ADD(1, i1, i2); GT_ADD(2, i2, i3);
-            tc_fence_after();
-            if (elect_one()) {
-                const unsigned a = a0 + (unsigned)(as * np16);
-#pragma unroll
-                for (int g = 0; g < G_SEGS; ++g) {
-                    if (sg[g].w >= 0) {
-                        const unsigned long long b = dT + (unsigned long long)sg[g].z;
-                        const unsigned d = tmem + (unsigned)sg[g].w, ah = a + (unsigned)sg[g].y;
-                        umma_tf32_ts(d, ah, b + lo_t, (unsigned)sg[g].x, since > 0 ? 1u : 0u);  // small terms first
-                        umma_tf32_ts(d, ah + 8, b, (unsigned)sg[g].x, 1u);
-                        umma_tf32_ts(d, ah, b, (unsigned)sg[g].x, 1u);
-                    }
+            for (int q = 0; q < G_SEG_PER_ISS; ++q) sg[q] = I.seg[set][wi + q * G_NISS];
+            const unsigned dlo0 = (smem_u32(smem) + (unsigned)P.off_t) >> 4;          // T ring, 16-byte units (descriptor start-address field)
+            const unsigned long long dhi = ((unsigned long long)(128 >> 4) << 32) | (1ull << 46) | ((unsigned long long)ncols << 16);  // SBO 128 B, LBO = ncols * 16 B, version 1
+            const unsigned lo_t = (unsigned)(2 * ncols), step = (unsigned)(P.tslot_bytes >> 4);
+            const unsigned a0 = tmem + (unsigned)T.acol0;
+            unsigned dlo = dlo0;
+            int ts = 0, since = 0, to_event = ev0;
+            unsigned tuse = 0, nev = 0;
+            for (int t = 0; t < nchunk; ++t) {
+                GT_T(i0);
+                if (to_event == 0) {  // the accumulators have been read back -> overwrite
+                    GW(flushed, nev & 1, 1, t);
+                    GD_SLEEP(2);
+                    since = 0;
+                    ++nev;
+                    to_event = BFLUSH_CHUNKS;
                 }
-                umma_commit(tfree0 + 8 * ts);
-                umma_commit(afree0 + 8 * as);
-                if (to_event == 1 || t == nchunk - 1) umma_commit(drained);  // a read-back follows this chunk
+                GT_T(i1);
+                const int as = t & 1;
+                GW(tfull0 + 8 * ts, tuse & 1, 2, t);
+                GT_T(i2);
+                GW(afull0 + 8 * as, (unsigned)(t >> 1) & 1, 3, t);
+                GD_SLEEP(4);
+                GT_T(i3);
+                if (wi == 0) { GT_ADD(0, i0, i1); GT_ADD(1, i1, i2); GT_ADD(2, i2, i3); }
+                tc_fence_after();
+                if (elect_one()) {
+                    const unsigned a = a0 + (unsigned)(as * np16);
+#pragma unroll
+                    for (int q = 0; q < G_SEG_PER_ISS; ++q) {
+#ifdef Z3D_GEN_DEBUG
+                        if (P.dbg & 16384) continue;
+#endif
+                        if (sg[q].w >= 0) {
+                            const unsigned long long b = dhi | (unsigned long long)(dlo + (unsigned)sg[q].z);
+                            const unsigned d = tmem + (unsigned)sg[q].z, ah = a + (unsigned)sg[q].y;
+#ifdef Z3D_GEN_DEBUG
+                            if (P.dbg & 2048) { umma_tf32_ts(d, ah, b, (unsigned)sg[q].x, since > 0 ? 1u : 0u); continue; }
+#endif
+                            umma_tf32_ts(d, ah, b + lo_t, (unsigned)sg[q].x, since > 0 ? 1u : 0u);  // small terms first
+                            umma_tf32_ts(d, ah + 8, b, (unsigned)sg[q].x, 1u);
+                            umma_tf32_ts(d, ah, b, (unsigned)sg[q].x, 1u);
+                        }
+                    }
+                    umma_commit(tfree0 + 8 * ts);
+                    umma_commit(afree0 + 8 * as);
+                    if (to_event == 1 || t == nchunk - 1) umma_commit(drained);  // a read-back follows this chunk
+                }
+                __syncwarp();
+                GT_T(i4);
+                if (wi == 0) GT_ADD(3, i3, i4);
+                ++since;
+                --to_event;
+                dlo += step;
+                if (++ts == NS) { ts = 0; ++tuse; dlo = dlo0; }
             }
-            __syncwarp();
-            GT_T(i4);
-            GT_ADD(3, i3, i4);
-            ++since;
-            --to_event;
-            dT += step;
-            if (++ts == NS) { ts = 0; ++tuse; dT = dT0; }
         }
     } else if (warp < G_WARP_SEED0 + G_NSEEDW) {
         // ---- seed warps: lane = (panel j = lane / 8 (+ 4 in the second pass), voxel k = lane % 8)
@@ -397,6 +425,9 @@ k_decompose_gen(const DevPlanG P, const float *__restrict__ Ft, int part, int np
             GD_SLEEP(8);
             GT_T(s1);
             float *slot = reinterpret_cast<float *>(gring + (size_t)gs * P.gslot_bytes);
+#ifdef Z3D_GEN_DEBUG
+            if (P.dbg & 32768) { __syncwarp(); if (lane == 0) mbar_arrive(gfull0 + 8 * gs); continue; }
+#endif
             float *seeds = slot + 40;  // [0..7] r^2, [8..39] trig of the panels, then the seeds [row][8]
             if (lane < 8) slot[lane] = r2;
 #pragma unroll
@@ -481,6 +512,9 @@ k_decompose_gen(const DevPlanG P, const float *__restrict__ Ft, int part, int np
             tc_fence_after();
             const float fa[8] = {fa0.x, fa0.y, fa0.z, fa0.w, fa1.x, fa1.y, fa1.z, fa1.w};
             const float fb[8] = {fb0.x, fb0.y, fb0.z, fb0.w, fb1.x, fb1.y, fb1.z, fb1.w};
+#ifdef Z3D_GEN_DEBUG
+            if (!(P.dbg & 4096))
+#endif
             for (int j = 0; j < npanel; ++j) {
                 const float tA = slot[8 + j * 4 + reim] * sg, tB = slot[8 + j * 4 + 2 + reim] * sg;
                 float hi[8], lo[8];
@@ -536,7 +570,11 @@ k_decompose_gen(const DevPlanG P, const float *__restrict__ Ft, int part, int np
             GT_T(t2);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
+#ifdef Z3D_GEN_DEBUG
+                const int len = (P.dbg & 8192) ? 0 : task[q].y;
+#else
                 const int len = task[q].y;
+#endif
                 if (len > 0) {
                     const int kh = task[q].w >> 16, srow = task[q].w & 0xffff;
                     const float4 s4 = *reinterpret_cast<const float4 *>(slot + 40 + srow * 8 + 4 * kh);
@@ -554,8 +592,13 @@ k_decompose_gen(const DevPlanG P, const float *__restrict__ Ft, int part, int np
                         Tn.z = fmaf(fmaf(kc4.x, r2.z, kc4.y), T1.z, kc4.z * T2.z);
                         Tn.w = fmaf(fmaf(kc4.x, r2.w, kc4.y), T1.w, kc4.z * T2.w);
                         split4_fast(Tn, h, l);
+#ifdef Z3D_GEN_DEBUG
+                        if (P.dbg & 1024) { if (h.x == 123.456f) *reinterpret_cast<float4 *>(hi + i * 4) = l; } else
+#endif
+                        {
                         *reinterpret_cast<float4 *>(hi + i * 4) = h;
                         *reinterpret_cast<float4 *>(lo + i * 4) = l;
+                        }
                         T2 = T1;
                         T1 = Tn;
                         kc4 = kn;

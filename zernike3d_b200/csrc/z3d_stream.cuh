@@ -195,6 +195,7 @@ __device__ __forceinline__ void st_hint(float *p, float v, unsigned long long po
 // (tcgen05.ld, 32 loads, add, 32 stores) of 2 000 - 3 500 clk while the T stream saturates the memory system (measured with
 // clock64 stamps), and the tensor core idles until the slowest warp is through: the units are dealt out evenly (at most 3 per
 // warp for 512 columns) and the partial sums are kept L2-resident (evict-last; the folds, 537 MB per tile, are evict-normal).
+template <int WARP0 = S_WARP_PROD0>
 __device__ __forceinline__ void s_flush(unsigned tmem, int ncols, float *out, bool add, unsigned drained_bar, unsigned parity, bool dbg_sleep = false) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3;
     const unsigned long long pol = l2_policy_evict_last();
@@ -202,7 +203,7 @@ __device__ __forceinline__ void s_flush(unsigned tmem, int ncols, float *out, bo
     if (dbg_sleep) __nanosleep(3000);
     tc_fence_after();
 #pragma unroll 1
-    for (int c32 = 32 * ((warp - S_WARP_PROD0) >> 2); c32 < ncols; c32 += 32 * (S_NPW / 4)) {
+    for (int c32 = 32 * ((warp - WARP0) >> 2); c32 < ncols; c32 += 32 * (S_NPW / 4)) {
         unsigned v[32];
         tmem_ld32(tmem + ((unsigned)(32 * q) << 16) + c32, v);
         float *p = out + (size_t)c32 * BTM + 32 * q + lane;
