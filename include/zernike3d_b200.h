@@ -187,6 +187,10 @@ int z3d_profile_last_ms(z3d_plan *plan, float *ms);
  * variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2. */
 int z3d_fma_peak(int device, int variant, int iters, double *tflops);
 
+/* Measured dense TF32 tensor-pipe throughput of `device` in TFLOP/s: tcgen05.mma kind::tf32 (M 128, N 256, K 8) issued back to
+ * back on every SM, iters x 8 instructions per SM.  The roofline denominator of the batched analysis kernel in bench.py. */
+int z3d_tf32_peak(int device, int iters, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

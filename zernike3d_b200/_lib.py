@@ -79,6 +79,7 @@ def lib() -> ctypes.CDLL:
     L.z3d_profile_enable.argtypes = [c_void_p, c_int]
     L.z3d_profile_last_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
     L.z3d_fma_peak.argtypes = [c_int, c_int, c_int, ctypes.POINTER(ctypes.c_double)]
+    L.z3d_tf32_peak.argtypes = [c_int, c_int, ctypes.POINTER(ctypes.c_double)]
     _lib = L
     return L
 
@@ -94,5 +95,5 @@ EXPORTS = [
     "z3d_reconstruct", "z3d_invariants", "z3d_decompose_host", "z3d_reconstruct_host", "z3d_launch_count",
     "z3d_fma_peak", "z3d_profile_enable", "z3d_profile_last_ms", "z3d_decompose_part", "z3d_comm_create", "z3d_comm_connect", "z3d_comm_destroy", "z3d_comm_error",
     "z3d_decompose_allreduce", "z3d_scale_moments", "z3d_stream_layout", "z3d_zcc", "z3d_crop_bin", "z3d_gen_layout",
-    "z3d_plan_prepare_tables",
+    "z3d_plan_prepare_tables", "z3d_tf32_peak",
 ]

@@ -1783,6 +1783,36 @@ extern "C" int z3d_fma_peak(int device, int variant, int iters, double *tflops) 
     return Z3D_OK;
 }
 
+// Measured dense TF32 tensor-pipe peak (tcgen05.mma kind::tf32, M 128, N 256, K 8 back to back on every SM): the denominator of
+// bench.py's roofline for the batched analysis kernel.
+extern "C" int z3d_tf32_peak(int device, int iters, double *tflops) {
+    if (!tflops || iters < 1) return fail(Z3D_ERR_INVALID, "z3d_tf32_peak: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) {
+        cudaGetLastError();
+        return fail(Z3D_ERR_NODEVICE, "z3d_tf32_peak: no such CUDA device");
+    }
+    USE_DEVICE(device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    k_tf32_peak<<<prop.multiProcessorCount, 128>>>(iters);  // warm-up
+    CUDA_TRY(cudaEventRecord(e0));
+    k_tf32_peak<<<prop.multiProcessorCount, 128>>>(iters);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 2;
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    *tflops = (double)prop.multiProcessorCount * (double)iters * 8.0 * (2.0 * 128 * 256 * 8) / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return Z3D_OK;
+}
+
 #ifdef Z3D_GEN_DEBUG
 // developer aid: mapped host memory the kernel's bounded waits report into (survives a trapped context)
 static int *g_trap_host = nullptr;

@@ -625,4 +625,48 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Measured tensor-pipe peak for the roofline (bench.py): back-to-back tcgen05.mma kind::tf32, M 128, N 256, K 8, shared-memory
+// operands (zeros), one converged warp issuing through elect.sync, one CTA per SM.  What the pipe sustains when nothing else
+// happens on the SM: N / 2 clk per instruction = 4096 flop / clk / SM.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) k_tf32_peak(int iters) {
+    __shared__ __align__(128) float sm[2 * 256 * 8 + 2 * 128 * 8];   // B: 256 rows x 8 (k halves apart), A: 128 rows x 8
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ unsigned tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 2 * 256 * 8 + 2 * 128 * 8; i += 128) sm[i] = 0.0f;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = tmem_slot;
+    if (warp == 0) {
+        const unsigned long long dB = umma_desc(smem_u32(sm), 256 * 16, 128), dA = umma_desc(smem_u32(sm + 2 * 256 * 8), 128 * 16, 128);
+        const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+        for (int it = 0; it < iters; ++it) {
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) umma_tf32(tmem + (unsigned)((j & 1) * 256), dA, dB, idesc, 1u);
+            }
+            __syncwarp();
+        }
+        if (elect_one()) umma_commit(smem_u32(&bar));
+        __syncwarp();
+        mbar_wait(smem_u32(&bar), 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
 }  // namespace z3d

@@ -284,3 +284,10 @@ def fma_peak_tflops(device: int = 0, variant: int = 0, iters: int = 4096) -> flo
     v = ctypes.c_double()
     _lib.check(_lib.lib().z3d_fma_peak(device, variant, iters, ctypes.byref(v)))
     return v.value
+
+
+def tf32_peak_tflops(device: int = 0, iters: int = 2048) -> float:
+    """Measured dense TF32 tensor-pipe throughput (``z3d_tf32_peak``): back-to-back tcgen05.mma kind::tf32 on every SM."""
+    v = ctypes.c_double()
+    _lib.check(_lib.lib().z3d_tf32_peak(device, iters, ctypes.byref(v)))
+    return v.value
