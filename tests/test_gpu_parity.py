@@ -384,12 +384,14 @@ def test_round_trip_full_size_properties(plans):
         assert cc > 0.9
 
 
-def test_256_stress_case(plans):
-    """C5b: 256^3 order 50 (the reference would need a 223 GB basis).  Size-independent checks: slab additivity,
-    real m = 0 moments, determinism."""
+def test_256_stress_case(plans, oracle_mod):
+    """C5b: 256^3 order 50 (the reference would need a 223 GB basis).  Plane-pair partials and reconstructed planes against the
+    float64 oracle (bounded CPU work: `rows=`), one whole volume against the oracle, a batch of 8 through the table-free
+    tensor-core kernel (the same kernel as at 128^3: no table, so no size cliff), slab additivity, real m = 0 moments, determinism."""
     order, dim = 50, 256
     P = plans(order, dim)
-    dv = dev(volume(8, dim))
+    v = volume(8, dim)
+    dv = dev(v)
     full = P.decompose(dv)
     parts = P.decompose(dv, pairs=(0, 50)) + P.decompose(dv, pairs=(50, 128))
     assert rel_l2(parts.cpu().numpy(), full.cpu().numpy()) < 1e-6   # different float32 summation grouping only
@@ -399,6 +401,75 @@ def test_256_stress_case(plans):
     m0 = nlm_table(order)[:, 2] == 0
     f = full.cpu().numpy()
     assert np.all(f.imag[m0] == 0) and np.isfinite(f.view(np.float32)).all()
+    # plane pairs (edge, off-centre, centre) against oracle rows: zm:2194-2217 restricted to the planes of the pair
+    for lo in (0, 77, 127):
+        got = P.decompose(dv, pairs=(lo, lo + 1)).cpu().numpy()
+        want = (oracle_mod.decompose(v, order, oracle_mod.EXACT, rows=(lo, lo + 1), return_f64=True)
+                + oracle_mod.decompose(v, order, oracle_mod.EXACT, rows=(dim - 1 - lo, dim - lo), return_f64=True))
+        assert rel_l2(got, want) < TOL_EXACT
+    exact = oracle_mod.decompose(v, order, oracle_mod.EXACT)          # the whole volume once (~15 s of host threads)
+    assert rel_l2(f, exact) < TOL_EXACT
+    assert rel_l2(P.invariants(full).cpu().numpy(), oracle_mod.invariants(exact, order)) < TOL_INV
+    # reconstructed planes against oracle rows (zm:2596-2614)
+    rec = P.reconstruct(full).cpu().numpy()
+    scale = np.sqrt(np.mean(rec.astype(np.float64) ** 2))
+    for p_ in (1, 100, 128, 255):
+        want = oracle_mod.reconstruct(f, dim, order, oracle_mod.EXACT, rows=(p_, p_ + 1))[0]
+        assert np.sqrt(np.mean((rec[p_] - want) ** 2)) / scale < TOL_EXACT
+    del rec
+    # a batch of 8 (>= gen_min): the tensor-core kernel at 256^3, volume 0 = v
+    batch = torch.stack([dv] + [dev(volume(80 + i, dim)) for i in range(7)])
+    info = P.info()
+    assert info["gen"] == 1 and batch.shape[0] >= info["gen_min"]
+    mb = P.decompose(batch).cpu().numpy()
+    assert rel_l2(mb[0], exact) < TOL_EXACT_BATCHED
+    assert rel_l2(P.invariants(dev(mb[0])).cpu().numpy(), oracle_mod.invariants(exact, order)) < TOL_INV
+    for i in (3, 7):
+        assert rel_l2(mb[i], P.decompose(batch[i]).cpu().numpy()) < 2 * TOL_EXACT_BATCHED
+
+
+def test_3dva_bundle_at_size(plans, oracle_mod):
+    """C4 at the BASELINE size: base map + 5 components at 128^3, order 50, ONE call (zm:2886-2889).  The base map is the golden
+    volume of C3, so its moments are checked against the reference's own run; every member against the float64 oracle."""
+    order, dim = 50, 128
+    P = plans(order, dim)
+    g = golden("c3_d128_o50")
+    base = volume(int(g["seeds"][0]), dim)
+    comps = []
+    for i in range(5):
+        c = 0.1 * volume(300 + i, dim)
+        comps.append((c - c.mean()).astype(np.float32))
+    vols = np.stack([base, *comps])
+    moms = P.decompose(dev(vols)).cpu().numpy()
+    assert rel_l2(moms[0], g["moments"][0]) < TOL_MOM
+    for i in range(6):
+        exact = oracle_mod.decompose(vols[i], order, oracle_mod.EXACT)
+        assert rel_l2(moms[i], exact) < TOL_EXACT
+        assert rel_l2(P.invariants(dev(moms[i])).cpu().numpy(), oracle_mod.invariants(exact, order)) < TOL_INV
+    assert np.array_equal(moms, np.stack([P.decompose(dev(x)).cpu().numpy() for x in vols]))   # bundle == one by one, bit for bit
+
+
+def test_reconstruction_at_full_size_against_oracle_planes(plans, oracle_mod):
+    """Synthesis at the BASELINE sizes (96^3 / order 60, 128^3 / order 50) against float64 oracle planes of zm:2596-2614 spread over
+    the box, instead of a property check: per plane and against the whole-map RMS."""
+    for name, planes in (("c5_d96_o60", (0, 17, 47, 48, 70, 95)), ("c3_d128_o50", (0, 9, 63, 64, 101, 127))):
+        g = golden(name)
+        order, dim = int(g["order"]), int(g["dim"])
+        P = plans(order, dim)
+        mom = np.asarray(g["moments"][0], np.complex64)
+        rec = P.reconstruct(dev(mom)).cpu().numpy()
+        scale = np.sqrt(np.mean(rec.astype(np.float64) ** 2))
+        for p_ in planes:
+            want = oracle_mod.reconstruct(mom, dim, order, oracle_mod.EXACT, rows=(p_, p_ + 1))[0]
+            assert rel_l2(rec[p_], want) < TOL_MAP
+            assert np.sqrt(np.mean((rec[p_] - want) ** 2)) / scale < TOL_EXACT
+        # and the round trip: decompose(reconstruct(mom)) is a fixed linear map of mom; the oracle's planes above pin the synthesis,
+        # here the analysis of that map must reproduce the oracle's analysis of the same map on a plane pair
+        lo = dim // 3
+        got = P.decompose(dev(rec), pairs=(lo, lo + 1)).cpu().numpy()
+        want = (oracle_mod.decompose(rec, order, oracle_mod.EXACT, rows=(lo, lo + 1), return_f64=True)
+                + oracle_mod.decompose(rec, order, oracle_mod.EXACT, rows=(dim - 1 - lo, dim - lo), return_f64=True))
+        assert rel_l2(got, want) < TOL_EXACT
 
 
 def test_host_buffer_api_matches_device_api(plans):
@@ -434,7 +505,7 @@ def test_error_paths(plans):
         P.reconstruct(torch.zeros(5, dtype=torch.complex64, device="cuda"))
 
 
-def test_cli_end_to_end(tmp_path, oracle_mod):
+def test_cli_end_to_end(tmp_path, oracle_mod, monkeypatch):
     """`zernike_master.py decomposition` -> .npz -> `reconstruct` -> .mrc, compared with the oracle."""
     import zernike_master as cli
     from zernike3d_b200 import mrc
@@ -454,6 +525,16 @@ def test_cli_end_to_end(tmp_path, oracle_mod):
     assert cli.main(f"reconstruct --mode spharm --moments {out}.npz --order {order} --dimensions {dim} --output {rec}".split()) == 0
     back = mrc.read(str(tmp_path / "rec_0.mrc")).data          # `<out>_<rec>.mrc` (zm:2714)
     assert rel_l2(back, oracle_mod.reconstruct(mom, dim, order, oracle_mod.EXACT)) < TOL_EXACT
+    # --verbose: the running sum after every fifth order in the working directory (zm:2703-2705)
+    from zernike3d_b200.indexing import num_moments
+
+    monkeypatch.chdir(tmp_path)
+    assert cli.main(f"reconstruct --mode spharm --moments {out}.npz --order {order} --dimensions {dim} --output {rec} --verbose".split()) == 0
+    for n in (0, 5, 10):
+        part = mrc.read(str(tmp_path / f"intermediate_vol_component_0n_{n:03d}.mrc")).data
+        cut = mom.copy()
+        cut[num_moments(n):] = 0
+        assert rel_l2(part, oracle_mod.reconstruct(cut, dim, order, oracle_mod.EXACT)) < 2 * TOL_EXACT
 
     # 3DVA bundle in, latents + arr_0..arr_K out, then a latent-scaled reconstruction
     part, cons, comps = bundle_3dva(dim, components=2, particles=16, seed=2)

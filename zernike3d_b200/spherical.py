@@ -141,6 +141,21 @@ class ZernikeSpherical:
             mat[i] = v[:want]
         print(f"Summing the Zernike components up to order, n: {order}")
         vols = self.plan.reconstruct(torch.from_numpy(mat).to(f"cuda:{self.plan.device}")).cpu().numpy()
+        if getattr(self.args, "verbose", False):
+            # zm:2703-2705: the running sum after every fifth order, `intermediate_vol_component_<rec>n_<nnn>.mrc` in the working
+            # directory.  The flat moment order is sorted by n first, so the sum up to order n is the synthesis of a prefix:
+            # all cut-offs of all maps go through ONE batched call.
+            from .indexing import num_moments as _nm
+
+            cuts = [n for n in range(order + 1) if n % 5 == 0]
+            trunc = np.zeros((len(vecs) * len(cuts), want), dtype=np.complex64)
+            for i in range(len(vecs)):
+                for j, n in enumerate(cuts):
+                    trunc[i * len(cuts) + j, :_nm(n)] = mat[i, :_nm(n)]
+            tv = self.plan.reconstruct(torch.from_numpy(trunc).to(f"cuda:{self.plan.device}")).cpu().numpy()
+            for i in range(len(vecs)):
+                for j, n in enumerate(cuts):
+                    self.write_mrc_file(volume=tv[i * len(cuts) + j], name=f"intermediate_vol_component_{i}n_{str(n).zfill(3)}.mrc")
         stem = str(self.args.output).split(".")[0]
         out = []
         for rec, vol in enumerate(vols):
