@@ -461,8 +461,9 @@ def test_reconstruction_at_full_size_against_oracle_planes(plans, oracle_mod):
         scale = np.sqrt(np.mean(rec.astype(np.float64) ** 2))
         for p_ in planes:
             want = oracle_mod.reconstruct(mom, dim, order, oracle_mod.EXACT, rows=(p_, p_ + 1))[0]
-            assert rel_l2(rec[p_], want) < TOL_MAP
-            assert np.sqrt(np.mean((rec[p_] - want) ** 2)) / scale < TOL_EXACT
+            assert np.sqrt(np.mean((rec[p_] - want) ** 2)) / scale < TOL_EXACT      # the bar is norm-wise over the map
+            if np.sqrt(np.mean(want.astype(np.float64) ** 2)) > 0.05 * scale:       # and per plane wherever the plane is not
+                assert rel_l2(rec[p_], want) < TOL_MAP                              # ~100x fainter than the map (edge planes)
         # and the round trip: decompose(reconstruct(mom)) is a fixed linear map of mom; the oracle's planes above pin the synthesis,
         # here the analysis of that map must reproduce the oracle's analysis of the same map on a plane pair
         lo = dim // 3
