@@ -72,7 +72,8 @@ int z3d_plan_destroy(z3d_plan *plan);
  * to 16, 22 size of the T table in MiB, 23 chunks of 8 folded voxels per volume;
  * table-free tensor-core variant (the default for batches): 24 available, 25 column sets, 26 splits, 27 accumulator columns over all
  * sets, 28 depth of the shared-memory T ring, 29 smallest batch routed to it, 30 basis-table level in use (z3d_plan_prepare_tables),
- * 31 columns of the widest set. */
+ * 31 columns of the widest set; its two-tile layout (while more than 64 volumes are left, 128 volumes share every generated
+ * T block): 32 available, 33 column sets, 34 splits, 35 depth of the T ring. */
 int z3d_plan_info(const z3d_plan *plan, int *info, int n_info);
 
 /* Host-only planner query (no device needed): the column-set layout of the streamed-T batched analysis kernel for `order` on a
@@ -86,6 +87,9 @@ int z3d_stream_layout(int order, int num_sms, int *out, int n_out);
  * list, 3 accumulator columns over all sets, 4 columns of the widest set, 5 violated invariants (0 = self-check passed),
  * 6 / 7 / 8 most a panels / MMA segments / recurrence-chain tasks of a set, 9 most seed rows, 10 estimated clocks per chunk. */
 int z3d_gen_layout(int order, int num_sms, int *out, int n_out);
+/* ... of the layout for `ntile` = 1 or 2 tiles of 64 volumes per generated T block (2: the sets hold half the columns - two
+ * accumulator banks and two sets of a-panel slots share the 512 tensor-memory columns - and the chunk list has half the splits). */
+int z3d_gen_layout_tiles(int order, int num_sms, int ntile, int *out, int n_out);
 
 /* Opt-in basis tables.  The default path never materialises a basis function: batches run through a tensor-core kernel that
  * generates R_nl * Q_lm in registers.  A caller with memory to spare may instead ask for the table-fed kernels of round 1:

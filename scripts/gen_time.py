@@ -12,4 +12,4 @@ ms = []
 for _ in range(5):
     P.decompose(v); ms.append(P.last_kernel_ms())
 i = P.info()
-print(f"dim {dim} order {order}: gen sets {i['gen_sets']} x {i['gen_splits']} slots {i['gen_slots']}: contraction kernel {min(ms):.3f} ms per {B} volumes = {min(ms) / B * 1e3:.1f} us/vol")
+print(f"dim {dim} order {order} B {B}: gen2 {i["gen2_sets"]} x {i["gen2_splits"]} gen sets {i['gen_sets']} x {i['gen_splits']} slots {i['gen_slots']}: contraction kernel {min(ms):.3f} ms per {B} volumes = {min(ms) / B * 1e3:.1f} us/vol")

@@ -58,6 +58,7 @@ def lib() -> ctypes.CDLL:
     L.z3d_plan_info.argtypes = [c_void_p, ctypes.POINTER(c_int), c_int]
     L.z3d_stream_layout.argtypes = [c_int, c_int, ctypes.POINTER(c_int), c_int]
     L.z3d_gen_layout.argtypes = [c_int, c_int, ctypes.POINTER(c_int), c_int]
+    L.z3d_gen_layout_tiles.argtypes = [c_int, c_int, c_int, ctypes.POINTER(c_int), c_int]
     L.z3d_plan_prepare_tables.argtypes = [c_void_p, c_int, c_size_t, ctypes.POINTER(c_int)]
     L.z3d_zcc.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
     L.z3d_crop_bin.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
@@ -94,6 +95,6 @@ EXPORTS = [
     "z3d_plan_create", "z3d_plan_destroy", "z3d_plan_info", "z3d_workspace_bytes", "z3d_decompose",
     "z3d_reconstruct", "z3d_invariants", "z3d_decompose_host", "z3d_reconstruct_host", "z3d_launch_count",
     "z3d_fma_peak", "z3d_profile_enable", "z3d_profile_last_ms", "z3d_decompose_part", "z3d_comm_create", "z3d_comm_connect", "z3d_comm_destroy", "z3d_comm_error",
-    "z3d_decompose_allreduce", "z3d_scale_moments", "z3d_stream_layout", "z3d_zcc", "z3d_crop_bin", "z3d_gen_layout",
+    "z3d_decompose_allreduce", "z3d_scale_moments", "z3d_stream_layout", "z3d_zcc", "z3d_crop_bin", "z3d_gen_layout", "z3d_gen_layout_tiles",
     "z3d_plan_prepare_tables", "z3d_tf32_peak",
 ]

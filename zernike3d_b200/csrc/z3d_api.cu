@@ -109,6 +109,13 @@ struct z3d_plan {
     int g_smem = 0, g_ncols_all = 0, g_maxcols = 0;
     GenIssue g_issue{};          // per-set MMA issue table, passed in the kernel parameters
     int2 *d_gcolmap = nullptr;
+    // ... its two-tile layout (128 volumes per generated T block: half the columns per set, half the splits), used while more than
+    // one tile of volumes is left; absent when the order needs more sets than SMs (order > ~70)
+    bool gen2 = false;
+    DevPlanG devg2{};
+    int g2_smem = 0;
+    GenIssue g2_issue{};
+    int2 *d_g2colmap[2] = {nullptr, nullptr};   // (set, accumulator column) of every moment, per tile
     // reduce / prepare tables
     int *d_src = nullptr;        // [2*nmom]  pass*SLOT_WORDS + word
     double *d_scale = nullptr;   // [nmom]    coeff(n) * kappa_lm
@@ -666,7 +673,9 @@ struct HostPlanG {
 // boundaries only - into sets of equal estimated tensor-pipe time per chunk: an MMA of N columns takes max(24, N / 2) clocks
 // (scripts/experiments/tc_probe4.cu), three per segment.  Limits per set: accumulator columns + 2 a-panel slots of 16 columns
 // per panel <= 512 (tensor memory), <= G_PANELS panels, <= G_SEGS segments, <= G_TASKS chain tasks, one kind.
-void build_gen_plan(int L, int num_sms, const HostPlan &hp, HostPlanG &hg, int force_splits) {
+// ntile = 2: TWO tiles of 64 volumes share every generated T block (two accumulator banks and two sets of a-panel slots in tensor
+// memory), so a set holds half the columns and the chunk list is cut into half as many splits.
+void build_gen_plan(int L, int num_sms, const HostPlan &hp, HostPlanG &hg, int force_splits, int ntile = 1) {
     const int S = L + 1;
     struct Chain { int l, len; };
     struct Group { int kind, m, pz; std::vector<Chain> chains; };
@@ -684,7 +693,7 @@ void build_gen_plan(int L, int num_sms, const HostPlan &hp, HostPlanG &hg, int f
     auto piece_cost = [&](int rows) {
         double c = 48.0;  // a panel: the a-panel team's work
         for (int c0 = 0, cols = pad16(rows); c0 < cols; c0 += 256) c += 3.0 * std::max(24.0, 0.5 * std::min(256, cols - c0));
-        return c;
+        return c * ntile;
     };
     auto set_cost = [&](const std::vector<Piece> &st) {
         double c = 0.0;
@@ -698,7 +707,7 @@ void build_gen_plan(int L, int num_sms, const HostPlan &hp, HostPlanG &hg, int f
             segs += (pad16(p.rows) + 255) / 256;
             chains += p.count;
         }
-        return cols + 32 * (int)st.size() <= 512 && (int)st.size() <= G_PANELS && segs <= G_SEGS && 2 * chains <= G_TASKS;
+        return ntile * (cols + 32 * (int)st.size()) <= 512 && (int)st.size() <= G_PANELS && segs <= G_SEGS && 2 * chains <= G_TASKS;
     };
     auto pack = [&](double cap) {
         Sets sets;
@@ -798,7 +807,7 @@ void build_gen_plan(int L, int num_sms, const HostPlan &hp, HostPlanG &hg, int f
         T.npanel = (int)st.size();
         T.kind = groups[st[0].group].kind;
         T.lpar = (groups[st[0].group].m + groups[st[0].group].pz) & 1;
-        T.acol0 = 512 - 2 * 16 * T.npanel;
+        T.acol0 = 512 - ntile * 2 * 16 * T.npanel;
         struct TaskC { int row0, len, rk, srow; };
         std::vector<TaskC> chains;
         int off = 0, soff = 0, gdo = 0;
@@ -870,7 +879,7 @@ void build_gen_plan(int L, int num_sms, const HostPlan &hp, HostPlanG &hg, int f
                     }
         }
         T.ntask = nt;
-        if (nt > G_TASKS || T.nseg > G_SEGS || T.ncols + 32 * T.npanel > 512) return;
+        if (nt > G_TASKS || T.nseg > G_SEGS || ntile * (T.ncols + 32 * T.npanel) > 512) return;
     }
     for (const int2 &r : hg.colmap)
         if (r.x < 0) return;
@@ -895,8 +904,10 @@ int set_kernel_attrs(int smem) {
     CUDA_TRY(cudaFuncSetAttribute(k_decompose_batched<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUDA_TRY(cudaFuncSetAttribute(k_decompose_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaFuncSetAttribute(k_decompose_stream, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CUDA_TRY(cudaFuncSetAttribute(k_decompose_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_decompose_gen, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_gen<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_gen<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_gen<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_decompose_gen<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return set_kernel_attrs_t<0>(smem);
 }
 
@@ -1051,13 +1062,18 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
         }
     }
     if (dim >= 14) {  // table-free variant (dim >= 14 keeps every 8-voxel chunk and its z-mirror inside a row)
-        HostPlanG hg;
         int force = 0;
         if (const char *e = getenv("Z3D_GEN_SPLITS")) force = atoi(e);
         const char *off = getenv("Z3D_GEN");
-        if (!(off && atoi(off) == 0)) build_gen_plan(order, prop.multiProcessorCount, hp, hg, force);
-        if (hg.ok) {
-            DevPlanG &g = pl->devg;
+        const char *off2 = getenv("Z3D_GEN2");
+        for (int ntile = 1; ntile <= 2; ++ntile) {
+            if (off && atoi(off) == 0) break;
+            if (ntile == 2 && (!pl->gen || (off2 && atoi(off2) == 0))) break;
+            HostPlanG hg;
+            build_gen_plan(order, prop.multiProcessorCount, hp, hg, force, ntile);
+            if (!hg.ok) continue;
+            DevPlanG &g = ntile == 1 ? pl->devg : pl->devg2;
+            GenIssue &issue = ntile == 1 ? pl->g_issue : pl->g2_issue;
             g.order = order; g.dim = dim; g.H = pl->H; g.nsets = hg.nsets; g.nsplits = hg.nsplits;
             g.tslot_bytes = hg.maxcols * 64;
             g.gslot_bytes = (40 + hg.maxseedrows * 8) * 4;
@@ -1070,25 +1086,33 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
             if (const char *e = getenv("Z3D_GEN_DBG")) g.dbg = atoi(e);
             g.nslots = std::min(G_NS_MAX, ((int)prop.sharedMemPerBlockOptin - g.off_t) / g.tslot_bytes);
             if (const char *e = getenv("Z3D_GEN_SLOTS")) g.nslots = std::max(2, std::min(g.nslots, atoi(e)));
-            if (g.nslots >= G_NTT && hg.nsets <= G_MAXSETS) {   // a T team's first chunk behind a read-back must find a free slot (see z3d_gen.cuh)
-                GenTabs *d_tabs; int4 *d_tasks; float2 *d_ggd; float4 *d_grk;
-                UP(hg.tabs, d_tabs) UP(hg.tasks, d_tasks) UP(hg.gd, d_ggd) UP(hg.rk, d_grk) UP(hg.colmap, pl->d_gcolmap)
-                g.tabs = d_tabs; g.tasks = d_tasks; g.gd = d_ggd; g.rk = d_grk; g.side = d_side;
+            if (g.nslots < G_NTT || hg.nsets > G_MAXSETS) continue;   // a T team's first chunk behind a read-back must find a free slot (see z3d_gen.cuh)
+            GenTabs *d_tabs; int4 *d_tasks; float2 *d_ggd; float4 *d_grk;
+            UP(hg.tabs, d_tabs) UP(hg.tasks, d_tasks) UP(hg.gd, d_ggd) UP(hg.rk, d_grk)
+            g.tabs = d_tabs; g.tasks = d_tasks; g.gd = d_ggd; g.rk = d_grk; g.side = d_side;
+            for (int i = 0; i < hg.nsets; ++i) {
+                const GenTabs &T = hg.tabs[i];
+                issue.hdr[i] = make_int4(T.ncols, T.nseg, T.npanel, T.acol0);
+                for (int s2 = 0; s2 < G_SEGS; ++s2) {
+                    const bool v = s2 < T.nseg;
+                    const int n = v ? T.seg_cols[s2] : 16;
+                    issue.seg[i][s2] = make_int4((int)((1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(SM_ROWS >> 4) << 24)),
+                                                 v ? T.seg_panel[s2] * 16 : 0, v ? T.seg_off[s2] : 0, v ? 0 : -1);
+                }
+            }
+            if (ntile == 1) {
+                UP(hg.colmap, pl->d_gcolmap)
                 pl->g_smem = g.off_t + g.nslots * g.tslot_bytes;
                 pl->g_ncols_all = hg.ncols_all;
                 pl->g_maxcols = hg.maxcols;
-                for (int i = 0; i < hg.nsets; ++i) {
-                    const GenTabs &T = hg.tabs[i];
-                    pl->g_issue.hdr[i] = make_int4(T.ncols, T.nseg, T.npanel, T.acol0);
-                    for (int s2 = 0; s2 < G_SEGS; ++s2) {
-                        const bool v = s2 < T.nseg;
-                        const int n = v ? T.seg_cols[s2] : 16;
-                        pl->g_issue.seg[i][s2] = make_int4((int)((1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(SM_ROWS >> 4) << 24)),
-                                                          v ? T.seg_panel[s2] * 16 : 0, v ? T.seg_off[s2] : 0, v ? 0 : -1);
-                    }
-                }
                 pl->b_chunks = (long long)analysis_items(0, pl->H, pl->H) * ((pl->H + KC - 1) / KC);
                 pl->gen = true;
+            } else {
+                std::vector<int2> cm1 = hg.colmap;   // tile 1's accumulators follow tile 0's
+                for (int2 &c : cm1) c.y += hg.tabs[c.x].ncols;
+                UP(hg.colmap, pl->d_g2colmap[0]) UP(cm1, pl->d_g2colmap[1])
+                pl->g2_smem = g.off_t + g.nslots * g.tslot_bytes;
+                pl->gen2 = true;
             }
         }
     }
@@ -1154,15 +1178,18 @@ extern "C" int z3d_stream_layout(int order, int num_sms, int *out, int n_out) {
 // Host-only: the column-set layout of the table-free kernel (no device needed; tests/test_cabi.py checks its invariants).
 // out[]: 0 available, 1 sets, 2 splits, 3 columns (all sets), 4 widest set, 5 violated invariants, 6 most panels, 7 most
 // segments, 8 most chain tasks, 9 most seed rows, 10 estimated clocks per chunk of the slowest set
-extern "C" int z3d_gen_layout(int order, int num_sms, int *out, int n_out) {
-    if (order < 0 || order > LMAX || num_sms < 1 || !out) return fail(Z3D_ERR_INVALID, "z3d_gen_layout: bad arguments");
+extern "C" int z3d_gen_layout_tiles(int order, int num_sms, int ntile, int *out, int n_out);
+extern "C" int z3d_gen_layout(int order, int num_sms, int *out, int n_out) { return z3d_gen_layout_tiles(order, num_sms, 1, out, n_out); }
+// ... of the layout for `ntile` (1 or 2) tiles of 64 volumes per generated T block
+extern "C" int z3d_gen_layout_tiles(int order, int num_sms, int ntile, int *out, int n_out) {
+    if (order < 0 || order > LMAX || num_sms < 1 || !out || ntile < 1 || ntile > 2) return fail(Z3D_ERR_INVALID, "z3d_gen_layout: bad arguments");
     HostPlan hp;
     int rc = build_host_plan(order, hp);
     if (rc) return rc;
     HostPlanG hg;
     int force = 0;
     if (const char *e = getenv("Z3D_GEN_SPLITS")) force = atoi(e);
-    build_gen_plan(order, num_sms, hp, hg, force);
+    build_gen_plan(order, num_sms, hp, hg, force, ntile);
     if (getenv("Z3D_GEN_DUMP"))   // developer aid: the sets on stderr
         for (int i = 0; i < hg.nsets && hg.ok; ++i) {
             const GenTabs &T = hg.tabs[i];
@@ -1186,8 +1213,8 @@ extern "C" int z3d_gen_layout(int order, int num_sms, int *out, int n_out) {
                 if (T.seg_panel[g] < 0 || T.seg_panel[g] >= T.npanel) ++bad;
                 cols += T.seg_cols[g];
             }
-            if (cols != T.ncols || T.ncols + 32 * T.npanel > 512 || T.npanel < 1 || T.npanel > G_PANELS || T.nseg > G_SEGS) ++bad;
-            if (T.ntask > G_TASKS || T.acol0 != 512 - 32 * T.npanel) ++bad;
+            if (cols != T.ncols || ntile * (T.ncols + 32 * T.npanel) > 512 || T.npanel < 1 || T.npanel > G_PANELS || T.nseg > G_SEGS) ++bad;
+            if (T.ntask > G_TASKS || T.acol0 != 512 - ntile * 32 * T.npanel) ++bad;
             std::vector<char> covered(T.ncols, 0);   // every chain task writes its own rows, twice (two k halves)
             for (int t = 0; t < T.ntask; ++t) {
                 const int4 tk = hg.tasks[(size_t)i * G_TASKS + t];
@@ -1239,7 +1266,7 @@ extern "C" int z3d_plan_destroy(z3d_plan *pl) {
 extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
     if (!pl || !info) return fail(Z3D_ERR_INVALID, "z3d_plan_info: NULL argument");
     const long long t_mb = pl->stream ? (long long)((double)pl->b_chunks * (double)pl->devs.trec * 4.0 / 1048576.0) : 0;
-    const int v[32] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
+    const int v[36] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
                        KC, pl->num_sms, pl->useful_acc, pl->padded_acc,
                        pl->batched ? pl->batched_min : 0, pl->devb[0].ngroups, pl->devb[1].ngroups, pl->batched ? pl->batched_wide : 0,
                        pl->devb[0].nrounds, pl->devb[1].nrounds,
@@ -1251,8 +1278,10 @@ extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
                        // table-free tensor-core variant: 24 available, 25 column sets, 26 splits, 27 moment rows padded to 16 per
                        // chain piece, 28 T-ring slots, 29 smallest batch routed to it, 30 basis-table level in use, 31 widest set
                        pl->gen ? 1 : 0, pl->devg.nsets, pl->devg.nsplits, pl->g_ncols_all, pl->devg.nslots, pl->gen ? pl->gen_min : 0,
-                       pl->tables_level, pl->g_maxcols};
-    for (int i = 0; i < n && i < 32; ++i) info[i] = v[i];
+                       pl->tables_level, pl->g_maxcols,
+                       // its two-tile layout (128 volumes per generated T block): 32 available, 33 column sets, 34 splits, 35 T-ring slots
+                       pl->gen2 ? 1 : 0, pl->devg2.nsets, pl->devg2.nsplits, pl->devg2.nslots};
+    for (int i = 0; i < n && i < 36; ++i) info[i] = v[i];
     return Z3D_OK;
 }
 
@@ -1269,7 +1298,7 @@ static size_t ws_decompose(const z3d_plan *pl, int batch) {
         w = std::max(w, (size_t)pl->num_sms * std::max(pl->devb[0].nrounds, pl->devb[1].nrounds) * BSLOT_WORDS * sizeof(float) +
                             (size_t)pl->b_chunks * ((pl->stream || batch >= pl->batched_wide) ? BCfg<64>::F_BYTES : BCfg<32>::F_BYTES));
     if (pl->gen && batch >= pl->gen_min)  // table-free tensor-core kernel: per-CTA partial sums + the folds of one tile of 64 volumes
-        w = std::max(w, (size_t)pl->num_sms * BSLOT_WORDS * sizeof(float) + (size_t)pl->b_chunks * 4 * S_FK_BYTES);
+        w = std::max(w, (size_t)pl->num_sms * BSLOT_WORDS * sizeof(float) + (size_t)pl->b_chunks * 4 * S_FK_BYTES * ((pl->gen2 && batch > SNV) ? 2 : 1));
     return w;
 }
 static size_t ws_reconstruct(const z3d_plan *pl, int batch) {
@@ -1413,22 +1442,33 @@ static int decompose_impl(const z3d_plan *pl, const float *d_vol, int batch, int
     // the threshold goes through the per-volume kernel
     const bool whole = half_lo == 0 && half_hi == pl->H;
     // default for batches: the table-free tensor-core kernel (tiles of up to 64 volumes; a tile costs the same whatever it holds)
+    // while more than one tile is left: two tiles per launch, which share every generated T block
     while (pl->gen && pl->tables_level == 0 && whole && batch - done >= pl->gen_min) {
-        const int nb = std::min(SNV, batch - done);
-        const DevPlanG &dp = pl->devg;
+        const bool two = pl->gen2 && batch - done > SNV;
+        const int nb = std::min(two ? 2 * SNV : SNV, batch - done);
+        const DevPlanG &dp = two ? pl->devg2 : pl->devg;
         const float *vol = d_vol + (size_t)done * N3;
         float *folds = partial + (size_t)pl->num_sms * BSLOT_WORDS;
+        const size_t tile_words = (size_t)pl->b_chunks * S_FK_BYTES;   // 4 kinds x S_FK_BYTES per chunk, in floats
         float *mom = d_moments + (size_t)done * 2 * pl->nmom;
-        k_fold_tile_gen<<<(unsigned)pl->b_chunks, 2 * SNV * KC, 0, st>>>(vol, nb, pl->dim, pl->H, folds);
+        k_fold_tile_gen<<<(unsigned)pl->b_chunks, 2 * SNV * KC, 0, st>>>(vol, std::min(nb, SNV), pl->dim, pl->H, folds);
+        if (two) k_fold_tile_gen<<<(unsigned)pl->b_chunks, 2 * SNV * KC, 0, st>>>(vol + (size_t)SNV * N3, nb - SNV, pl->dim, pl->H, folds + tile_words);
         CUDA_TRY(cudaGetLastError());
         const bool timed = pl->profiling && mpl->n_timed < z3d_plan::MAX_TIMED;
         if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t0[mpl->n_timed], st));
-        k_decompose_gen<<<dim3(dp.nsplits, dp.nsets), GNT, pl->g_smem, st>>>(dp, pl->g_issue, folds, part, nparts, partial);
+        if (two) k_decompose_gen<2><<<dim3(dp.nsplits, dp.nsets), GNT, pl->g2_smem, st>>>(dp, pl->g2_issue, folds, tile_words, part, nparts, partial);
+        else k_decompose_gen<1><<<dim3(dp.nsplits, dp.nsets), GNT, pl->g_smem, st>>>(dp, pl->g_issue, folds, 0, part, nparts, partial);
         CUDA_TRY(cudaGetLastError());
         if (timed) CUDA_TRY(cudaEventRecord(mpl->ev_t1[mpl->n_timed++], st));
-        k_reduce_stream<<<(pl->nmom * SM_ROWS + 255) / 256, 256, 0, st>>>(partial, pl->d_gcolmap, pl->d_scale, pl->nmom, dp.nsplits, nb, mom);
+        const unsigned rblocks = (unsigned)((pl->nmom * SM_ROWS + 255) / 256);
+        if (two) {
+            k_reduce_stream<<<rblocks, 256, 0, st>>>(partial, pl->d_g2colmap[0], pl->d_scale, pl->nmom, dp.nsplits, SNV, mom);
+            k_reduce_stream<<<rblocks, 256, 0, st>>>(partial, pl->d_g2colmap[1], pl->d_scale, pl->nmom, dp.nsplits, nb - SNV, mom + (size_t)SNV * 2 * pl->nmom);
+        } else {
+            k_reduce_stream<<<rblocks, 256, 0, st>>>(partial, pl->d_gcolmap, pl->d_scale, pl->nmom, dp.nsplits, nb, mom);
+        }
         CUDA_TRY(cudaGetLastError());
-        g_launches += 3;
+        g_launches += two ? 5 : 3;
         done += nb;
     }
     // opt-in (z3d_plan_prepare_tables): the table-fed kernels
@@ -1813,7 +1853,7 @@ extern "C" int z3d_tf32_peak(int device, int iters, double *tflops) {
     return Z3D_OK;
 }
 
-#ifdef Z3D_GEN_DEBUG
+#if defined(Z3D_GEN_DEBUG) && !defined(Z3D_GEN_ABL)
 // developer aid: mapped host memory the kernel's bounded waits report into (survives a trapped context)
 static int *g_trap_host = nullptr;
 extern "C" int z3d_debug_trap_arm(void) {

@@ -112,7 +112,7 @@ __device__ long long g_gdbg[32];
 #define GT_ADD(slot, t0, t1)
 #endif
 
-#ifdef Z3D_GEN_DEBUG
+#if defined(Z3D_GEN_DEBUG) && !defined(Z3D_GEN_ABL)
 // developer aid: hazard probes.  GD_SLEEP(bit) delays one role at one point when the bit is set in P.dbg (a race that
 // disappears under a delay names its hazard); bounded waits report the barrier that never completed through mapped host memory.
 __device__ int *g_gen_trap;
@@ -137,6 +137,7 @@ __device__ __forceinline__ void g_wait_dbg(unsigned mbar, unsigned parity, int i
 #define GW(bar, par, id, t) g_wait_dbg(bar, par, id, t)
 #define GWR(bar, par, id, t) g_wait_dbg(bar, par, id, t)
 #else
+// (-DZ3D_GEN_DEBUG -DZ3D_GEN_ABL: only the work-skipping switches of P.dbg, with the product's waits - timing ablations)
 #define GD_SLEEP(bit)
 #define GD_FLUSHSLEEP false
 #define GW(bar, par, id, t) mbar_wait(bar, par)
@@ -223,9 +224,14 @@ __device__ __forceinline__ void g_flush_event(unsigned tmem, int ncols, float *o
     ++nev;
 }
 
+// NTILE = 2: two tiles of 64 volumes per generated T block.  Tile 1's accumulators follow tile 0's in tensor memory (columns
+// [ncols, 2 ncols)), every a-panel slot holds both tiles' panels (slot (chunk parity, tile) at acol0 + (parity * NTILE + tile) *
+// 16 npanel), tile 1's folds lie `tile_stride` floats behind tile 0's.  T, the seeds and the geometry - everything that does not
+// depend on the volumes - is produced once per chunk and feeds 6 MMAs per segment instead of 3.
+template <int NTILE>
 __global__ void __launch_bounds__(GNT, 1)
-k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenIssue I, const float *__restrict__ Ft, int part, int nparts,
-                float *__restrict__ partial) {
+k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenIssue I, const float *__restrict__ Ft, size_t tile_stride,
+                int part, int nparts, float *__restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int set = blockIdx.y, split = blockIdx.x, bid = blockIdx.y * gridDim.x + blockIdx.x;   // grid = (splits, sets)
@@ -235,10 +241,13 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
     float4 *rks = reinterpret_cast<float4 *>(smem + P.off_rk);
     unsigned char *gring = smem + P.off_g, *tring = smem + P.off_t;
     const int NS = P.nslots;
-    // barriers: gfull[DG] gfree[DG] tfull[NS_MAX] tfree[NS_MAX] afull[2] afree[2] drained flushed
+    // barriers: gfull[DG] gfree[DG] tfull[NS_MAX] tfree[NS_MAX] afull[2][NTILE] afree[2][NTILE] drained flushed
+    // (the a-panel slots are handed over per TILE: tile 0's MMAs run while the team still builds tile 1's panels, and tile 0's slot
+    // is free again as soon as its own MMAs have retired)
     const unsigned gfull0 = smem_u32(bars), gfree0 = gfull0 + 8 * G_DG, tfull0 = gfree0 + 8 * G_DG, tfree0 = tfull0 + 8 * G_NS_MAX,
-                   afull0 = tfree0 + 8 * G_NS_MAX, afree0 = afull0 + 8 * G_NAT, drained = afree0 + 8 * G_NAT, flushed = drained + 8;
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + G_OFF_BAR + 8 * (2 * G_DG + 2 * G_NS_MAX + 2 * G_NAT + 2));
+                   afull0 = tfree0 + 8 * G_NS_MAX, afree0 = afull0 + 8 * G_NAT * 2, drained = afree0 + 8 * G_NAT * 2, flushed = drained + 8;
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + G_OFF_BAR + 8 * (2 * G_DG + 2 * G_NS_MAX + 4 * G_NAT + 2));
+    static_assert(8 * (2 * G_DG + 2 * G_NS_MAX + 4 * G_NAT + 2) + 4 <= G_OFF_GD - G_OFF_BAR, "barrier block");
     for (int i = tid; i < (int)(sizeof(GenTabs) / 4); i += GNT)
         reinterpret_cast<int *>(smem + G_OFF_TABS)[i] = reinterpret_cast<const int *>(P.tabs + set)[i];
     for (int i = tid; i < P.gd_bytes / 8; i += GNT) gds[i] = P.gd[(size_t)set * (P.gd_bytes / 8) + i];
@@ -255,7 +264,7 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(tfull0 + 8 * i));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tfree0 + 8 * i), "r"(nactive));
         }
-        for (int i = 0; i < G_NAT; ++i) {
+        for (int i = 0; i < G_NAT * 2; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(afull0 + 8 * i));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(afree0 + 8 * i), "r"(nactive));
         }
@@ -288,7 +297,7 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
     const int np16 = npanel * 16;
 
     if (nchunk == 0) {
-        for (int i = tid; i < ncols * BTM; i += GNT) out[i] = 0.0f;  // the reduction reads every split
+        for (int i = tid; i < NTILE * ncols * BTM; i += GNT) out[i] = 0.0f;  // the reduction reads every split
     } else if (warp < G_NISS) {
         // ---- issuing warps: warp w owns the segments g = w, w + G_NISS, .. (different accumulator columns: no ordering between the
         // warps' MMAs is needed); a warp without a segment has nothing to do.  The serial per-chunk path of an issuing warp (two
@@ -319,34 +328,42 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
                 const int as = t & 1;
                 GW(tfull0 + 8 * ts, tuse & 1, 2, t);
                 GT_T(i2);
-                GW(afull0 + 8 * as, (unsigned)(t >> 1) & 1, 3, t);
-                GD_SLEEP(4);
                 GT_T(i3);
-                if (wi == 0) { GT_ADD(0, i0, i1); GT_ADD(1, i1, i2); GT_ADD(2, i2, i3); }
-                tc_fence_after();
-                if (elect_one()) {
-                    const unsigned a = a0 + (unsigned)(as * np16);
+                if (wi == 0) { GT_ADD(0, i0, i1); GT_ADD(1, i1, i2); }
 #pragma unroll
-                    for (int q = 0; q < G_SEG_PER_ISS; ++q) {
+                for (int tile = 0; tile < NTILE; ++tile) {
+                    GT_T(j0);
+                    GW(afull0 + 8 * (as * NTILE + tile), (unsigned)(t >> 1) & 1, 3, t);
+                    GD_SLEEP(4);
+                    GT_T(j1);
+                    if (wi == 0) GT_ADD(2, j0, j1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const unsigned a = a0 + (unsigned)((as * NTILE + tile) * np16);
+#pragma unroll
+                        for (int q = 0; q < G_SEG_PER_ISS; ++q) {
 #ifdef Z3D_GEN_DEBUG
-                        if (P.dbg & 16384) continue;
+                            if (P.dbg & 16384) continue;
 #endif
-                        if (sg[q].w >= 0) {
-                            const unsigned long long b = dhi | (unsigned long long)(dlo + (unsigned)sg[q].z);
-                            const unsigned d = tmem + (unsigned)sg[q].z, ah = a + (unsigned)sg[q].y;
+                            if (sg[q].w >= 0) {
+                                const unsigned long long b = dhi | (unsigned long long)(dlo + (unsigned)sg[q].z);
+                                const unsigned d = tmem + (unsigned)(tile * ncols) + (unsigned)sg[q].z, ah = a + (unsigned)sg[q].y;
 #ifdef Z3D_GEN_DEBUG
-                            if (P.dbg & 2048) { umma_tf32_ts(d, ah, b, (unsigned)sg[q].x, since > 0 ? 1u : 0u); continue; }
+                                if (P.dbg & 2048) { umma_tf32_ts(d, ah, b, (unsigned)sg[q].x, since > 0 ? 1u : 0u); continue; }
 #endif
-                            umma_tf32_ts(d, ah, b + lo_t, (unsigned)sg[q].x, since > 0 ? 1u : 0u);  // small terms first
-                            umma_tf32_ts(d, ah + 8, b, (unsigned)sg[q].x, 1u);
-                            umma_tf32_ts(d, ah, b, (unsigned)sg[q].x, 1u);
+                                umma_tf32_ts(d, ah, b + lo_t, (unsigned)sg[q].x, since > 0 ? 1u : 0u);  // small terms first
+                                umma_tf32_ts(d, ah + 8, b, (unsigned)sg[q].x, 1u);
+                                umma_tf32_ts(d, ah, b, (unsigned)sg[q].x, 1u);
+                            }
+                        }
+                        umma_commit(afree0 + 8 * (as * NTILE + tile));
+                        if (tile == NTILE - 1) {
+                            umma_commit(tfree0 + 8 * ts);
+                            if (to_event == 1 || t == nchunk - 1) umma_commit(drained);  // a read-back follows this chunk
                         }
                     }
-                    umma_commit(tfree0 + 8 * ts);
-                    umma_commit(afree0 + 8 * as);
-                    if (to_event == 1 || t == nchunk - 1) umma_commit(drained);  // a read-back follows this chunk
+                    __syncwarp();
                 }
-                __syncwarp();
                 GT_T(i4);
                 if (wi == 0) GT_ADD(3, i3, i4);
                 ++since;
@@ -481,23 +498,30 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
         const int team = (warp - G_WARP_A0) >> 2, quarter = warp & 3;
         const int row = quarter * 32 + lane, reim = row >> 6, b = row & 63;
         const float sign = reim ? -1.0f : 1.0f;  // im rows are negated
-        const unsigned arow = tmem + ((unsigned)(32 * quarter) << 16) + (unsigned)T.acol0 + (unsigned)(team * np16);
+        const unsigned arow = tmem + ((unsigned)(32 * quarter) << 16) + (unsigned)T.acol0 + (unsigned)(team * NTILE * np16);
         const float *fbase = Ft + (size_t)T.kind * (S_FK_BYTES / 4) + (size_t)(reim * SNV + b) * KC;
         bool had = false;
         int nev = 0;
-        float4 fa0, fa1, fb0, fb1;
-        if (team < nchunk) {
-            const float *f = fbase + (size_t)(cbeg + team) * (4 * S_FK_BYTES / 4);
-            fa0 = ldg_stream4(f); fa1 = ldg_stream4(f + 4);
-            fb0 = ldg_stream4(f + 2 * SNV * KC); fb1 = ldg_stream4(f + 2 * SNV * KC + 4);
-        }
-        for (int t = team; t < nchunk; t += G_NAT) {
-            float4 na0 = fa0, na1 = fa1, nb0 = fb0, nb1 = fb1;
-            if (t + G_NAT < nchunk) {  // folds of the team's next chunk: in flight while this chunk's panels are built
-                const float *f = fbase + (size_t)(cbeg + t + G_NAT) * (4 * S_FK_BYTES / 4);
-                na0 = ldg_stream4(f); na1 = ldg_stream4(f + 4);
-                nb0 = ldg_stream4(f + 2 * SNV * KC); nb1 = ldg_stream4(f + 2 * SNV * KC + 4);
-            }
+        // The folds come from global memory (DRAM: a tile's folds are 0.5 GB) straight into registers, a whole round of the team
+        // ahead: with two tiles buffer i holds tile i's folds and is reloaded with the team's next chunk as soon as its panels are
+        // built; with one tile the buffers alternate between the team's chunks.  (One step ahead left a DRAM latency on the team's
+        // critical path: the kernel without any work - barriers and these loads only - took 960 clk per chunk, 1 480 with two tiles.)
+        struct Fold { float4 a0, a1, b0, b1; };
+        Fold F[2];
+        auto ldf = [&](Fold &f, int t, int tile) {
+            const float *q = fbase + (size_t)tile * tile_stride + (size_t)(cbeg + t) * (4 * S_FK_BYTES / 4);
+            f.a0 = ldg_stream4(q); f.a1 = ldg_stream4(q + 4);
+            f.b0 = ldg_stream4(q + 2 * SNV * KC); f.b1 = ldg_stream4(q + 2 * SNV * KC + 4);
+        };
+        constexpr int NU = NTILE == 1 ? 2 : 1;   // chunks per trip of the outer loop (static buffer indices)
+        if (team < nchunk) ldf(F[0], team, 0);
+        if (NTILE == 2) { if (team < nchunk) ldf(F[1], team, 1); }
+        else if (team + G_NAT < nchunk) ldf(F[1], team + G_NAT, 0);
+        for (int t0 = team; t0 < nchunk; t0 += NU * G_NAT) {
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            const int t = t0 + u * G_NAT;
+            if (t >= nchunk) break;
             int pos, len;
             s_interval(t, ev0, nchunk, pos, len);
             const float sg = sign * (1.0f + BTRUNC_PER_MMA * (float)(3 * (len - 1 - pos) + 1));  // truncation pre-compensation
@@ -506,39 +530,45 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
             GT_T(a0);
             GWR(gfull0 + 8 * gs, (unsigned)(t / G_DG) & 1, 5, t);
             GT_T(a1);
-            if (t >= G_NAT) GWR(afree0 + 8 * team, (unsigned)(t / G_NAT - 1) & 1, 6, t);  // the slot's previous MMAs retired
-            GD_SLEEP(32);
             GT_T(a2);
-            tc_fence_after();
-            const float fa[8] = {fa0.x, fa0.y, fa0.z, fa0.w, fa1.x, fa1.y, fa1.z, fa1.w};
-            const float fb[8] = {fb0.x, fb0.y, fb0.z, fb0.w, fb1.x, fb1.y, fb1.z, fb1.w};
-#ifdef Z3D_GEN_DEBUG
-            if (!(P.dbg & 4096))
-#endif
-            for (int j = 0; j < npanel; ++j) {
-                const float tA = slot[8 + j * 4 + reim] * sg, tB = slot[8 + j * 4 + 2 + reim] * sg;
-                float hi[8], lo[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) split_fast(fmaf(fa[q], tA, fb[q] * tB), hi[q], lo[q]);
-                tmem_st8(arow + (unsigned)(j * 16), hi);
-                tmem_st8(arow + (unsigned)(j * 16 + 8), lo);
-            }
-            tmem_st_wait();
-            GD_SLEEP(64);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(afull0 + 8 * team);
-                mbar_arrive(gfree0 + 8 * gs);
+            for (int tile = 0; tile < NTILE; ++tile) {
+                if (t >= G_NAT) GWR(afree0 + 8 * (team * NTILE + tile), (unsigned)(t / G_NAT - 1) & 1, 6, t);  // the slot's previous MMAs retired
+                GD_SLEEP(32);
+                tc_fence_after();
+                const int bi = NTILE == 1 ? u : tile;
+                const Fold &c = F[bi];
+                const float fa[8] = {c.a0.x, c.a0.y, c.a0.z, c.a0.w, c.a1.x, c.a1.y, c.a1.z, c.a1.w};
+                const float fb[8] = {c.b0.x, c.b0.y, c.b0.z, c.b0.w, c.b1.x, c.b1.y, c.b1.z, c.b1.w};
+#ifdef Z3D_GEN_DEBUG
+                if (!(P.dbg & 4096))
+#endif
+                for (int j = 0; j < npanel; ++j) {
+                    const float tA = slot[8 + j * 4 + reim] * sg, tB = slot[8 + j * 4 + 2 + reim] * sg;
+                    float hi[8], lo[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) split_fast(fmaf(fa[q], tA, fb[q] * tB), hi[q], lo[q]);
+                    tmem_st8(arow + (unsigned)(tile * np16 + j * 16), hi);
+                    tmem_st8(arow + (unsigned)(tile * np16 + j * 16 + 8), lo);
+                }
+                if (t + NU * G_NAT < nchunk) ldf(F[bi], t + NU * G_NAT, tile);   // in flight for a whole round of the team
+                tmem_st_wait();
+                GD_SLEEP(64);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(afull0 + 8 * (team * NTILE + tile));
+                    if (tile == NTILE - 1) mbar_arrive(gfree0 + 8 * gs);
+                }
             }
             GT_T(a3);
-            while (nev < nregular && ev0 + nev * BFLUSH_CHUNKS <= t) g_flush_event(tmem, ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
+            while (nev < nregular && ev0 + nev * BFLUSH_CHUNKS <= t) g_flush_event(tmem, NTILE * ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
             GT_T(a4);
             if (warp == G_WARP_A0) { GT_ADD(6, a0, a1); GT_ADD(7, a1, a2); GT_ADD(8, a2, a3); GT_ADD(9, a3, a4); }
-            fa0 = na0; fa1 = na1; fb0 = nb0; fb1 = nb1;
+          }
         }
-        while (nev < nregular) g_flush_event(tmem, ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
-        g_flush_event(tmem, ncols, out, had, drained, flushed, nev, true, GD_FLUSHSLEEP);
+        while (nev < nregular) g_flush_event(tmem, NTILE * ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
+        g_flush_event(tmem, NTILE * ncols, out, had, drained, flushed, nev, true, GD_FLUSHSLEEP);
     } else {
         // ---- T teams: thread u of a team owns tasks u and u + 128: (chain (l, m), k half) -> 4 voxels of every n of the chain
         // the tasks are sorted by chain length, so a team's first logical warp is its busiest: rotate the logical warps over the
@@ -613,12 +643,12 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
                 mbar_arrive(gfree0 + 8 * gs);
             }
             GT_T(t3);
-            while (nev < nregular && ev0 + nev * BFLUSH_CHUNKS <= t) g_flush_event(tmem, ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
+            while (nev < nregular && ev0 + nev * BFLUSH_CHUNKS <= t) g_flush_event(tmem, NTILE * ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
             GT_T(t4);
             if (u < 32 && team == 0) { GT_ADD(10, t0, t1); GT_ADD(11, t1, t2); GT_ADD(12, t2, t3); GT_ADD(13, t3, t4); }
         }
-        while (nev < nregular) g_flush_event(tmem, ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
-        g_flush_event(tmem, ncols, out, had, drained, flushed, nev, true, GD_FLUSHSLEEP);
+        while (nev < nregular) g_flush_event(tmem, NTILE * ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
+        g_flush_event(tmem, NTILE * ncols, out, had, drained, flushed, nev, true, GD_FLUSHSLEEP);
     }
     tc_fence_before();
     __syncthreads();
