@@ -18,7 +18,9 @@ L.z3d_debug_gen(buf, 1)
 i = P.info()
 nch = i["chunks"] // (i["gen2_splits"] if B > 64 and i["gen2"] else i["gen_splits"])
 names = ["issuer wait flushed", "issuer wait tfull", "issuer wait afull", "issuer issue", "seed0 wait gfree", "seed0 work (per its chunks)",
-         "A0 wait gfull", "A0 wait afree", "A0 work", "A0 flush", "T0 wait gfull", "T0 wait tfree", "T0 work", "T0 flush"]
+         "A0 wait gfull", "A0 wait afree", "A0 work", "A0 flush", "T0 wait gfull", "T0 wait tfree", "T0 work", "T0 flush",
+         "A0 fold read + panels + tcgen05.st issue", "A0 tcgen05.wait::st", "A0 fence + arrive",
+         "issuer tcgen05.fence::after", "issuer MMA issue (elected lane)", "issuer commits (elected lane)", "issuer elect block + syncwarp"]
 print(f"kernel {ms:.3f} ms, {nch} chunks per CTA, {ms * 1e-3 * 1.965e9 / nch:.0f} clk per chunk at 1965 MHz")
 for n, c in zip(names, list(buf)):
     print(f"  {n:32s} {c:12d} clk = {c / nch:8.1f} per chunk of the CTA")

@@ -707,7 +707,7 @@ void build_gen_plan(int L, int num_sms, const HostPlan &hp, HostPlanG &hg, int f
             segs += (pad16(p.rows) + 255) / 256;
             chains += p.count;
         }
-        return ntile * (cols + 32 * (int)st.size()) <= 512 && (int)st.size() <= G_PANELS && segs <= G_SEGS && 2 * chains <= G_TASKS;
+        return ntile * (cols + g_aslots(ntile) * 16 * (int)st.size()) <= 512 && (int)st.size() <= G_PANELS && segs <= G_SEGS && 2 * chains <= G_TASKS;
     };
     auto pack = [&](double cap) {
         Sets sets;
@@ -807,7 +807,7 @@ void build_gen_plan(int L, int num_sms, const HostPlan &hp, HostPlanG &hg, int f
         T.npanel = (int)st.size();
         T.kind = groups[st[0].group].kind;
         T.lpar = (groups[st[0].group].m + groups[st[0].group].pz) & 1;
-        T.acol0 = 512 - ntile * 2 * 16 * T.npanel;
+        T.acol0 = 512 - ntile * g_aslots(ntile) * 16 * T.npanel;
         struct TaskC { int row0, len, rk, srow; };
         std::vector<TaskC> chains;
         int off = 0, soff = 0, gdo = 0;
@@ -879,7 +879,7 @@ void build_gen_plan(int L, int num_sms, const HostPlan &hp, HostPlanG &hg, int f
                     }
         }
         T.ntask = nt;
-        if (nt > G_TASKS || T.nseg > G_SEGS || ntile * (T.ncols + 32 * T.npanel) > 512) return;
+        if (nt > G_TASKS || T.nseg > G_SEGS || ntile * (T.ncols + g_aslots(ntile) * 16 * T.npanel) > 512) return;
     }
     for (const int2 &r : hg.colmap)
         if (r.x < 0) return;
@@ -1068,7 +1068,10 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
         const char *off2 = getenv("Z3D_GEN2");
         for (int ntile = 1; ntile <= 2; ++ntile) {
             if (off && atoi(off) == 0) break;
-            if (ntile == 2 && (!pl->gen || (off2 && atoi(off2) == 0))) break;
+            // two tiles per T block: correct and tested, but not faster yet (9.4 ms per 128 volumes against 2 x 3.7 ms at 128^3 /
+            // order 50: with twice the a-panel work per chunk the a-panel teams and the single issuing warp become the bottleneck) -
+            // opt-in with Z3D_GEN2=1
+            if (ntile == 2 && (!pl->gen || !(off2 && atoi(off2) != 0))) break;
             HostPlanG hg;
             build_gen_plan(order, prop.multiProcessorCount, hp, hg, force, ntile);
             if (!hg.ok) continue;
@@ -1081,7 +1084,8 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
             g.rk_bytes = hg.rk_entries * 16;
             g.off_rk = (G_OFF_GD + g.gd_bytes + 15) / 16 * 16;
             g.off_g = g.off_rk + g.rk_bytes;
-            g.off_t = (g.off_g + G_DG * g.gslot_bytes + 127) / 128 * 128;
+            g.off_f = (g.off_g + G_DG * g.gslot_bytes + 127) / 128 * 128;
+            g.off_t = (g.off_f + G_FOLD_BYTES + 127) / 128 * 128;
             g.dbg = 0;
             if (const char *e = getenv("Z3D_GEN_DBG")) g.dbg = atoi(e);
             g.nslots = std::min(G_NS_MAX, ((int)prop.sharedMemPerBlockOptin - g.off_t) / g.tslot_bytes);
@@ -1213,8 +1217,8 @@ extern "C" int z3d_gen_layout_tiles(int order, int num_sms, int ntile, int *out,
                 if (T.seg_panel[g] < 0 || T.seg_panel[g] >= T.npanel) ++bad;
                 cols += T.seg_cols[g];
             }
-            if (cols != T.ncols || ntile * (T.ncols + 32 * T.npanel) > 512 || T.npanel < 1 || T.npanel > G_PANELS || T.nseg > G_SEGS) ++bad;
-            if (T.ntask > G_TASKS || T.acol0 != 512 - ntile * 32 * T.npanel) ++bad;
+            if (cols != T.ncols || ntile * (T.ncols + g_aslots(ntile) * 16 * T.npanel) > 512 || T.npanel < 1 || T.npanel > G_PANELS || T.nseg > G_SEGS) ++bad;
+            if (T.ntask > G_TASKS || T.acol0 != 512 - ntile * g_aslots(ntile) * 16 * T.npanel) ++bad;
             std::vector<char> covered(T.ncols, 0);   // every chain task writes its own rows, twice (two k halves)
             for (int t = 0; t < T.ntask; ++t) {
                 const int4 tk = hg.tasks[(size_t)i * G_TASKS + t];

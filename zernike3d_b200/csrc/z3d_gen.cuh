@@ -40,10 +40,18 @@ constexpr int G_TASKS = 256;       // T chain tasks (chain, k half) per column s
 #define G_DG_ 12
 #endif
 constexpr int G_NSEEDW = G_NSEEDW_;        // seed warps
-constexpr int G_NAT = 2;           // a-panel teams = a-panel slots in tensor memory
+constexpr int G_NAT = 2;           // a-panel teams
+#ifndef G_ASLOTS_
+#define G_ASLOTS_ 2
+#endif
+constexpr int G_ASLOTS = G_ASLOTS_;  // a-panel slots (chunks in flight) in tensor memory with one tile per T block (two tiles: 2), a multiple of G_NAT
+__host__ __device__ constexpr int g_aslots(int ntile) { return ntile == 1 ? G_ASLOTS : 2; }
+static_assert(G_ASLOTS % G_NAT == 0 && G_ASLOTS <= 4, "a-panel slots");
 constexpr int G_NTT = 4;           // T teams
 constexpr int G_DG = G_DG_;            // depth of the geometry / seed ring
 constexpr int G_NS_MAX = 8;        // depth of the T ring at most
+constexpr int G_FD = 4;            // depth of every a-panel warp's private fold ring (steps of 2 KB: 32 rows x (set A | set B) x 8 voxels)
+constexpr int G_FOLD_BYTES = 4 * G_NAT * G_FD * 2048 + 4 * G_NAT * G_FD * 8;   // the rings of the 8 a-panel warps + one mbarrier per slot
 // A parity wait is only meaningful when the waiter knows the barrier is at most one phase behind: the previous user of a ring
 // slot must be the SAME agent (warp / team), whose own progress then proves the earlier phase complete.  Chunk t is handled by
 // seed warp t % G_NSEEDW, a-panel team t % G_NAT and T team t % G_NTT and uses geometry slot t % G_DG, so G_DG must be a common
@@ -55,7 +63,7 @@ static_assert(G_DG % G_NSEEDW == 0 && G_DG % G_NAT == 0 && G_DG % G_NTT == 0, "g
 #endif
 constexpr int G_NISS = G_NISS_;           // issuing warps, one per scheduler (SM sub-partition = warp % 4): warp w issues the segments g = w mod 4
 constexpr int G_WARP_SEED0 = G_NISS;
-constexpr int G_WARP_A0 = G_NISS == 1 ? 4 : 8;
+constexpr int G_WARP_A0 = (G_NISS + G_NSEEDW + 3) / 4 * 4;
 constexpr int G_WARP_T0 = G_WARP_A0 + 4 * G_NAT;
 constexpr int G_NWARP = G_WARP_T0 + 4 * G_NTT;     // 32
 constexpr int GNT = G_NWARP * 32;                  // 1024 threads
@@ -91,6 +99,7 @@ struct DevPlanG {
     int gslot_bytes;               // seeds of the set with the most (panel, l) rows + r^2 + trig
     int gd_bytes, rk_bytes;        // shared-memory copies of the coefficient tables
     int off_rk, off_g, off_t;      // byte offsets in dynamic shared memory
+    int off_f;                     // the a-panel warps' fold rings (G_FOLD_BYTES)
     int dbg;                       // developer switches (-DZ3D_GEN_DEBUG builds only)
     const GenTabs *tabs;           // [nsets]
     const int4 *tasks;             // [nsets][G_TASKS]  (first column, length, index in the radial table, seed row | k half << 16)
@@ -99,13 +108,35 @@ struct DevPlanG {
     const double *side;            // [dim]
 };
 
+// Producer-side wait.  A failed mbarrier.try_wait comes back after ~100 clk whatever suspend-time hint it is given, so a waiting
+// warp executes a 7-instruction loop ten times per microsecond; with six of the seven warps of a scheduler waiting most of the time
+// (ncu: nine of ten executed instructions of the kernel were these loops) the warp that has work - above all the single issuing
+// warp - gets a fraction of its scheduler's issue slots.  Producers therefore SLEEP between polls (G_SLEEP_NS; their rings are
+// deep enough to absorb the wake-up latency); only the issuing warp spins.
+#ifndef G_SLEEP_NS
+#define G_SLEEP_NS 128
+#endif
+__device__ __forceinline__ void g_wait_relaxed(unsigned mbar, unsigned parity) {
+#pragma unroll 1
+    for (int it = 0; it < (1 << 24); ++it) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (ok) return;
+#if G_SLEEP_NS > 0
+        __nanosleep(G_SLEEP_NS);
+#endif
+    }
+    __trap();
+}
+
 #ifdef Z3D_GEN_TIMING
 // developer instrumentation: clocks spent per role and wait reason, CTA 0 only (z3d_debug_gen)
 __device__ long long g_gdbg[32];
 #define GT_T(var) const long long var = clock64()
 #define GT_ADD(slot, t0, t1) do { if (blockIdx.y * gridDim.x + blockIdx.x == GT_BLOCK && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&g_gdbg[slot], (unsigned long long)((t1) - (t0))); } while (0)
 #ifndef GT_BLOCK
-#define GT_BLOCK 0
+#define GT_BLOCK P.dbg   // the CTA to time: Z3D_GEN_DBG=<set * splits + split>
 #endif
 #else
 #define GT_T(var)
@@ -141,7 +172,7 @@ __device__ __forceinline__ void g_wait_dbg(unsigned mbar, unsigned parity, int i
 #define GD_SLEEP(bit)
 #define GD_FLUSHSLEEP false
 #define GW(bar, par, id, t) mbar_wait(bar, par)
-#define GWR(bar, par, id, t) mbar_wait_relaxed(bar, par)
+#define GWR(bar, par, id, t) g_wait_relaxed(bar, par)
 #endif
 
 // ---- tensor-memory helpers -------------------------------------------------------------------------------------------
@@ -214,6 +245,7 @@ __device__ __forceinline__ float4 ldg_stream4(const float *p) {  // read-once da
 // one read-back event of a producer warp (see s_flush)
 __device__ __forceinline__ void g_flush_event(unsigned tmem, int ncols, float *out, bool &had, unsigned drained, unsigned flushed, int &nev,
                                               bool last, bool dbg_sleep = false) {
+    g_wait_relaxed(drained, nev & 1);   // (s_flush's own wait then succeeds at once)
     s_flush<G_WARP_A0>(tmem, ncols, out, had, drained, nev & 1, dbg_sleep);
     had = true;
     if (!last) {
@@ -253,6 +285,7 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
     for (int i = tid; i < P.gd_bytes / 8; i += GNT) gds[i] = P.gd[(size_t)set * (P.gd_bytes / 8) + i];
     __syncthreads();
     const int ncols = T.ncols, nseg = T.nseg, npanel = T.npanel;
+    constexpr int NCS = g_aslots(NTILE);   // chunk t uses a-panel slot t % NCS
     const int nactive = min(nseg, G_NISS);   // issuing warps that own a segment
     for (int i = tid; i < P.rk_bytes / 16; i += GNT) rks[i] = P.rk[(size_t)T.lpar * (P.rk_bytes / 16) + i];
     if (tid == 0) {
@@ -268,6 +301,8 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(afull0 + 8 * i));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(afree0 + 8 * i), "r"(nactive));
         }
+        for (int i = 0; i < 4 * G_NAT * G_FD; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(smem + P.off_f + 4 * G_NAT * G_FD * 2048) + 8 * i));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(drained), "r"(nactive));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(flushed), "r"(S_NPW));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -325,7 +360,7 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
                     to_event = BFLUSH_CHUNKS;
                 }
                 GT_T(i1);
-                const int as = t & 1;
+                const int as = t % NCS;
                 GW(tfull0 + 8 * ts, tuse & 1, 2, t);
                 GT_T(i2);
                 GT_T(i3);
@@ -333,11 +368,12 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
 #pragma unroll
                 for (int tile = 0; tile < NTILE; ++tile) {
                     GT_T(j0);
-                    GW(afull0 + 8 * (as * NTILE + tile), (unsigned)(t >> 1) & 1, 3, t);
+                    GW(afull0 + 8 * (as * NTILE + tile), (unsigned)(t / NCS) & 1, 3, t);
                     GD_SLEEP(4);
                     GT_T(j1);
                     if (wi == 0) GT_ADD(2, j0, j1);
                     tc_fence_after();
+                    GT_T(k0);
                     if (elect_one()) {
                         const unsigned a = a0 + (unsigned)((as * NTILE + tile) * np16);
 #pragma unroll
@@ -345,24 +381,35 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
 #ifdef Z3D_GEN_DEBUG
                             if (P.dbg & 16384) continue;
 #endif
-                            if (sg[q].w >= 0) {
-                                const unsigned long long b = dhi | (unsigned long long)(dlo + (unsigned)sg[q].z);
-                                const unsigned d = tmem + (unsigned)(tile * ncols) + (unsigned)sg[q].z, ah = a + (unsigned)sg[q].y;
+                            const int4 sq = sg[q];
+                            if (sq.w >= 0) {
+                                const unsigned long long b = dhi | (unsigned long long)(dlo + (unsigned)sq.z);
+                                const unsigned d = tmem + (unsigned)(tile * ncols) + (unsigned)sq.z, ah = a + (unsigned)sq.y;
 #ifdef Z3D_GEN_DEBUG
-                                if (P.dbg & 2048) { umma_tf32_ts(d, ah, b, (unsigned)sg[q].x, since > 0 ? 1u : 0u); continue; }
+                                if (P.dbg & 2048) { umma_tf32_ts(d, ah, b, (unsigned)sq.x, since > 0 ? 1u : 0u); continue; }
 #endif
-                                umma_tf32_ts(d, ah, b + lo_t, (unsigned)sg[q].x, since > 0 ? 1u : 0u);  // small terms first
-                                umma_tf32_ts(d, ah + 8, b, (unsigned)sg[q].x, 1u);
-                                umma_tf32_ts(d, ah, b, (unsigned)sg[q].x, 1u);
+                                umma_tf32_ts(d, ah, b + lo_t, (unsigned)sq.x, since > 0 ? 1u : 0u);  // small terms first
+                                umma_tf32_ts(d, ah + 8, b, (unsigned)sq.x, 1u);
+                                umma_tf32_ts(d, ah, b, (unsigned)sq.x, 1u);
                             }
                         }
-                        umma_commit(afree0 + 8 * (as * NTILE + tile));
+                        // ONE commit per chunk: tcgen05.commit holds the issuing thread for ~420 clk (measured: the kernel stripped of
+                        // all work spent 845 clk per chunk in this block with two commits, 1 260 with three), so the T slot and the
+                        // a-panel slot are released by the same mbarrier - the a-panel team waits on the T ring's barrier of its
+                        // slot's previous chunk
+                        GT_T(k1);
                         if (tile == NTILE - 1) {
                             umma_commit(tfree0 + 8 * ts);
                             if (to_event == 1 || t == nchunk - 1) umma_commit(drained);  // a read-back follows this chunk
                         }
+                        GT_T(k2);
+#ifdef Z3D_GEN_TIMING
+                        if (wi == 0 && bid == GT_BLOCK) { atomicAdd((unsigned long long *)&g_gdbg[18], (unsigned long long)(k1 - k0)); atomicAdd((unsigned long long *)&g_gdbg[19], (unsigned long long)(k2 - k1)); }
+#endif
                     }
                     __syncwarp();
+                    GT_T(k3);
+                    if (wi == 0) { GT_ADD(17, j1, k0); GT_ADD(20, k0, k3); }
                 }
                 GT_T(i4);
                 if (wi == 0) GT_ADD(3, i3, i4);
@@ -438,7 +485,7 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
             const float r2 = (float)(rho2 + zz), z4 = (float)(4.0 * zz), r4 = r2 * r2;
             const int gs = t % G_DG;
             GT_T(s0);
-            if (t >= G_DG) GW(gfree0 + 8 * gs, (unsigned)(t / G_DG - 1) & 1, 4, t);
+            if (t >= G_DG) GWR(gfree0 + 8 * gs, (unsigned)(t / G_DG - 1) & 1, 4, t);
             GD_SLEEP(8);
             GT_T(s1);
             float *slot = reinterpret_cast<float *>(gring + (size_t)gs * P.gslot_bytes);
@@ -498,48 +545,64 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
         const int team = (warp - G_WARP_A0) >> 2, quarter = warp & 3;
         const int row = quarter * 32 + lane, reim = row >> 6, b = row & 63;
         const float sign = reim ? -1.0f : 1.0f;  // im rows are negated
-        const unsigned arow = tmem + ((unsigned)(32 * quarter) << 16) + (unsigned)T.acol0 + (unsigned)(team * NTILE * np16);
-        const float *fbase = Ft + (size_t)T.kind * (S_FK_BYTES / 4) + (size_t)(reim * SNV + b) * KC;
+        const unsigned arow0 = tmem + ((unsigned)(32 * quarter) << 16) + (unsigned)T.acol0;
         bool had = false;
         int nev = 0;
-        // The folds come from global memory (DRAM: a tile's folds are 0.5 GB) straight into registers, a whole round of the team
-        // ahead: with two tiles buffer i holds tile i's folds and is reloaded with the team's next chunk as soon as its panels are
-        // built; with one tile the buffers alternate between the team's chunks.  (One step ahead left a DRAM latency on the team's
-        // critical path: the kernel without any work - barriers and these loads only - took 960 clk per chunk, 1 480 with two tiles.)
-        struct Fold { float4 a0, a1, b0, b1; };
-        Fold F[2];
-        auto ldf = [&](Fold &f, int t, int tile) {
-            const float *q = fbase + (size_t)tile * tile_stride + (size_t)(cbeg + t) * (4 * S_FK_BYTES / 4);
-            f.a0 = ldg_stream4(q); f.a1 = ldg_stream4(q + 4);
-            f.b0 = ldg_stream4(q + 2 * SNV * KC); f.b1 = ldg_stream4(q + 2 * SNV * KC + 4);
+        // The folds of a warp's 32 rows (2 x 1 KB per (chunk, tile) step) come through the warp's PRIVATE ring of G_FD slots in shared
+        // memory: lane 0 issues two bulk copies per step, G_FD steps ahead, completion counted on the slot's mbarrier; nobody else
+        // touches the ring, so there is no consumer barrier - the warp re-arms a slot itself once its lanes have read it.  (Loaded
+        // into registers one step ahead, a DRAM round trip sat on the team's critical path at every step - a tile's folds are
+        // 0.5 GB - and two steps ahead the registers spilled.)
+        const int aw = warp - G_WARP_A0;
+        const float *fring = reinterpret_cast<const float *>(smem + P.off_f + (size_t)aw * (G_FD * 2048));
+        const unsigned fring_s = smem_u32(fring), fbar0 = smem_u32(smem + P.off_f + 4 * G_NAT * G_FD * 2048) + (unsigned)(aw * G_FD * 8);
+        const float *fwarp = Ft + (size_t)T.kind * (S_FK_BYTES / 4) + (size_t)(reim * SNV + (b & 32)) * KC;   // the warp's 32 rows: 1 KB
+        const int npos = nchunk > team ? ((nchunk - team + G_NAT - 1) / G_NAT) * NTILE : 0;
+        auto fissue = [&](int p) {   // lane 0 only
+            const int t = team + G_NAT * (p / NTILE), tile = p % NTILE, sl = p % G_FD;
+            const float *q = fwarp + (size_t)tile * tile_stride + (size_t)(cbeg + t) * (4 * S_FK_BYTES / 4);
+            mbar_expect_tx(fbar0 + 8 * sl, 2048);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 1024, [%2];"
+                         ::"r"(fring_s + (unsigned)(sl * 2048)), "l"(q), "r"(fbar0 + 8 * sl) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 1024, [%2];"
+                         ::"r"(fring_s + (unsigned)(sl * 2048 + 1024)), "l"(q + 2 * SNV * KC), "r"(fbar0 + 8 * sl) : "memory");
         };
-        constexpr int NU = NTILE == 1 ? 2 : 1;   // chunks per trip of the outer loop (static buffer indices)
-        if (team < nchunk) ldf(F[0], team, 0);
-        if (NTILE == 2) { if (team < nchunk) ldf(F[1], team, 1); }
-        else if (team + G_NAT < nchunk) ldf(F[1], team + G_NAT, 0);
-        for (int t0 = team; t0 < nchunk; t0 += NU * G_NAT) {
-#pragma unroll
-          for (int u = 0; u < NU; ++u) {
-            const int t = t0 + u * G_NAT;
-            if (t >= nchunk) break;
+        if (lane == 0)
+            for (int p = 0; p < G_FD && p < npos; ++p) fissue(p);
+        int p = 0;
+        for (int t = team; t < nchunk; t += G_NAT) {
             int pos, len;
             s_interval(t, ev0, nchunk, pos, len);
             const float sg = sign * (1.0f + BTRUNC_PER_MMA * (float)(3 * (len - 1 - pos) + 1));  // truncation pre-compensation
             const int gs = t % G_DG;
             const float *slot = reinterpret_cast<const float *>(gring + (size_t)gs * P.gslot_bytes);
+            const int cs = t % NCS;
+            const unsigned arow = arow0 + (unsigned)(cs * NTILE * np16);
             GT_T(a0);
             GWR(gfull0 + 8 * gs, (unsigned)(t / G_DG) & 1, 5, t);
             GT_T(a1);
-            GT_T(a2);
 #pragma unroll
-            for (int tile = 0; tile < NTILE; ++tile) {
-                if (t >= G_NAT) GWR(afree0 + 8 * (team * NTILE + tile), (unsigned)(t / G_NAT - 1) & 1, 6, t);  // the slot's previous MMAs retired
+            for (int tile = 0; tile < NTILE; ++tile, ++p) {
+                GT_T(b0);
+#ifdef Z3D_GEN_ABL
+                if (!(P.dbg & 65536))   // timing ablation: an a-panel ring of unbounded depth
+#endif
+                if (t >= NCS && tile == 0) GWR(tfree0 + 8 * ((t - NCS) % NS), (unsigned)((t - NCS) / NS) & 1, 6, t);  // the slot's previous MMAs (chunk t - NCS) retired
                 GD_SLEEP(32);
+                const int sl = p % G_FD;
+                GWR(fbar0 + 8 * sl, (unsigned)(p / G_FD) & 1, 9, t);   // this step's folds have landed
+                GT_T(b1);
+                if (warp == G_WARP_A0) GT_ADD(7, b0, b1);
                 tc_fence_after();
-                const int bi = NTILE == 1 ? u : tile;
-                const Fold &c = F[bi];
-                const float fa[8] = {c.a0.x, c.a0.y, c.a0.z, c.a0.w, c.a1.x, c.a1.y, c.a1.z, c.a1.w};
-                const float fb[8] = {c.b0.x, c.b0.y, c.b0.z, c.b0.w, c.b1.x, c.b1.y, c.b1.z, c.b1.w};
+                const float4 *fq = reinterpret_cast<const float4 *>(fring + sl * 512) + lane * 2;
+                const float4 fa0 = fq[0], fa1 = fq[1], fb0 = fq[64], fb1 = fq[65];
+                const float fa[8] = {fa0.x, fa0.y, fa0.z, fa0.w, fa1.x, fa1.y, fa1.z, fa1.w};
+                const float fb[8] = {fb0.x, fb0.y, fb0.z, fb0.w, fb1.x, fb1.y, fb1.z, fb1.w};
+                __syncwarp();
+                if (lane == 0 && p + G_FD < npos) {   // every lane has its folds in registers: refill the slot
+                    fence_async_smem();
+                    fissue(p + G_FD);
+                }
 #ifdef Z3D_GEN_DEBUG
                 if (!(P.dbg & 4096))
 #endif
@@ -551,21 +614,23 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
                     tmem_st8(arow + (unsigned)(tile * np16 + j * 16), hi);
                     tmem_st8(arow + (unsigned)(tile * np16 + j * 16 + 8), lo);
                 }
-                if (t + NU * G_NAT < nchunk) ldf(F[bi], t + NU * G_NAT, tile);   // in flight for a whole round of the team
+                GT_T(c0);
                 tmem_st_wait();
+                GT_T(c1);
                 GD_SLEEP(64);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(afull0 + 8 * (team * NTILE + tile));
+                    mbar_arrive(afull0 + 8 * (cs * NTILE + tile));
                     if (tile == NTILE - 1) mbar_arrive(gfree0 + 8 * gs);
                 }
+                GT_T(c2);
+                if (warp == G_WARP_A0) { GT_ADD(14, b1, c0); GT_ADD(15, c0, c1); GT_ADD(16, c1, c2); }
             }
             GT_T(a3);
             while (nev < nregular && ev0 + nev * BFLUSH_CHUNKS <= t) g_flush_event(tmem, NTILE * ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
             GT_T(a4);
-            if (warp == G_WARP_A0) { GT_ADD(6, a0, a1); GT_ADD(7, a1, a2); GT_ADD(8, a2, a3); GT_ADD(9, a3, a4); }
-          }
+            if (warp == G_WARP_A0) { GT_ADD(6, a0, a1); GT_ADD(8, a1, a3); GT_ADD(9, a3, a4); }
         }
         while (nev < nregular) g_flush_event(tmem, NTILE * ncols, out, had, drained, flushed, nev, false, GD_FLUSHSLEEP);
         g_flush_event(tmem, NTILE * ncols, out, had, drained, flushed, nev, true, GD_FLUSHSLEEP);
