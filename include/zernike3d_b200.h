@@ -126,9 +126,10 @@ int z3d_decompose_part(const z3d_plan *plan, const float *d_vol, int batch, int 
  * counterpart (the reference has no multi-GPU path).  z3d_comm_create allocates this rank's peer-visible buffer and
  * returns its 64-byte CUDA IPC handle; the ranks exchange the handles out of band (torch.distributed) and call
  * z3d_comm_connect with all of them.  z3d_decompose_allreduce then runs the rank's share of the work list
- * (as z3d_decompose_part(rank, world)) followed by ONE kernel that reduces the rank's partials, publishes them in the
- * peer-mapped buffer and completes a one-shot all-gather + rank-ordered sum over NVLink peer loads: every rank ends
- * with the full, bit-identical moments, without an NCCL call on the data path.  d_vol must hold the whole volume(s).
+ * (as z3d_decompose_part(rank, world)) followed by ONE kernel that reduces the rank's partials, pushes them into every
+ * rank's peer-mapped buffer with posted NVLink stores (block by block, one flag per block and source rank) and sums the
+ * rows that arrived in its own buffer in rank order: a one-shot all-gather + ordered sum, every rank ends with the full,
+ * bit-identical moments, without an NCCL call on the data path.  d_vol must hold the whole volume(s).
  * z3d_comm_error returns 1 if an exchange timed out (~2 s; the affected results are NaN) - it never hangs. */
 typedef struct z3d_comm z3d_comm;
 int z3d_comm_create(const z3d_plan *plan, int batch_max, z3d_comm **out, unsigned char *handle64);

@@ -47,6 +47,20 @@ mine = P.decompose(torch.from_numpy(np.stack(allv[lo:hi])).cuda())
 ok &= bool(torch.equal(torch.view_as_real(got[lo:hi]), torch.view_as_real(mine)))
 other = (lo + count // 2) % count                                   # a volume another rank decomposed
 ok &= rel(got[other].cpu().numpy(), P.decompose(torch.from_numpy(allv[other]).cuda()).cpu().numpy()) < 2e-6
+# latency of one volume spread over the ranks: fused push exchange vs compute + NCCL all-reduce (device time, max over ranks)
+def _ms(fn, reps=50):
+    for _ in range(5): fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier(); torch.cuda.synchronize(); e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+one = vols[:1].contiguous()
+t_fused, t_nccl = _ms(lambda: P.decompose_allreduce(one, comm)), _ms(lambda: zdist.decompose_work_sharded(P.decompose, one))
+t_part = _ms(lambda: P.decompose(one, part=(rank, world)))
+if rank == 0:
+    print(f"P2P_TIME world={world} order={order} dim={dim}: fused {t_fused:.4f} ms, compute + NCCL {t_nccl:.4f} ms, compute share alone {t_part:.4f} ms")
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -1909,7 +1909,6 @@ struct z3d_comm {
     float *local = nullptr;
     PeerBufs peers{};
     bool opened[MAX_RANKS] = {};
-    unsigned *d_done = nullptr;
     int *d_err = nullptr;
     unsigned epoch = 0;
 };
@@ -1920,11 +1919,9 @@ extern "C" int z3d_comm_create(const z3d_plan *pl, int batch_max, z3d_comm **out
     z3d_comm *c = new z3d_comm();
     c->device = pl->device;
     c->max_elems = (size_t)batch_max * 2 * pl->nmom;
-    c->bytes = 2 * c->max_elems * sizeof(float) + 2 * MAX_RANKS * sizeof(unsigned);
+    c->bytes = comm_bytes(c->max_elems);
     CUDA_TRY(cudaMalloc((void **)&c->local, c->bytes));
     CUDA_TRY(cudaMemset(c->local, 0, c->bytes));
-    CUDA_TRY(cudaMalloc((void **)&c->d_done, sizeof(unsigned)));
-    CUDA_TRY(cudaMemset(c->d_done, 0, sizeof(unsigned)));
     CUDA_TRY(cudaMalloc((void **)&c->d_err, sizeof(int)));
     CUDA_TRY(cudaMemset(c->d_err, 0, sizeof(int)));
     cudaIpcMemHandle_t h;
@@ -1964,7 +1961,6 @@ extern "C" int z3d_comm_destroy(z3d_comm *c) {
     for (int r = 0; r < MAX_RANKS; ++r)
         if (c->opened[r]) cudaIpcCloseMemHandle(c->peers.data[r]);
     if (c->local) cudaFree(c->local);
-    if (c->d_done) cudaFree(c->d_done);
     if (c->d_err) cudaFree(c->d_err);
     delete c;
     return Z3D_OK;
@@ -1989,8 +1985,9 @@ extern "C" int z3d_decompose_allreduce(const z3d_plan *pl, z3d_comm *c, const fl
     for (int b0 = 0; b0 < batch; b0 += grp) {
         const int nb = std::min(grp, batch - b0);
         dim3 g((2 * pl->nmom + 255) / 256, nb);
-        // every block of the exchange kernel waits for the peers, so all of them must be co-resident
-        if ((int)(g.x * g.y) > pl->num_sms * 4)
+        // a block of the exchange kernel waits for its counterpart blocks on the peers: keep the whole grid co-resident so that
+        // progress never depends on the order in which the ranks' block schedulers hand out blocks; one flag per block
+        if ((int)(g.x * g.y) > std::min(pl->num_sms * 4, P2P_MAX_BLOCKS))
             return fail(Z3D_ERR_UNSUPPORTED, "z3d_decompose_allreduce: order %d too large for the one-shot exchange (use "
                                              "z3d_decompose_part + a library all-reduce)", pl->order);
         const float *vol = d_vol + (size_t)b0 * N3;
@@ -2003,7 +2000,7 @@ extern "C" int z3d_decompose_allreduce(const z3d_plan *pl, z3d_comm *c, const fl
         if (pl->profiling && b0 == 0) CUDA_TRY(cudaEventRecord(pl->ev_k1, st));
         c->epoch += 1;
         k_reduce_allreduce_p2p<<<g, 256, 0, st>>>(partial, pl->d_src, pl->d_scale, pl->nmom, pl->npass, pl->nsplit, nb, c->peers,
-                                                  c->rank, c->world, c->max_elems, c->epoch, c->d_done, c->d_err,
+                                                  c->rank, c->world, c->max_elems, c->epoch, c->d_err,
                                                   d_moments + (size_t)b0 * 2 * pl->nmom);
         CUDA_TRY(cudaGetLastError());
         g_launches += 2;

@@ -61,9 +61,16 @@ static_assert(G_DG % G_NSEEDW == 0 && G_DG % G_NAT == 0 && G_DG % G_NTT == 0, "g
 #ifndef G_NISS_
 #define G_NISS_ 1
 #endif
-constexpr int G_NISS = G_NISS_;           // issuing warps, one per scheduler (SM sub-partition = warp % 4): warp w issues the segments g = w mod 4
-constexpr int G_WARP_SEED0 = G_NISS;
-constexpr int G_WARP_A0 = (G_NISS + G_NSEEDW + 3) / 4 * 4;
+constexpr int G_NISS = G_NISS_;           // issuing warps by SEGMENT, one per scheduler (SM sub-partition = warp % 4): warp w issues the segments g = w mod G_NISS
+#ifndef G_NALT_
+#define G_NALT_ 1
+#endif
+constexpr int G_NALT = G_NALT_;           // issuing warps by CHUNK: warp a issues the chunks t = a mod G_NALT (2: measured slower, see the issuing role below)
+static_assert(G_NISS == 1 || G_NALT == 1, "split the issue work by segment or by chunk, not both");
+static_assert(G_NALT == 1 || G_NALT == 2, "alternating issuers");
+constexpr int G_NISSW = G_NISS * G_NALT;  // issuing warps in all
+constexpr int G_WARP_SEED0 = G_NISSW;
+constexpr int G_WARP_A0 = (G_NISSW + G_NSEEDW + 3) / 4 * 4;
 constexpr int G_WARP_T0 = G_WARP_A0 + 4 * G_NAT;
 constexpr int G_NWARP = G_WARP_T0 + 4 * G_NTT;     // 32
 constexpr int GNT = G_NWARP * 32;                  // 1024 threads
@@ -278,8 +285,9 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
     // is free again as soon as its own MMAs have retired)
     const unsigned gfull0 = smem_u32(bars), gfree0 = gfull0 + 8 * G_DG, tfull0 = gfree0 + 8 * G_DG, tfree0 = tfull0 + 8 * G_NS_MAX,
                    afull0 = tfree0 + 8 * G_NS_MAX, afree0 = afull0 + 8 * G_NAT * 2, drained = afree0 + 8 * G_NAT * 2, flushed = drained + 8;
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + G_OFF_BAR + 8 * (2 * G_DG + 2 * G_NS_MAX + 4 * G_NAT + 2));
-    static_assert(8 * (2 * G_DG + 2 * G_NS_MAX + 4 * G_NAT + 2) + 4 <= G_OFF_GD - G_OFF_BAR, "barrier block");
+    const unsigned issued0 = flushed + 8;   // issued[a]: issuing warp a has handed its chunk's MMAs to the tensor core (chunk order between the warps)
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + G_OFF_BAR + 8 * (2 * G_DG + 2 * G_NS_MAX + 4 * G_NAT + 2 + 2));
+    static_assert(8 * (2 * G_DG + 2 * G_NS_MAX + 4 * G_NAT + 2 + 2) + 4 <= G_OFF_GD - G_OFF_BAR, "barrier block");
     for (int i = tid; i < (int)(sizeof(GenTabs) / 4); i += GNT)
         reinterpret_cast<int *>(smem + G_OFF_TABS)[i] = reinterpret_cast<const int *>(P.tabs + set)[i];
     for (int i = tid; i < P.gd_bytes / 8; i += GNT) gds[i] = P.gd[(size_t)set * (P.gd_bytes / 8) + i];
@@ -303,8 +311,10 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
         }
         for (int i = 0; i < 4 * G_NAT * G_FD; ++i)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(smem + P.off_f + 4 * G_NAT * G_FD * 2048) + 8 * i));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(drained), "r"(nactive));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(drained), "r"(nactive * G_NALT));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(flushed), "r"(S_NPW));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(issued0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(issued0 + 8));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -333,12 +343,16 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
 
     if (nchunk == 0) {
         for (int i = tid; i < NTILE * ncols * BTM; i += GNT) out[i] = 0.0f;  // the reduction reads every split
-    } else if (warp < G_NISS) {
-        // ---- issuing warps: warp w owns the segments g = w, w + G_NISS, .. (different accumulator columns: no ordering between the
-        // warps' MMAs is needed); a warp without a segment has nothing to do.  The serial per-chunk path of an issuing warp (two
-        // waits, the operand set-up of its MMAs - every UTCHMMA operand has to be moved into uniform registers -, two commits) is
-        // what bounds the kernel's period: with one issuing warp for all segments it was ~50 clk per MMA, ~1000 clk per chunk.
-        const int wi = warp;
+    } else if (warp < G_NISSW) {
+        // ---- issuing warp: ONE converged warp issues all MMAs of a chunk (elect.sync), then one commit.
+        // Tried (compile with -DG_NALT_=2): two warps that ALTERNATE over the chunks - warp a issues the chunks t = a mod 2 and does
+        // its waits, tcgen05.fence and commit while the other warp's MMAs execute; the chunks enter the tensor core in order through
+        // the hand-over barriers `issued[a]` (a warp arrives after its chunk's last MMA instruction and waits for the other's before
+        // its next chunk's first).  Bit-identical results, but 4.24 ms against 3.73 ms per 64 x 128^3 tile: what the single issuing
+        // warp loses is mostly starvation (read-back bubbles, T / a-panel hand-overs), not its own bookkeeping, and the second
+        // spinning warp costs the producers issue slots.
+        // (G_NISS > 1, the earlier scheme: warp w owns the segments g = w, w + G_NISS, .. - different accumulator columns, no order.)
+        const int wi = warp / G_NALT, alt = warp % G_NALT;
         if (wi < nactive) {
             int4 sg[G_SEG_PER_ISS];
 #pragma unroll
@@ -347,32 +361,47 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
             const unsigned long long dhi = ((unsigned long long)(128 >> 4) << 32) | (1ull << 46) | ((unsigned long long)ncols << 16);  // SBO 128 B, LBO = ncols * 16 B, version 1
             const unsigned lo_t = (unsigned)(2 * ncols), step = (unsigned)(P.tslot_bytes >> 4);
             const unsigned a0 = tmem + (unsigned)T.acol0;
-            unsigned dlo = dlo0;
-            int ts = 0, since = 0, to_event = ev0;
+            const unsigned my_issued = issued0 + 8 * alt, other_issued = issued0 + 8 * (alt ^ 1);
+            int ts = alt % NS;
             unsigned tuse = 0, nev = 0;
-            for (int t = 0; t < nchunk; ++t) {
-                GT_T(i0);
-                if (to_event == 0) {  // the accumulators have been read back -> overwrite
-                    GW(flushed, nev & 1, 1, t);
+            int next_ev = ev0;        // the next read-back event lies in front of this chunk
+            unsigned mine = 0;        // chunks this warp has issued
+            auto cross_event = [&](bool wait) {   // pass the event in front of chunk next_ev (or the final one, next_ev >= nchunk)
+                const int before = min(next_ev, nchunk) - 1;   // the last chunk in front of the event
+                if (G_NALT > 1 && before % G_NALT != alt) {    // not mine: my own MMAs so far must have retired as well
+                    if (elect_one()) umma_commit(drained);
+                    __syncwarp();
+                }
+                if (wait) {
+                    GW(flushed, nev & 1, 1, next_ev);
                     GD_SLEEP(2);
-                    since = 0;
-                    ++nev;
-                    to_event = BFLUSH_CHUNKS;
+                }
+                ++nev;
+                next_ev += BFLUSH_CHUNKS;
+            };
+            for (int t = alt; t < nchunk; t += G_NALT) {
+                GT_T(i0);
+                bool first = t == 0;
+                if (next_ev <= t) {  // the accumulators have been read back -> overwrite
+                    first = next_ev == t;
+                    cross_event(true);
                 }
                 GT_T(i1);
                 const int as = t % NCS;
+                const unsigned dlo = dlo0 + (unsigned)ts * step;
                 GW(tfull0 + 8 * ts, tuse & 1, 2, t);
                 GT_T(i2);
                 GT_T(i3);
-                if (wi == 0) { GT_ADD(0, i0, i1); GT_ADD(1, i1, i2); }
+                if (warp == 0) { GT_ADD(0, i0, i1); GT_ADD(1, i1, i2); }
 #pragma unroll
                 for (int tile = 0; tile < NTILE; ++tile) {
                     GT_T(j0);
                     GW(afull0 + 8 * (as * NTILE + tile), (unsigned)(t / NCS) & 1, 3, t);
                     GD_SLEEP(4);
                     GT_T(j1);
-                    if (wi == 0) GT_ADD(2, j0, j1);
+                    if (warp == 0) GT_ADD(2, j0, j1);
                     tc_fence_after();
+                    if (G_NALT > 1 && tile == 0 && t > 0) GW(other_issued, (alt ? mine : mine - 1) & 1, 10, t);   // chunk t - 1 is in the queue
                     GT_T(k0);
                     if (elect_one()) {
                         const unsigned a = a0 + (unsigned)((as * NTILE + tile) * np16);
@@ -386,9 +415,9 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
                                 const unsigned long long b = dhi | (unsigned long long)(dlo + (unsigned)sq.z);
                                 const unsigned d = tmem + (unsigned)(tile * ncols) + (unsigned)sq.z, ah = a + (unsigned)sq.y;
 #ifdef Z3D_GEN_DEBUG
-                                if (P.dbg & 2048) { umma_tf32_ts(d, ah, b, (unsigned)sq.x, since > 0 ? 1u : 0u); continue; }
+                                if (P.dbg & 2048) { umma_tf32_ts(d, ah, b, (unsigned)sq.x, first ? 0u : 1u); continue; }
 #endif
-                                umma_tf32_ts(d, ah, b + lo_t, (unsigned)sq.x, since > 0 ? 1u : 0u);  // small terms first
+                                umma_tf32_ts(d, ah, b + lo_t, (unsigned)sq.x, first ? 0u : 1u);  // small terms first
                                 umma_tf32_ts(d, ah + 8, b, (unsigned)sq.x, 1u);
                                 umma_tf32_ts(d, ah, b, (unsigned)sq.x, 1u);
                             }
@@ -399,24 +428,28 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
                         // slot's previous chunk
                         GT_T(k1);
                         if (tile == NTILE - 1) {
+                            if (G_NALT > 1) mbar_arrive(my_issued);   // the other warp may issue chunk t + 1 while this one commits
                             umma_commit(tfree0 + 8 * ts);
-                            if (to_event == 1 || t == nchunk - 1) umma_commit(drained);  // a read-back follows this chunk
+                            if (t + 1 == next_ev || t == nchunk - 1) umma_commit(drained);  // a read-back follows this chunk
                         }
                         GT_T(k2);
 #ifdef Z3D_GEN_TIMING
-                        if (wi == 0 && bid == GT_BLOCK) { atomicAdd((unsigned long long *)&g_gdbg[18], (unsigned long long)(k1 - k0)); atomicAdd((unsigned long long *)&g_gdbg[19], (unsigned long long)(k2 - k1)); }
+                        if (warp == 0 && bid == GT_BLOCK) { atomicAdd((unsigned long long *)&g_gdbg[18], (unsigned long long)(k1 - k0)); atomicAdd((unsigned long long *)&g_gdbg[19], (unsigned long long)(k2 - k1)); }
 #endif
                     }
                     __syncwarp();
                     GT_T(k3);
-                    if (wi == 0) { GT_ADD(17, j1, k0); GT_ADD(20, k0, k3); }
+                    if (warp == 0) { GT_ADD(17, j1, k0); GT_ADD(20, k0, k3); }
                 }
                 GT_T(i4);
-                if (wi == 0) GT_ADD(3, i3, i4);
-                ++since;
-                --to_event;
-                dlo += step;
-                if (++ts == NS) { ts = 0; ++tuse; dlo = dlo0; }
+                if (warp == 0) GT_ADD(3, i3, i4);
+                ++mine;
+                ts += G_NALT;
+                if (ts >= NS) { ts -= NS; ++tuse; }
+            }
+            if (G_NALT > 1) {  // events behind this warp's last chunk: every issuing warp arrives on `drained` at every event
+                while (next_ev < nchunk) cross_event(true);
+                if ((nchunk - 1) % G_NALT != alt) cross_event(false);
             }
         }
     } else if (warp < G_WARP_SEED0 + G_NSEEDW) {

@@ -608,73 +608,87 @@ __global__ void k_reduce_moments(const float *__restrict__ partial, const int *_
 
 // Fused "reduce partials + all-reduce over NVLink peer memory" for the work-sharded analysis of ONE volume spread
 // over several GPUs (one process per GPU).  Every rank owns a communication buffer that all ranks have mapped
-// (CUDA IPC): [2 slots][max_elems] floats of data followed by [2 slots][MAX_RANKS] epoch flags.
-//   1. each thread reduces this rank's per-CTA partials for its elements (same arithmetic as k_reduce_moments) and
-//      writes them into the LOCAL buffer, slot = epoch & 1;
-//   2. the last block to finish publishes `epoch` into flag[slot][rank] of EVERY rank's buffer (system-scope release);
-//   3. all blocks wait until all ranks' epochs arrived in the local flags (acquire), then
-//   4. every thread sums its elements over the ranks in rank order through peer loads (L1-bypassing) and writes the
+// (CUDA IPC): [2 slots][MAX_RANKS source ranks][max_elems] floats of data, then [2 slots][MAX_RANKS][P2P_MAX_BLOCKS] epoch flags.
+// PUSH, block by block - no grid-wide step and no remote load anywhere:
+//   1. each thread reduces this rank's per-CTA partials for its element (same arithmetic as k_reduce_moments) and STORES the
+//      value into row `rank` of EVERY rank's buffer (posted NVLink writes, slot = epoch & 1);
+//   2. after the block barrier, thread r (< world) publishes `epoch` into flag[slot][rank][block] of rank r (system-scope
+//      release, cumulative over the block's stores through the barrier) - the `world` flag stores leave in parallel;
+//   3. thread r then waits for rank r's flag of THIS block in the local buffer (acquire; local memory polls), so a block
+//      only ever waits for its own counterpart blocks on the peers;
+//   4. every thread sums its element over the source rows in rank order from LOCAL memory (L1-bypassing loads) and writes the
 //      final moments: one-shot all-gather + ordered sum, bit-identical on all ranks, no NCCL call on the data path.
-// Two slots make back-to-back calls safe: a rank can be at most one call ahead of the slowest reader.
+// Two slots make back-to-back calls safe: a peer can only push epoch e + 2 into a slot after this rank has published all of its
+// epoch e + 1 flags, i.e. after its epoch e kernel (the slot's last reader) has completed.
+// (Round 1's version published once per rank from the last block to finish and pulled the peers' vectors through remote loads:
+// a grid-wide atomic, one thread storing 8 flags in sequence, and 8 dependent NVLink round trips per thread - 0.18-0.45 ms at
+// 8 GPUs depending on the node, against 0.145 ms for compute + NCCL.)
 constexpr int MAX_RANKS = 16;
+constexpr int P2P_MAX_BLOCKS = 1024;
 struct PeerBufs {
     float *data[MAX_RANKS];            // base of each rank's buffer (own included), device-accessible from this GPU
 };
-__device__ __forceinline__ unsigned *comm_flags(float *base, size_t max_elems) {
-    return reinterpret_cast<unsigned *>(base + 2 * max_elems);
+__host__ __device__ __forceinline__ size_t comm_bytes(size_t max_elems) {
+    return 2 * (size_t)MAX_RANKS * max_elems * sizeof(float) + 2 * (size_t)MAX_RANKS * P2P_MAX_BLOCKS * sizeof(unsigned);
 }
-__global__ void k_reduce_allreduce_p2p(const float *__restrict__ partial, const int *__restrict__ src,
-                                       const double *__restrict__ scale, int nmom, int npass, int nsplit, int batch,
-                                       PeerBufs peers, int rank, int world, size_t max_elems, unsigned epoch,
-                                       unsigned *done_counter, int *error_flag, float *__restrict__ moments) {
+__device__ __forceinline__ unsigned *comm_flags(float *base, size_t max_elems) {
+    return reinterpret_cast<unsigned *>(base + 2 * (size_t)MAX_RANKS * max_elems);
+}
+__global__ void __launch_bounds__(256)
+k_reduce_allreduce_p2p(const float *__restrict__ partial, const int *__restrict__ src,
+                       const double *__restrict__ scale, int nmom, int npass, int nsplit, int batch,
+                       PeerBufs peers, int rank, int world, size_t max_elems, unsigned epoch,
+                       int *error_flag, float *__restrict__ moments) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     const int slot = epoch & 1;
+    const int block = blockIdx.y * gridDim.x + blockIdx.x;
     const bool live = e < 2 * nmom && b < batch;
     const size_t idx = (size_t)b * 2 * nmom + e;
+    const size_t row = ((size_t)slot * MAX_RANKS + rank) * max_elems + idx;
     if (live) {
         const int s = src[e];
         const int pass = s / SLOT_WORDS, off = s % SLOT_WORDS;
         const float *p = partial + (((size_t)b * npass + pass) * nsplit) * SLOT_WORDS + off;
         double sum = 0.0;
         for (int sp = 0; sp < nsplit; ++sp) sum += (double)p[(size_t)sp * SLOT_WORDS];
-        peers.data[rank][(size_t)slot * max_elems + idx] = (float)(sum * scale[e >> 1]);
+        const float v = (float)(sum * scale[e >> 1]);
+        for (int r = 0; r < world; ++r) peers.data[r][row] = v;
     }
-    __threadfence_system();
     __syncthreads();
-    __shared__ bool ok;
-    if (threadIdx.x == 0) {
-        ok = true;
-        const unsigned nblocks = gridDim.x * gridDim.y;
-        if (atomicAdd(done_counter, 1u) == nblocks - 1) {  // last block of this rank: publish
-            *done_counter = 0;
-            __threadfence_system();
-            for (int r = 0; r < world; ++r) {
-                unsigned *f = comm_flags(peers.data[r], max_elems) + slot * MAX_RANKS + rank;
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
-            }
-        }
-        const unsigned *mine = comm_flags(peers.data[rank], max_elems) + slot * MAX_RANKS;
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    if ((int)threadIdx.x < world) {
+        const int r = threadIdx.x;
+        __threadfence_system();
+        unsigned *f = comm_flags(peers.data[r], max_elems) + ((size_t)slot * MAX_RANKS + rank) * P2P_MAX_BLOCKS + block;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+        const unsigned *mine = comm_flags(peers.data[rank], max_elems) + ((size_t)slot * MAX_RANKS + r) * P2P_MAX_BLOCKS + block;
         const long long t0 = clock64();
-        for (int r = 0; r < world; ++r) {
-            unsigned v;
-            do {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + r) : "memory");
-                if (v != epoch && clock64() - t0 > 4000000000LL) {  // ~2 s: a peer never arrived - fail, do not hang
-                    ok = false;
-                    atomicExch(error_flag, 1);
-                    break;
-                }
-            } while (v != epoch);
-        }
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if (v != epoch && clock64() - t0 > 4000000000LL) {  // ~2 s: a peer never arrived - fail, do not hang
+                atomicExch(&bad, 1);
+                atomicExch(error_flag, 1);
+                break;
+            }
+        } while (v != epoch);
     }
     __syncthreads();
     if (live) {
         float acc = 0.0f;
-        if (ok)
-            for (int r = 0; r < world; ++r) acc += __ldcv(peers.data[r] + (size_t)slot * max_elems + idx);
-        else
+        if (!bad) {
+            const float *mine = peers.data[rank] + (size_t)slot * MAX_RANKS * max_elems + idx;
+            float v[MAX_RANKS];
+#pragma unroll
+            for (int r = 0; r < MAX_RANKS; ++r) v[r] = r < world ? __ldcv(mine + (size_t)r * max_elems) : 0.0f;
+#pragma unroll
+            for (int r = 0; r < MAX_RANKS; ++r)
+                if (r < world) acc += v[r];
+        } else {
             acc = __int_as_float(0x7fc00000);  // NaN marks the failed exchange
+        }
         moments[idx] = acc;
     }
 }
