@@ -250,6 +250,7 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - zernike3d_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa_node = zdist.bind_to_gpu_numa(local)   # before any pinned allocation (no-op where the platform hides the topology)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -418,6 +419,7 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": BATCH * nmom * 8,
                     "per_rank_h2d_gbs": [round(float(x), 2) for x in rank_gbs.cpu().tolist()],
+                    "rank0_numa_node": numa_node,
                     "how": "Plan.decompose_host -> z3d_decompose_host: pinned host volumes -> H2D -> kernels -> D2H moments, "
                            "64-volume groups double buffered"},
             "gpu_launches": int(launches),

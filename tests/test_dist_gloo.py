@@ -103,3 +103,11 @@ def test_world_size_2_gloo(tmp_path, oracle_mod):
     bw = np.stack([oracle_mod.decompose(volume(20 + i, DIM), ORDER, oracle_mod.EXACT) for i in range(3)])
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"batch_{r}.npy"), bw)
+
+
+def test_parse_cpulist_and_numa_binding_is_a_noop_without_topology(tmp_path):
+    from zernike3d_b200 import dist as zdist
+
+    assert zdist.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert zdist.parse_cpulist("") == set()
+    assert zdist.bind_to_gpu_numa(0, sysfs=str(tmp_path)) == -1   # no CUDA device / no sysfs entry: nothing changes

@@ -1888,6 +1888,14 @@ extern "C" int z3d_debug_gen(long long *out, int reset) {
 }
 #endif
 
+#ifdef Z3D_GEN_CTACLK
+extern "C" int z3d_debug_gen_cta(long long *out, int n) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, z3d::g_cta_clk, sizeof(long long) * std::min(n, 5 * 1024));
+    return 0;
+}
+#endif
+
 #ifdef Z3D_DEBUG_TIMING
 extern "C" int z3d_debug_dump(long long *out, int reset) {
     cudaDeviceSynchronize();

@@ -137,6 +137,17 @@ __device__ __forceinline__ void g_wait_relaxed(unsigned mbar, unsigned parity) {
     __trap();
 }
 
+#ifdef Z3D_GEN_CTACLK
+// developer instrumentation, cheap enough not to disturb the timing: per CTA of the last launch, in SM clocks, [0] the CTA's
+// duration and what the issuing warp spent waiting for [1] read-backs (flushed), [2] T blocks (tfull), [3] a panels (afull),
+// [4] inside the elected MMA / commit block (z3d_debug_gen_cta) - what the planner's cost model of a column set is fitted against
+__device__ long long g_cta_clk[5][1024];
+#define GC_T(var) const long long var = clock64()
+#define GC_ADD(acc, t0, t1) acc += (t1) - (t0)
+#else
+#define GC_T(var)
+#define GC_ADD(acc, t0, t1)
+#endif
 #ifdef Z3D_GEN_TIMING
 // developer instrumentation: clocks spent per role and wait reason, CTA 0 only (z3d_debug_gen)
 __device__ long long g_gdbg[32];
@@ -274,6 +285,9 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int set = blockIdx.y, split = blockIdx.x, bid = blockIdx.y * gridDim.x + blockIdx.x;   // grid = (splits, sets)
+#ifdef Z3D_GEN_CTACLK
+    const long long cta_t0 = clock64();
+#endif
     GenTabs &T = *reinterpret_cast<GenTabs *>(smem + G_OFF_TABS);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + G_OFF_BAR);
     float2 *gds = reinterpret_cast<float2 *>(smem + G_OFF_GD);
@@ -366,6 +380,9 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
             unsigned tuse = 0, nev = 0;
             int next_ev = ev0;        // the next read-back event lies in front of this chunk
             unsigned mine = 0;        // chunks this warp has issued
+#ifdef Z3D_GEN_CTACLK
+            long long gc_flushed = 0, gc_tfull = 0, gc_afull = 0, gc_issue = 0;
+#endif
             auto cross_event = [&](bool wait) {   // pass the event in front of chunk next_ev (or the final one, next_ev >= nchunk)
                 const int before = min(next_ev, nchunk) - 1;   // the last chunk in front of the event
                 if (G_NALT > 1 && before % G_NALT != alt) {    // not mine: my own MMAs so far must have retired as well
@@ -373,8 +390,11 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
                     __syncwarp();
                 }
                 if (wait) {
+                    GC_T(g0);
                     GW(flushed, nev & 1, 1, next_ev);
                     GD_SLEEP(2);
+                    GC_T(g1);
+                    GC_ADD(gc_flushed, g0, g1);
                 }
                 ++nev;
                 next_ev += BFLUSH_CHUNKS;
@@ -389,20 +409,27 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
                 GT_T(i1);
                 const int as = t % NCS;
                 const unsigned dlo = dlo0 + (unsigned)ts * step;
+                GC_T(g2);
                 GW(tfull0 + 8 * ts, tuse & 1, 2, t);
+                GC_T(g3);
+                GC_ADD(gc_tfull, g2, g3);
                 GT_T(i2);
                 GT_T(i3);
                 if (warp == 0) { GT_ADD(0, i0, i1); GT_ADD(1, i1, i2); }
 #pragma unroll
                 for (int tile = 0; tile < NTILE; ++tile) {
                     GT_T(j0);
+                    GC_T(g4);
                     GW(afull0 + 8 * (as * NTILE + tile), (unsigned)(t / NCS) & 1, 3, t);
+                    GC_T(g5);
+                    GC_ADD(gc_afull, g4, g5);
                     GD_SLEEP(4);
                     GT_T(j1);
                     if (warp == 0) GT_ADD(2, j0, j1);
                     tc_fence_after();
                     if (G_NALT > 1 && tile == 0 && t > 0) GW(other_issued, (alt ? mine : mine - 1) & 1, 10, t);   // chunk t - 1 is in the queue
                     GT_T(k0);
+                    GC_T(g6);
                     if (elect_one()) {
                         const unsigned a = a0 + (unsigned)((as * NTILE + tile) * np16);
 #pragma unroll
@@ -438,6 +465,8 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
 #endif
                     }
                     __syncwarp();
+                    GC_T(g7);
+                    GC_ADD(gc_issue, g6, g7);
                     GT_T(k3);
                     if (warp == 0) { GT_ADD(17, j1, k0); GT_ADD(20, k0, k3); }
                 }
@@ -447,6 +476,11 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
                 ts += G_NALT;
                 if (ts >= NS) { ts -= NS; ++tuse; }
             }
+#ifdef Z3D_GEN_CTACLK
+            if (lane == 0 && alt == 0 && bid < 1024) {
+                g_cta_clk[1][bid] = gc_flushed; g_cta_clk[2][bid] = gc_tfull; g_cta_clk[3][bid] = gc_afull; g_cta_clk[4][bid] = gc_issue;
+            }
+#endif
             if (G_NALT > 1) {  // events behind this warp's last chunk: every issuing warp arrives on `drained` at every event
                 while (next_ev < nchunk) cross_event(true);
                 if ((nchunk - 1) % G_NALT != alt) cross_event(false);
@@ -631,11 +665,6 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
                 const float4 fa0 = fq[0], fa1 = fq[1], fb0 = fq[64], fb1 = fq[65];
                 const float fa[8] = {fa0.x, fa0.y, fa0.z, fa0.w, fa1.x, fa1.y, fa1.z, fa1.w};
                 const float fb[8] = {fb0.x, fb0.y, fb0.z, fb0.w, fb1.x, fb1.y, fb1.z, fb1.w};
-                __syncwarp();
-                if (lane == 0 && p + G_FD < npos) {   // every lane has its folds in registers: refill the slot
-                    fence_async_smem();
-                    fissue(p + G_FD);
-                }
 #ifdef Z3D_GEN_DEBUG
                 if (!(P.dbg & 4096))
 #endif
@@ -656,6 +685,13 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
                 if (lane == 0) {
                     mbar_arrive(afull0 + 8 * (cs * NTILE + tile));
                     if (tile == NTILE - 1) mbar_arrive(gfree0 + 8 * gs);
+                    // refill the fold slot only now, off the path between "slot free" and "panels ready" (the slot round trip through
+                    // the issuing warp paces the kernel; 3.72 -> 3.62 ms per 64 x 128^3 tile).  Every lane consumed its folds in the
+                    // panel loop above, so the loads have completed before the bulk copies may overwrite the slot.
+                    if (p + G_FD < npos) {
+                        fence_async_smem();
+                        fissue(p + G_FD);
+                    }
                 }
                 GT_T(c2);
                 if (warp == G_WARP_A0) { GT_ADD(14, b1, c0); GT_ADD(15, c0, c1); GT_ADD(16, c1, c2); }
@@ -751,6 +787,9 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+#ifdef Z3D_GEN_CTACLK
+    if (tid == 0 && bid < 1024) g_cta_clk[0][bid] = clock64() - cta_t0;
+#endif
 }
 
 

@@ -40,6 +40,37 @@ def batch_range(count: int, rank: int, world: int) -> tuple[int, int]:
     return (count * rank // world, count * (rank + 1) // world)
 
 
+def parse_cpulist(text: str) -> set[int]:
+    """``"0-15,32-47"`` (the kernel's cpulist format) -> set of CPU numbers."""
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if part:
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device: int, sysfs: str = "/sys") -> int:
+    """Pin this process to the CPUs of the NUMA node ``device`` hangs off, BEFORE it allocates pinned host buffers (first touch
+    then places them on that node), so that a rank's H2D / D2H traffic does not cross the socket interconnect.  Returns the node,
+    or -1 when the platform does not say (virtualised boxes report ``numa_node = -1``) - then nothing is changed."""
+    import os
+
+    try:
+        p = torch.cuda.get_device_properties(device)
+        pci = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"{sysfs}/bus/pci/devices/{pci}/numa_node").read())
+        if node < 0:
+            return -1
+        cpus = parse_cpulist(open(f"{sysfs}/devices/system/node/node{node}/cpulist").read()) & os.sched_getaffinity(0)
+        if not cpus:
+            return -1
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return -1
+
+
 def _world(group):
     if not dist.is_available() or not dist.is_initialized():
         return 0, 1
