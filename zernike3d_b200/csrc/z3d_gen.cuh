@@ -206,7 +206,8 @@ __device__ __forceinline__ void tmem_st8(unsigned taddr, const float (&v)[8]) {
 }
 // x = hi + lo, hi = x rounded to TF32 (nearest, ties away: what cvt.rna.tf32.f32 computes, which ptxas expands into four
 // instructions per value - FSETP / VIADD / SEL / LOP3 - for the infinity case; the operands here are finite): add half an ulp of
-// the 13 dropped bits to the magnitude, clear them
+// the 13 dropped bits to the magnitude, clear them.  (Plain truncation - one instruction less - biases hi: moments 2.3e-6 from the
+// float64 oracle instead of 6.5e-7, for 0.7 % of the kernel's time.)
 __device__ __forceinline__ void split_fast(float x, float &hi, float &lo) {
 #ifdef G_OLDSPLIT
     split_tf32(x, hi, lo);
@@ -707,8 +708,11 @@ k_decompose_gen(const __grid_constant__ DevPlanG P, const __grid_constant__ GenI
         // ---- T teams: thread u of a team owns tasks u and u + 128: (chain (l, m), k half) -> 4 voxels of every n of the chain
         // the tasks are sorted by chain length, so a team's first logical warp is its busiest: rotate the logical warps over the
         // physical ones by team, or the four teams' busiest warps all sit on scheduler 0 next to the issuing warp
-#ifdef G_NOROT
+#if defined(G_NOROT)
         const int team = (warp - G_WARP_T0) >> 2, u = ((warp - G_WARP_T0) & 3) * 32 + lane;
+#elif defined(G_LIGHT0)
+        // the issuing warp's scheduler (warps = 0 mod 4) gets every team's LIGHTEST logical warp; the other three rotate by team
+        const int team = (warp - G_WARP_T0) >> 2, pq = warp & 3, u = (pq == 0 ? 3 : (pq - 1 + team) % 3) * 32 + lane;
 #else
         const int team = (warp - G_WARP_T0) >> 2, u = ((warp - team + 1) & 3) * 32 + lane;
 #endif
