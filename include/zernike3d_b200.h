@@ -73,7 +73,8 @@ int z3d_plan_destroy(z3d_plan *plan);
  * table-free tensor-core variant (the default for batches): 24 available, 25 column sets, 26 splits, 27 accumulator columns over all
  * sets, 28 depth of the shared-memory T ring, 29 smallest batch routed to it, 30 basis-table level in use (z3d_plan_prepare_tables),
  * 31 columns of the widest set; its two-tile layout (while more than 64 volumes are left, 128 volumes share every generated
- * T block): 32 available, 33 column sets, 34 splits, 35 depth of the T ring. */
+ * T block): 32 in use by the analysis (opt-in), 33 column sets, 34 splits, 35 depth of the T ring;
+ * tensor-core batched synthesis (z3d_reconstruct_batched): 36 available, 37 smallest batch of maps worth routing to it. */
 int z3d_plan_info(const z3d_plan *plan, int *info, int n_info);
 
 /* Host-only planner query (no device needed): the column-set layout of the streamed-T batched analysis kernel for `order` on a
@@ -146,6 +147,15 @@ int z3d_decompose_allreduce(const z3d_plan *plan, z3d_comm *comm, const float *d
 int z3d_reconstruct(const z3d_plan *plan, const float *d_moments /* [batch][num_moments][2] */, int batch,
                     int half_lo, int half_hi, float *d_vol /* [batch][N][N][N] */, void *d_workspace,
                     size_t workspace_bytes, void *stream);
+
+/* Batched synthesis on the tensor cores, for ensembles / latent trajectories of maps (the loop over volumes of Reconstruct,
+ * zm:2642-2715, and of the 3DVA consumer, moment_analysis_3dva.py:197-246): the same sum as z3d_reconstruct over the WHOLE box,
+ * evaluated for tiles of 64 moment sets as a GEMM over the moment rows (tcgen05.mma kind::tf32, FP32-accurate 3xTF32 split; the
+ * basis operand R_nl Q_lm is generated inside the kernel, nothing is materialised).  A tile costs the same whatever it holds, so
+ * callers route batches below z3d_plan_info entry 37 to z3d_reconstruct.  Needs its own (larger) workspace. */
+size_t z3d_reconstruct_batched_workspace_bytes(const z3d_plan *plan, int batch);
+int z3d_reconstruct_batched(const z3d_plan *plan, const float *d_moments /* [batch][num_moments][2] */, int batch,
+                            float *d_vol /* [batch][N][N][N] */, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Rotational invariants F_nl = || Omega_nl. ||_2 over m = -l..l  (Moments.calculate_invariants,
  * zm:62-76): d_invariants [batch][num_radial] float32 in sorted (n, l) order. */

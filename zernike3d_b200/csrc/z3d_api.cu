@@ -4,6 +4,7 @@
 #include "z3d_batched.cuh"
 #include "z3d_stream.cuh"
 #include "z3d_gen.cuh"
+#include "z3d_synth.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -111,11 +112,18 @@ struct z3d_plan {
     int2 *d_gcolmap = nullptr;
     // ... its two-tile layout (128 volumes per generated T block: half the columns per set, half the splits), used while more than
     // one tile of volumes is left; absent when the order needs more sets than SMs (order > ~70)
-    bool gen2 = false;
+    bool gen2 = false;           // the analysis kernel uses it (opt-in, Z3D_GEN2=1)
+    bool g2_built = false;       // the layout exists (the tensor-core synthesis kernel runs on it)
     DevPlanG devg2{};
     int g2_smem = 0;
     GenIssue g2_issue{};
     int2 *d_g2colmap[2] = {nullptr, nullptr};   // (set, accumulator column) of every moment, per tile
+    // tensor-core batched synthesis (z3d_synth.cuh) on the two-tile layout's column sets
+    bool synth = false;
+    int synth_min = 12;          // smallest batch of maps routed to it by the host layer (a tile costs the same whatever it holds)
+    int synth_maxcols = 0, synth_off_t = 0, synth_slots = 0, synth_smem = 0;
+    int *d_synth_colsrc = nullptr;   // [sets][maxcols] -> moment index or -1
+    KindSets synth_kinds{};
     // reduce / prepare tables
     int *d_src = nullptr;        // [2*nmom]  pass*SLOT_WORDS + word
     double *d_scale = nullptr;   // [nmom]    coeff(n) * kappa_lm
@@ -910,6 +918,8 @@ int set_kernel_attrs(int smem) {
     CUDA_TRY(cudaFuncSetAttribute(k_decompose_gen<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUDA_TRY(cudaFuncSetAttribute(k_decompose_gen<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaFuncSetAttribute(k_decompose_gen<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(k_synth_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_synth_gen, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return set_kernel_attrs_t<0>(smem);
 }
 
@@ -1073,7 +1083,7 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
             // two tiles per T block: correct and tested, but not faster yet (9.4 ms per 128 volumes against 2 x 3.7 ms at 128^3 /
             // order 50: with twice the a-panel work per chunk the a-panel teams and the single issuing warp become the bottleneck) -
             // opt-in with Z3D_GEN2=1
-            if (ntile == 2 && (!pl->gen || !(off2 && atoi(off2) != 0))) break;
+            if (ntile == 2 && !pl->gen) break;
             HostPlanG hg;
             build_gen_plan(order, prop.multiProcessorCount, hp, hg, force, ntile);
             if (!hg.ok) continue;
@@ -1118,7 +1128,25 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
                 for (int2 &c : cm1) c.y += hg.tabs[c.x].ncols;
                 UP(hg.colmap, pl->d_g2colmap[0]) UP(cm1, pl->d_g2colmap[1])
                 pl->g2_smem = g.off_t + g.nslots * g.tslot_bytes;
-                pl->gen2 = true;
+                pl->g2_built = true;
+                pl->gen2 = off2 && atoi(off2) != 0;
+                // tensor-core synthesis: which moment every column of every set holds, and the sets of every fold kind (the planner
+                // lays the sets out kind by kind)
+                pl->synth_maxcols = (hg.maxcols + 15) / 16 * 16;
+                std::vector<int> colsrc((size_t)hg.nsets * pl->synth_maxcols, -1);
+                for (int mu = 0; mu < pl->nmom; ++mu) colsrc[(size_t)hg.colmap[mu].x * pl->synth_maxcols + hg.colmap[mu].y] = mu;
+                UP(colsrc, pl->d_synth_colsrc)
+                bool ordered = true;
+                for (int k = 0, i = 0; k <= 4; ++k) {
+                    while (i < hg.nsets && hg.tabs[i].kind < k) ++i;
+                    pl->synth_kinds.first[k] = i;
+                }
+                for (int i = 1; i < hg.nsets; ++i) ordered = ordered && hg.tabs[i].kind >= hg.tabs[i - 1].kind;
+                // its T ring: 128 B per row (the one MN-major layout the tensor core reads for 32-bit operands), in place of the fold rings
+                pl->synth_off_t = (g.off_f + 1023) / 1024 * 1024;
+                pl->synth_slots = std::min(G_NS_MAX, ((int)prop.sharedMemPerBlockOptin - pl->synth_off_t - 1024) / (2 * g.tslot_bytes));
+                pl->synth_smem = pl->synth_off_t + 1024 + pl->synth_slots * 2 * g.tslot_bytes;
+                pl->synth = ordered && pl->synth_slots >= G_NTT && !(getenv("Z3D_SYNTH") && atoi(getenv("Z3D_SYNTH")) == 0);
             }
         }
     }
@@ -1130,6 +1158,7 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
     if (const char *e = getenv("Z3D_BATCHED_MIN")) pl->batched_min = std::max(1, atoi(e));  // tuning / tests
     if (const char *e = getenv("Z3D_BATCHED_WIDE")) pl->batched_wide = std::max(1, atoi(e));
     if (const char *e = getenv("Z3D_GEN_MIN")) pl->gen_min = std::max(1, atoi(e));
+    if (const char *e = getenv("Z3D_SYNTH_MIN")) pl->synth_min = std::max(1, atoi(e));
     rc = set_kernel_attrs((int)prop.sharedMemPerBlockOptin);  // per-function attribute: plans of any size coexist
     if (rc) {
         z3d_plan_destroy(pl);
@@ -1272,7 +1301,7 @@ extern "C" int z3d_plan_destroy(z3d_plan *pl) {
 extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
     if (!pl || !info) return fail(Z3D_ERR_INVALID, "z3d_plan_info: NULL argument");
     const long long t_mb = pl->stream ? (long long)((double)pl->b_chunks * (double)pl->devs.trec * 4.0 / 1048576.0) : 0;
-    const int v[36] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
+    const int v[38] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
                        KC, pl->num_sms, pl->useful_acc, pl->padded_acc,
                        pl->batched ? pl->batched_min : 0, pl->devb[0].ngroups, pl->devb[1].ngroups, pl->batched ? pl->batched_wide : 0,
                        pl->devb[0].nrounds, pl->devb[1].nrounds,
@@ -1286,8 +1315,10 @@ extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
                        pl->gen ? 1 : 0, pl->devg.nsets, pl->devg.nsplits, pl->g_ncols_all, pl->devg.nslots, pl->gen ? pl->gen_min : 0,
                        pl->tables_level, pl->g_maxcols,
                        // its two-tile layout (128 volumes per generated T block): 32 available, 33 column sets, 34 splits, 35 T-ring slots
-                       pl->gen2 ? 1 : 0, pl->devg2.nsets, pl->devg2.nsplits, pl->devg2.nslots};
-    for (int i = 0; i < n && i < 36; ++i) info[i] = v[i];
+                       pl->gen2 ? 1 : 0, pl->devg2.nsets, pl->devg2.nsplits, pl->devg2.nslots,
+                       // tensor-core batched synthesis: 36 available, 37 smallest batch of maps the host layer routes to it
+                       pl->synth ? 1 : 0, pl->synth ? pl->synth_min : 0};
+    for (int i = 0; i < n && i < 38; ++i) info[i] = v[i];
     return Z3D_OK;
 }
 
@@ -1576,6 +1607,58 @@ extern "C" int z3d_reconstruct(const z3d_plan *pl, const float *d_moments, int b
     k_sum_passes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pvol, pl->npass, batch, pl->dim, half_lo, half_hi, d_vol);
     CUDA_TRY(cudaGetLastError());
     g_launches += 3;
+    return Z3D_OK;
+}
+
+// ---- tensor-core batched synthesis (z3d_synth.cuh): tiles of 64 maps, the chunk list in parts so that the partial folds of a part
+// (sets x chunks x 8 KB) stay below ~1.5 GB
+static int synth_parts(const z3d_plan *pl) {
+    const double bytes = (double)pl->devg2.nsets * (double)pl->b_chunks * 2.0 * SM_ROWS * KC * sizeof(float);
+    return std::max(1, (int)std::ceil(bytes / 1.5e9));
+}
+static size_t synth_part_floats(const z3d_plan *pl) {
+    const long long per = (pl->b_chunks + synth_parts(pl) - 1) / synth_parts(pl) + 1;
+    return (size_t)pl->devg2.nsets * (size_t)per * 2 * SM_ROWS * KC;
+}
+static size_t synth_op_floats(const z3d_plan *pl) { return (size_t)pl->devg2.nsets * SM_ROWS * 2 * pl->synth_maxcols; }
+
+extern "C" size_t z3d_reconstruct_batched_workspace_bytes(const z3d_plan *pl, int batch) {
+    if (!pl || batch < 1 || !pl->synth) return 0;
+    return (synth_op_floats(pl) + synth_part_floats(pl)) * sizeof(float);
+}
+
+extern "C" int z3d_reconstruct_batched(const z3d_plan *pl, const float *d_moments, int batch, float *d_vol, void *d_ws, size_t ws_bytes,
+                                       void *stream) {
+    if (!pl) return fail(Z3D_ERR_INVALID, "z3d_reconstruct_batched: plan is NULL");
+    if (batch < 1 || !d_moments || !d_vol || !d_ws) return fail(Z3D_ERR_INVALID, "z3d_reconstruct_batched: bad arguments");
+    if (!pl->synth) return fail(Z3D_ERR_UNSUPPORTED, "z3d_reconstruct_batched: no tensor-core synthesis layout for order %d / box %d", pl->order, pl->dim);
+    if (ws_bytes < z3d_reconstruct_batched_workspace_bytes(pl, batch))
+        return fail(Z3D_ERR_WORKSPACE, "z3d_reconstruct_batched: workspace %zu < %zu bytes", ws_bytes, z3d_reconstruct_batched_workspace_bytes(pl, batch));
+    USE_DEVICE(pl->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    float *Op = (float *)d_ws, *Fs = Op + synth_op_floats(pl);
+    const DevPlanG &dp = pl->devg2;
+    const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
+    const int nparts = synth_parts(pl);
+    const_cast<z3d_plan *>(pl)->last_was_decompose = false;
+    for (int b0 = 0; b0 < batch; b0 += SNV) {
+        const int nb = std::min(SNV, batch - b0);
+        k_prepare_synth<<<dim3(dp.nsets, SM_ROWS), 128, 0, st>>>(d_moments + (size_t)b0 * pl->nmom * 2, pl->d_synth_colsrc, pl->d_ofac,
+                                                                 pl->synth_maxcols, pl->nmom, nb, Op);
+        CUDA_TRY(cudaGetLastError());
+        ++g_launches;
+        if (pl->profiling && b0 == 0) CUDA_TRY(cudaEventRecord(pl->ev_k0, st));
+        for (int part = 0; part < nparts; ++part) {
+            const long long gbeg = pl->b_chunks * part / nparts, glen = pl->b_chunks * (part + 1) / nparts - gbeg;
+            if (glen <= 0) continue;
+            k_synth_gen<<<dim3(dp.nsplits, dp.nsets), GNT, pl->synth_smem, st>>>(dp, Op, pl->synth_maxcols, pl->synth_off_t, pl->synth_slots, part, nparts, Fs);
+            CUDA_TRY(cudaGetLastError());
+            k_unfold_tile<<<(unsigned)glen, 2 * SNV * KC, 0, st>>>(Fs, gbeg, glen, pl->synth_kinds, nb, pl->dim, pl->H, d_vol + (size_t)b0 * N3);
+            CUDA_TRY(cudaGetLastError());
+            g_launches += 2;
+        }
+        if (pl->profiling && b0 == 0) CUDA_TRY(cudaEventRecord(pl->ev_k1, st));
+    }
     return Z3D_OK;
 }
 

@@ -1,0 +1,419 @@
+// zernike3d_b200 - batched SYNTHESIS on the tensor cores (maps from moments for tiles of 64 moment sets), table-free.
+//
+// The exact adjoint of z3d_gen.cuh.  The reference's sum (zm:2596-2614)
+//     vol(v) = sum_{n,l,m>=0} w_m kappa_lm T_nlm(v) (Re O_nlm cos m phi_v - Im O_nlm sin m phi_v),   T = R_nl Q_lm,  w_0 = 1, w_m = 2,
+// is evaluated on the 1/16 of the voxels the grid's mirror / transpose symmetries leave: for a folded voxel k of a row group
+//     G_X[kind][re|im](k) = sum over the (m, pz) panels j of the kind of   trig_X,j[re|im] * out_j[re|im](k),     X = row group A or its transpose B,
+//     out_j[(re|im, b)](k) = sum over the rows of panel j of   O'[(re|im, b)][row] * T[row](k),     O'[re] = w kappa Re O,  O'[im] = - w kappa Im O,
+// and the 8 mirror images of k are the 8-point Walsh-Hadamard transform of the 8 class values (kind, re|im) - k_fold_tile_gen run backwards.
+// out_j is a GEMM over the moment rows: tcgen05.mma kind::tf32 with M = 128 = (re|im) x 64 maps, K = 8 rows per instruction, and N = 16 =
+// the chunk's 8 folded voxels TWICE: the T block of a chunk lies in shared memory as [T_hi k half 0 | T_hi k half 1 | T_lo k half 0 | T_lo
+// k half 1] with one stride, which an MN-major descriptor reads as 4 vectors of 4 voxels - one MMA with A = O'_hi yields O'_hi T_hi in
+// columns 0-7 and O'_hi T_lo in columns 8-15, a second with A = O'_lo adds O'_lo T_hi (3xTF32: the three are summed in the epilogue).
+//   * O' of the CTA's column set stays in TENSOR memory for the whole kernel (columns [0, ncols) hi, [ncols, 2 ncols) lo; the MMA's A operand),
+//   * T is generated exactly as in k_decompose_gen (seed warps, T teams, the same ring and the same plan tables: the two-tile layout of
+//     the analysis kernel, whose sets hold <= 224 columns),
+//   * the accumulators out_j (32 columns per panel, two banks by chunk parity) are read by two epilogue teams (thread = (re|im, map) =
+//     tensor-memory lane), multiplied by the row trig of the chunk and summed over the set's panels; the sets of one kind add up in
+//     k_unfold_tile, which also applies the Walsh-Hadamard transform and writes the 16 images.  No read-back interval: an accumulator lives
+//     for one chunk.
+// Roles (28 warps): warp 0 issues, warps 1-3 seeds, warps 4-11 two epilogue teams, warps 12-27 four T teams.
+#pragma once
+#include "z3d_gen.cuh"
+
+namespace z3d {
+
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
+    unsigned r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, float (&v)[8]) {
+    unsigned r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// O' of a tile of maps in the layout the synthesis kernel loads into tensor memory: Op[set][row = (re|im, map)][hi: maxcols | lo: maxcols]
+// (zero for padding columns and for maps beyond nvol)
+__global__ void k_prepare_synth(const float *__restrict__ moments, const int *__restrict__ colsrc /* [nsets][maxcols] -> mu or -1 */,
+                                const double *__restrict__ ofac, int maxcols, int nmom, int nvol, float *__restrict__ Op) {
+    const int set = blockIdx.x, row = blockIdx.y, reim = row / SNV, b = row % SNV;
+    float *dst = Op + ((size_t)set * SM_ROWS + row) * (2 * maxcols);
+    for (int c = threadIdx.x; c < maxcols; c += blockDim.x) {
+        const int mu = colsrc[(size_t)set * maxcols + c];
+        float v = 0.0f;
+        if (mu >= 0 && b < nvol) {
+            const double x = (double)moments[((size_t)b * nmom + mu) * 2 + reim] * ofac[mu];
+            v = (float)(reim ? -x : x);
+        }
+        float hi, lo;
+        split_fast(v, hi, lo);
+        dst[c] = hi;
+        dst[maxcols + c] = lo;
+    }
+}
+
+// Partial folds of the launch's chunk range: Fs[set][chunk - gbeg][row group A|B][row = (re|im, map)][k]
+__global__ void __launch_bounds__(GNT, 1)
+k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, int maxcols, int off_ts, int NS, int part, int nparts,
+            float *__restrict__ Fs) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int set = blockIdx.y, split = blockIdx.x;
+    GenTabs &T = *reinterpret_cast<GenTabs *>(smem + G_OFF_TABS);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + G_OFF_BAR);
+    float2 *gds = reinterpret_cast<float2 *>(smem + G_OFF_GD);
+    float4 *rks = reinterpret_cast<float4 *>(smem + P.off_rk);
+    // (the analysis kernel's fold rings are not needed: the T ring starts there, on a 1024-byte boundary of the shared-memory WINDOW - the
+    // swizzle of the MN-major layout works on absolute address bits)
+    off_ts = (int)(((smem_u32(smem) + (unsigned)off_ts + 1023u) & ~1023u) - smem_u32(smem));
+    unsigned char *gring = smem + P.off_g, *tring = smem + off_ts;
+    const int slot_bytes = 2 * P.tslot_bytes;   // 128 B per row
+    // barriers: gfull[DG] gfree[DG] tfull[NS_MAX] tfree[NS_MAX] dfull[2] dfree[2] oready
+    const unsigned gfull0 = smem_u32(bars), gfree0 = gfull0 + 8 * G_DG, tfull0 = gfree0 + 8 * G_DG, tfree0 = tfull0 + 8 * G_NS_MAX,
+                   dfull0 = tfree0 + 8 * G_NS_MAX, dfree0 = dfull0 + 16, oready = dfree0 + 16;
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + G_OFF_BAR + 8 * (2 * G_DG + 2 * G_NS_MAX + 5));
+    static_assert(8 * (2 * G_DG + 2 * G_NS_MAX + 5) + 4 <= G_OFF_GD - G_OFF_BAR, "barrier block");
+    for (int i = tid; i < (int)(sizeof(GenTabs) / 4); i += GNT)
+        reinterpret_cast<int *>(smem + G_OFF_TABS)[i] = reinterpret_cast<const int *>(P.tabs + set)[i];
+    for (int i = tid; i < P.gd_bytes / 8; i += GNT) gds[i] = P.gd[(size_t)set * (P.gd_bytes / 8) + i];
+    // rows of a panel are padded to 16: the padding rows of the T ring are never written by a chain and multiply O' = 0 - they must be finite
+    for (int i = tid; i < NS * slot_bytes / 16; i += GNT) reinterpret_cast<float4 *>(tring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const int ncols = T.ncols, nseg = T.nseg, npanel = T.npanel;
+    for (int i = tid; i < P.rk_bytes / 16; i += GNT) rks[i] = P.rk[(size_t)T.lpar * (P.rk_bytes / 16) + i];
+    if (tid == 0) {
+        for (int i = 0; i < G_DG; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gfull0 + 8 * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(gfree0 + 8 * i));   // 4 warps of a T team + 4 of an epilogue team
+        }
+        for (int i = 0; i < G_NS_MAX; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(tfull0 + 8 * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tfree0 + 8 * i));
+        }
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dfull0 + 8 * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(dfree0 + 8 * i));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(oready));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    fence_async_smem();   // the zeroed T ring is read by the tensor core's async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *tmem_slot;
+    const unsigned dcol0 = 512u - 64u * (unsigned)npanel;   // accumulator banks: dcol0 + (bank * npanel + j) * 32 (+ 16: the O'_lo product)
+
+    const int CPR = (P.H + KC - 1) / KC;
+    const long long total = (long long)analysis_items(0, P.H, P.H) * CPR;
+    const long long gbeg = total * part / nparts, glen = total * (part + 1) / nparts - gbeg;
+    const long long cbeg = gbeg + glen * split / P.nsplits, cend = gbeg + glen * (split + 1) / P.nsplits;
+    const int nchunk = (int)(cend - cbeg);
+
+    if (nchunk == 0) {
+        // nothing to do
+    } else if (warp == 0) {
+        // ---- issuing warp
+        const unsigned dlo0 = (smem_u32(smem) + (unsigned)off_ts) >> 4;
+        // MN-major B for 32-bit operands exists in ONE shared-memory layout (scripts/experiments/tc_probe6.cu: every other layout type
+        // makes the tensor core read zeros): SWIZZLE_128B_BASE32B - rows of 128 B (32 elements along MN), 4 rows = one 512-byte atom,
+        // the 32-byte unit c of row k stored at unit c ^ (k % 4), atoms along K `SBO` apart.  A T row holds [T_hi 8 voxels | T_lo 8
+        // voxels | unused]; an MMA reads 2 atoms = 8 rows.
+        const unsigned long long dhi = ((unsigned long long)(512 >> 4) << 32) | (1ull << 46) | ((unsigned long long)(512 >> 4) << 16) | (1ull << 61);
+        const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((16u >> 3) << 17) | ((unsigned)(SM_ROWS >> 4) << 24);
+        const unsigned step = (unsigned)(slot_bytes >> 4);
+        int ts = 0;
+        unsigned tuse = 0;
+        mbar_wait(oready, 0);
+        for (int t = 0; t < nchunk; ++t) {
+            const int bank = t & 1;
+            mbar_wait(tfull0 + 8 * ts, tuse & 1);
+            if (t >= 2) mbar_wait(dfree0 + 8 * bank, (unsigned)(t / 2 - 1) & 1);   // the epilogue has read chunk t - 2 out of this bank
+            tc_fence_after();
+            if (elect_one()) {
+                const unsigned dl = dlo0 + (unsigned)ts * step;
+                int prev_panel = -1;
+                for (int g = 0; g < nseg; ++g) {
+                    const int j = T.seg_panel[g], off = T.seg_off[g], cols = T.seg_cols[g];
+                    const unsigned d = tmem + dcol0 + (unsigned)((bank * npanel + j) * 32);
+                    const bool fresh = j != prev_panel;
+                    prev_panel = j;
+                    for (int ks = 0; ks < cols; ks += 8) {
+                        const unsigned r = (unsigned)(off + ks);
+                        const unsigned long long b = dhi | (unsigned long long)(dl + r * 8u);   // row r -> atom r / 4 -> 512 B each
+                        const unsigned acc = (fresh && ks == 0) ? 0u : 1u;
+                        umma_tf32_ts(d, tmem + r, b, idesc, acc);                            // O'_hi x [T_hi | T_lo]
+                        umma_tf32_ts(d + 16, tmem + (unsigned)ncols + r, b, idesc, acc);     // O'_lo x [T_hi | (T_lo: not used)]
+                    }
+                }
+                umma_commit(tfree0 + 8 * ts);
+                umma_commit(dfull0 + 8 * bank);
+            }
+            __syncwarp();
+            if (++ts == NS) { ts = 0; ++tuse; }
+        }
+    } else if (warp < G_WARP_SEED0 + G_NSEEDW) {
+        // ---- seed warps: as in k_decompose_gen (lane = (panel j = lane / 8 (+ 4 in the second pass), voxel k = lane % 8))
+        const int sw = warp - G_WARP_SEED0, k = lane & 7;
+        int pm[2], ppz[2], pnl[2], psoff[2], pgd[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int j = (lane >> 3) + 4 * q;
+            const bool v = j < npanel;
+            pm[q] = v ? T.panel_m[j] : 0;
+            ppz[q] = v ? T.panel_pz[j] : 0;
+            pnl[q] = v ? T.panel_nl[j] : 0;
+            psoff[q] = v ? T.panel_soff[j] : 0;
+            pgd[q] = v ? T.panel_gd[j] : 0;
+        }
+        const int npass = npanel > 4 ? 2 : 1;
+        int maxnl = 0;
+        for (int j = 0; j < npanel; ++j) maxnl = max(maxnl, T.panel_nl[j]);
+        int item_have = -1;
+        double rho2 = 0.0, rhom[2] = {0.0, 0.0};
+        float tr[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        for (int t = sw; t < nchunk; t += G_NSEEDW) {
+            const long long cc = cbeg + t;
+            const int item = (int)(cc / CPR), kc = (int)(cc % CPR);
+            if (item != item_have) {
+                item_have = item;
+                int ip, jp;
+                bool paired;
+                decode_item(item, 0, P.H, P.H, ip, jp, paired);
+                const double y0 = P.side[ip], x0 = P.side[jp];
+                rho2 = x0 * x0 + y0 * y0;
+                const double rho = sqrt(rho2);
+                double ur = 1.0, ui = 0.0;
+                if (rho > 0.0) {
+                    ur = x0 / rho;
+                    ui = y0 / rho;
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int m = pm[q];
+                    double br = ur, bi = ui, cr = 1.0, ci = 0.0, pw = 1.0, pb = rho;
+                    for (int e = m; e; e >>= 1) {
+                        if (e & 1) {
+                            const double tt = cr * br - ci * bi;
+                            ci = cr * bi + ci * br;
+                            cr = tt;
+                            pw *= pb;
+                        }
+                        const double tt = br * br - bi * bi;
+                        bi = 2.0 * br * bi;
+                        br = tt;
+                        pb *= pb;
+                    }
+                    rhom[q] = pw;
+                    const int mq = m & 3;
+                    tr[q][0] = (float)cr;
+                    tr[q][1] = (float)ci;
+                    tr[q][2] = (float)((mq == 0) ? cr : (mq == 1) ? ci : (mq == 2) ? -cr : -ci);
+                    tr[q][3] = (float)((mq == 0) ? -ci : (mq == 1) ? cr : (mq == 2) ? ci : -cr);
+                }
+            }
+            const int kk = kc * KC + k;
+            const double z = (kk < P.H) ? P.side[kk] : 0.0;
+            const double zz = z * z;
+            const float r2 = (float)(rho2 + zz), z4 = (float)(4.0 * zz), r4 = r2 * r2;
+            const int gs = t % G_DG;
+            if (t >= G_DG) g_wait_relaxed(gfree0 + 8 * gs, (unsigned)(t / G_DG - 1) & 1);
+            float *slot = reinterpret_cast<float *>(gring + (size_t)gs * P.gslot_bytes);
+            float *seeds = slot + 40;
+            if (lane < 8) slot[lane] = r2;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (q < npass) {
+                    const int j = (lane >> 3) + 4 * q;
+                    const float tv = k == 0 ? tr[q][0] : k == 1 ? tr[q][1] : k == 2 ? tr[q][2] : tr[q][3];
+                    if (k < 4 && j < npanel) slot[8 + j * 4 + k] = tv;
+                    float S1 = (float)(ppz[q] ? 2.0 * z * rhom[q] : rhom[q]), S2 = 0.0f;
+                    float *sp = seeds + psoff[q] * 8 + k;
+                    const float2 *gp = gds + pgd[q];
+                    const int nl = pnl[q];
+                    if (nl > 0) sp[0] = S1;
+                    for (int i0 = 1; i0 < maxnl; i0 += 8) {
+                        float2 g[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) g[e] = gp[i0 - 1 + e];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float S = fmaf(fmaf(-g[e].x, r2, z4), S1, (g[e].y * r4) * S2);
+                            S2 = S1;
+                            S1 = S;
+                            if (i0 + e < nl) sp[(i0 + e) * 8] = S;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gfull0 + 8 * gs);
+        }
+    } else if (warp < G_WARP_A0) {
+        // (no role)
+    } else if (warp < G_WARP_T0) {
+        // ---- epilogue teams: thread = row (re|im, map b) = tensor-memory lane; chunk t -> team t & 1 = accumulator bank
+        const int team = (warp - G_WARP_A0) >> 2, quarter = warp & 3;
+        const int row = quarter * 32 + lane, reim = row >> 6;
+        const unsigned lane0 = tmem + ((unsigned)(32 * quarter) << 16);
+        if (team == 0) {   // O' of the set -> tensor memory, once
+            const float *src = Op + ((size_t)set * SM_ROWS + row) * (2 * maxcols);
+            for (int c = 0; c < ncols; c += 8) {
+                float hi[8], lo[8];
+                const float4 h0 = *reinterpret_cast<const float4 *>(src + c), h1 = *reinterpret_cast<const float4 *>(src + c + 4);
+                const float4 l0 = *reinterpret_cast<const float4 *>(src + maxcols + c), l1 = *reinterpret_cast<const float4 *>(src + maxcols + c + 4);
+                hi[0] = h0.x; hi[1] = h0.y; hi[2] = h0.z; hi[3] = h0.w; hi[4] = h1.x; hi[5] = h1.y; hi[6] = h1.z; hi[7] = h1.w;
+                lo[0] = l0.x; lo[1] = l0.y; lo[2] = l0.z; lo[3] = l0.w; lo[4] = l1.x; lo[5] = l1.y; lo[6] = l1.z; lo[7] = l1.w;
+                tmem_st8(lane0 + (unsigned)c, hi);
+                tmem_st8(lane0 + (unsigned)(ncols + c), lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(oready);
+        }
+        const int bank = team;
+        for (int t = team; t < nchunk; t += 2) {
+            const int gs = t % G_DG;
+            const float *slot = reinterpret_cast<const float *>(gring + (size_t)gs * P.gslot_bytes);
+            g_wait_relaxed(dfull0 + 8 * bank, (unsigned)(t / 2) & 1);
+            tc_fence_after();
+            float FA[8], FB[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) FA[v] = FB[v] = 0.0f;
+            for (int j = 0; j < npanel; ++j) {
+                float d[16], e[8];
+                const unsigned ta = lane0 + dcol0 + (unsigned)((bank * npanel + j) * 32);
+                tmem_ld16(ta, d);
+                tmem_ld8(ta + 16, e);
+                tmem_ld_wait();
+                const float tA = slot[8 + j * 4 + reim], tB = slot[8 + j * 4 + 2 + reim];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const float o = (d[8 + v] + e[v]) + d[v];   // small terms first
+                    FA[v] = fmaf(tA, o, FA[v]);
+                    FB[v] = fmaf(tB, o, FB[v]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(dfree0 + 8 * bank);
+                mbar_arrive(gfree0 + 8 * gs);
+            }
+            float *dst = Fs + (((size_t)set * glen + (size_t)(cbeg + t - gbeg)) * 2) * (SM_ROWS * KC) + (size_t)row * KC;
+            *reinterpret_cast<float4 *>(dst) = make_float4(FA[0], FA[1], FA[2], FA[3]);
+            *reinterpret_cast<float4 *>(dst + 4) = make_float4(FA[4], FA[5], FA[6], FA[7]);
+            *reinterpret_cast<float4 *>(dst + SM_ROWS * KC) = make_float4(FB[0], FB[1], FB[2], FB[3]);
+            *reinterpret_cast<float4 *>(dst + SM_ROWS * KC + 4) = make_float4(FB[4], FB[5], FB[6], FB[7]);
+        }
+    } else {
+        // ---- T teams: as in k_decompose_gen
+        const int team = (warp - G_WARP_T0) >> 2, u = ((warp - team + 1) & 3) * 32 + lane;
+        int4 task[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = u + 128 * q;
+            task[q] = i < T.ntask ? P.tasks[(size_t)set * G_TASKS + i] : make_int4(0, 0, 0, 0);
+        }
+        for (int t = team; t < nchunk; t += G_NTT) {
+            const int ts = t % NS;
+            const unsigned tuse = (unsigned)(t / NS);
+            const int gs = t % G_DG;
+            const float *slot = reinterpret_cast<const float *>(gring + (size_t)gs * P.gslot_bytes);
+            unsigned char *tb = tring + (size_t)ts * slot_bytes;
+            g_wait_relaxed(gfull0 + 8 * gs, (unsigned)(t / G_DG) & 1);
+            if (tuse) g_wait_relaxed(tfree0 + 8 * ts, (tuse - 1) & 1);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int len = task[q].y;
+                if (len > 0) {
+                    const int kh = task[q].w >> 16, srow = task[q].w & 0xffff;
+                    const float4 s4 = *reinterpret_cast<const float4 *>(slot + 40 + srow * 8 + 4 * kh);
+                    const float4 r2 = *reinterpret_cast<const float4 *>(slot + 4 * kh);
+                    const float4 *K = rks + task[q].z;
+                    const int row0 = task[q].x;
+                    float4 T1 = make_float4(0.f, 0.f, 0.f, 0.f), T2 = s4;
+                    float4 kc4 = K[0];
+#pragma unroll 2
+                    for (int i = 0; i < len; ++i) {
+                        const float4 kn = K[i + 1];
+                        float4 Tn, h, l;
+                        Tn.x = fmaf(fmaf(kc4.x, r2.x, kc4.y), T1.x, kc4.z * T2.x);
+                        Tn.y = fmaf(fmaf(kc4.x, r2.y, kc4.y), T1.y, kc4.z * T2.y);
+                        Tn.z = fmaf(fmaf(kc4.x, r2.z, kc4.y), T1.z, kc4.z * T2.z);
+                        Tn.w = fmaf(fmaf(kc4.x, r2.w, kc4.y), T1.w, kc4.z * T2.w);
+                        split4_fast(Tn, h, l);
+                        const int r = row0 + i, k4 = r & 3;
+                        unsigned char *rowp = tb + (size_t)r * 128 + kh * 16;
+                        *reinterpret_cast<float4 *>(rowp + (k4 << 5)) = h;          // unit 0 ^ k4
+                        *reinterpret_cast<float4 *>(rowp + ((k4 ^ 1) << 5)) = l;    // unit 1 ^ k4
+                        T2 = T1;
+                        T1 = Tn;
+                        kc4 = kn;
+                    }
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(tfull0 + 8 * ts);
+                mbar_arrive(gfree0 + 8 * gs);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+// Sum of the partial folds over the column sets of every kind, 8-point Walsh-Hadamard transform of the 8 class values, the 8 mirror
+// images of both row groups -> the maps.  One CTA per chunk of the launch's range; thread = (row group A|B, map, k).
+struct KindSets { int first[5]; };
+__global__ void __launch_bounds__(2 * SNV * KC) k_unfold_tile(const float *__restrict__ Fs, long long gbeg, long long glen, KindSets ks,
+                                                              int nvol, int N, int H, float *__restrict__ vol) {
+    const int CPR = (H + KC - 1) / KC;
+    const long long rel = blockIdx.x, chunk = gbeg + rel;
+    ChunkPos p;
+    chunk_pos(chunk, CPR, H, p);
+    const int tid = threadIdx.x;
+    const int k = tid % KC, b = (tid / KC) % SNV, set = tid / (KC * SNV);
+    const int kk = p.kc * KC + k, k2 = N - 1 - kk;
+    const int ri = set ? p.jp : p.ip, rj = set ? p.ip : p.jp;
+    const int i2 = N - 1 - ri, j2 = N - 1 - rj;
+    const bool live = b < nvol && kk < H && (set == 0 || p.paired);
+    if (!live) return;
+    float v[8];
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+        const int reim = c8 >> 2, kind = ((((c8 >> 1) & 1) ^ reim) << 1) | (c8 & 1);
+        float s = 0.0f;
+        for (int q = ks.first[kind]; q < ks.first[kind + 1]; ++q)
+            s += Fs[((((size_t)q * glen + rel) * 2 + set) * SM_ROWS + (reim * SNV + b)) * KC + k];
+        v[c8] = s;
+    }
+    wht8(v);
+    float *vb = vol + (size_t)b * N * N * N;
+#pragma unroll
+    for (int img = 0; img < 8; ++img) {
+        const bool sy = img & 4, sx = img & 2, sz = img & 1;
+        const bool dup = (sy && i2 == ri) || (sx && j2 == rj) || (sz && k2 == kk);
+        if (!dup) vb[((size_t)(sy ? i2 : ri) * N + (sx ? j2 : rj)) * N + (sz ? k2 : kk)] = v[img];
+    }
+}
+
+}  // namespace z3d

@@ -25,7 +25,7 @@ class Plan:
                  "batched_min", "batched_row_groups", "batched_row_groups_wide", "batched_wide_min", "batched_rounds",
                  "batched_rounds_wide", "stream_state", "stream_sets", "stream_splits", "stream_rows16", "stream_table_mib",
                  "chunks", "gen", "gen_sets", "gen_splits", "gen_cols", "gen_slots", "gen_min", "tables_level", "gen_maxcols",
-                 "gen2", "gen2_sets", "gen2_splits", "gen2_slots")
+                 "gen2", "gen2_sets", "gen2_splits", "gen2_slots", "synth", "synth_min")
 
     def __init__(self, order: int, dim: int, device: int | None = None):
         if not torch.cuda.is_available():
@@ -40,6 +40,8 @@ class Plan:
         self.num_radial = self._L.z3d_num_radial(self.order)
         self.half = (self.dim + 1) // 2
         self._ws = None
+        self._ws_synth = None
+        self._info = None
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -51,8 +53,8 @@ class Plan:
 
     # ------------------------------------------------------------------ helpers
     def info(self) -> dict:
-        arr = (ctypes.c_int * 36)()
-        _lib.check(self._L.z3d_plan_info(self._h, arr, 36))
+        arr = (ctypes.c_int * 38)()
+        _lib.check(self._L.z3d_plan_info(self._h, arr, 38))
         return dict(zip(self.INFO_KEYS, list(arr)))
 
     def prepare_tables(self, level: int, max_bytes: int = 0) -> int:
@@ -150,16 +152,40 @@ class Plan:
                                                    self._stream(stream)))
         return out[0] if single else out
 
-    def reconstruct(self, moments: torch.Tensor, pairs=None, out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
-        """complex64 CUDA ``[B, num_moments]`` -> float32 ``[B, N, N, N]`` (planes outside ``pairs`` untouched)."""
+    def reconstruct(self, moments: torch.Tensor, pairs=None, out: torch.Tensor | None = None, stream=None,
+                    batched: bool | None = None) -> torch.Tensor:
+        """complex64 CUDA ``[B, num_moments]`` -> float32 ``[B, N, N, N]`` (planes outside ``pairs`` untouched).
+        ``batched``: None = whole maps of a batch of at least ``info()["synth_min"]`` go through the tensor-core synthesis kernel
+        in tiles of 64 (``z3d_reconstruct_batched``), everything else through the per-map kernel; True / False force one of them."""
         single = moments.dim() == 1
         m = moments.unsqueeze(0) if single else moments
         m = self._check_moments(m, "reconstruct")
         B, N = m.shape[0], self.dim
+        lo, hi = self._pairs(pairs)
+        if self._info is None:
+            self._info = self.info()
+        if batched is None:   # whole maps of a large enough batch: tiles of 64 on the tensor cores (z3d_reconstruct_batched)
+            batched = bool(self._info["synth"]) and B >= self._info["synth_min"] and (lo, hi) == (0, self.half)
+        if batched:
+            if (lo, hi) != (0, self.half):
+                raise ValueError("reconstruct: the tensor-core path synthesises whole maps (pairs must cover the box)")
+            if out is None:
+                out = torch.empty((B, N, N, N), dtype=torch.float32, device=m.device)
+            need = int(self._L.z3d_reconstruct_batched_workspace_bytes(self._h, B))
+            if need == 0:
+                raise _lib.Z3DError(_lib.ERR_INVALID, "reconstruct: no tensor-core synthesis layout for this plan")
+            if self._ws_synth is None or self._ws_synth.numel() < need:
+                self._ws_synth = None
+                self._ws_synth = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
+            if stream is not None:
+                self._ws_synth.record_stream(stream)
+                out.record_stream(stream)
+            _lib.check(self._L.z3d_reconstruct_batched(self._h, _ptr(m), B, _ptr(out), _ptr(self._ws_synth), self._ws_synth.numel(),
+                                                       self._stream(stream)))
+            return out[0] if single else out
         if out is None:
             out = torch.zeros((B, N, N, N), dtype=torch.float32, device=m.device)
         ws = self._workspace(B, stream)
-        lo, hi = self._pairs(pairs)
         _lib.check(self._L.z3d_reconstruct(self._h, _ptr(m), B, lo, hi, _ptr(out), _ptr(ws), ws.numel(),
                                            self._stream(stream)))
         return out[0] if single else out
