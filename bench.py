@@ -376,6 +376,21 @@ def run_gpu_arm(args):
     plan.reconstruct(moms[:1])
     rec_kernel_ms = plan.last_kernel_ms()
 
+    # ---- batched reconstruction on the tensor cores (z3d_reconstruct_batched): one tile of 64 moment sets
+    recb = None
+    if info.get("synth"):
+        m64 = out[:TILE].contiguous()
+        rbuf = plan.reconstruct(m64, batched=True)
+        recb_ms = maxreduce(_time_ms(lambda: plan.reconstruct(m64, batched=True, out=rbuf), 3, warm=1))
+        recb = {"ms_per_64_maps": recb_ms, "maps_per_s_per_gpu": TILE / (recb_ms * 1e-3), "kernel": "z3d::k_synth_gen + z3d::k_unfold_tile",
+                "speedup_over_per_map_kernel": rec_ms * TILE / recb_ms,
+                "rel_l2_vs_per_map_kernel_map_5": _rel(rbuf[5].cpu().numpy(), plan.reconstruct(m64[5:6], batched=False)[0].cpu().numpy())}
+        if rank == 0:
+            want = oracle.reconstruct(m64[9].cpu().numpy(), DIM, ORDER, oracle.EXACT, rows=(40, 42))
+            recb["rel_l2_vs_f64_oracle_map_9_planes_40_41"] = _rel(rbuf[9, 40:42].cpu().numpy(), want)
+        del rbuf
+        torch.cuda.empty_cache()
+
     configs = other_configs(rank, world, local, maxreduce, oracle)
 
     if rank == 0:
@@ -474,6 +489,7 @@ def run_gpu_arm(args):
                                                    "(posted NVLink stores, one flag per block and source rank) and sums the "
                                                    "rows that arrived locally in rank order"},
             "reconstructions_per_s_per_gpu": 1e3 / rec_ms,
+            "reconstruct_batched_tensor_core": recb,
         }
         emit(line)
     if world > 1:

@@ -473,6 +473,72 @@ def test_reconstruction_at_full_size_against_oracle_planes(plans, oracle_mod):
         assert rel_l2(got, want) < TOL_EXACT
 
 
+@pytest.mark.parametrize("name,count", [("d16_o10", 13), ("d15_o8", 70), ("d32_o20", 16), ("d20_o25", 12), ("c1_d64_o50", 14)])
+def test_batched_synthesis_vs_reference_golden(plans, name, count):
+    """Tensor-core batched synthesis (z3d_reconstruct_batched: tiles of 64 moment sets, zm:2642-2715 for an ensemble): the golden
+    moment sets of the reference, scaled copies and sums of them as one batch; every map against the reference's own reconstruction
+    (linearity of zm:2596-2614) and against the per-map kernel."""
+    g = golden(name)
+    order, dim = int(g["order"]), int(g["dim"])
+    P = plans(order, dim)
+    assert P.info()["synth"] == 1
+    base = np.stack([np.asarray(m, np.complex64) for m in g["moments"]])
+    rng = np.random.default_rng(5)
+    w = rng.normal(size=(count, base.shape[0])).astype(np.float32)
+    w[: base.shape[0]] = np.eye(base.shape[0], dtype=np.float32)
+    moms = (w.astype(np.complex64) @ base).astype(np.complex64)
+    rec = P.reconstruct(dev(moms), batched=True).cpu().numpy()
+    assert rec.shape == (count, dim, dim, dim) and np.isfinite(rec).all()
+    want = np.tensordot(w, np.stack(g["recon"]).astype(np.float64), axes=1)
+    for i in range(count):
+        assert rel_l2(rec[i], want[i]) < TOL_MAP
+    per_map = P.reconstruct(dev(moms[:3]), batched=False).cpu().numpy()
+    for i in range(3):
+        assert rel_l2(rec[i], per_map[i]) < TOL_EXACT
+    again = P.reconstruct(dev(moms), batched=True).cpu().numpy()
+    assert np.array_equal(rec, again)                                   # deterministic
+    auto = P.reconstruct(dev(moms)).cpu().numpy()                       # count >= synth_min: routed to the tensor cores by default
+    assert np.array_equal(auto, rec) == (count >= P.info()["synth_min"])
+
+
+def test_batched_synthesis_at_full_size_against_oracle_planes(plans, oracle_mod):
+    """128^3 / order 50, 70 moment sets (a full tile + a ragged one) through the tensor-core synthesis kernel: planes of maps of
+    both tiles against the float64 oracle's zm:2596-2614, and the 96^3 / order 60 layout (143 column sets)."""
+    for name, count, planes in (("c3_d128_o50", 70, (0, 40, 64, 127)), ("c5_d96_o60", 20, (1, 47, 80))):
+        g = golden(name)
+        order, dim = int(g["order"]), int(g["dim"])
+        P = plans(order, dim)
+        m0 = np.asarray(g["moments"][0], np.complex64)
+        rng = np.random.default_rng(11)
+        moms = np.stack([m0 * np.float32(s) for s in rng.uniform(0.5, 1.5, size=count)]).astype(np.complex64)
+        moms[1::2] = np.conj(moms[1::2])                                # conjugated moments = the map mirrored in y: a different map
+        rec = P.reconstruct(dev(moms), batched=True)
+        for b in (0, 1, count - 1):
+            r = rec[b].cpu().numpy()
+            scale = np.sqrt(np.mean(r.astype(np.float64) ** 2))
+            for p_ in planes:
+                want = oracle_mod.reconstruct(moms[b], dim, order, oracle_mod.EXACT, rows=(p_, p_ + 1))[0]
+                assert np.sqrt(np.mean((r[p_] - want) ** 2)) / scale < TOL_EXACT_BATCHED
+        del rec
+
+
+def test_batched_synthesis_error_paths(plans):
+    from zernike3d_b200 import _lib
+
+    P = plans(10, 16)
+    m = torch.zeros((16, P.num_moments), dtype=torch.complex64, device="cuda")
+    with pytest.raises(ValueError):
+        P.reconstruct(m, pairs=(0, 4), batched=True)                    # whole maps only
+    L = _lib.lib()
+    need = L.z3d_reconstruct_batched_workspace_bytes(P._h, 16)
+    assert need > 0
+    ws = torch.empty(need - 1, dtype=torch.uint8, device="cuda")
+    out = torch.empty((16, 16, 16, 16), dtype=torch.float32, device="cuda")
+    rc = L.z3d_reconstruct_batched(P._h, m.data_ptr(), 16, out.data_ptr(), ws.data_ptr(), ws.numel(), None)
+    assert rc == _lib.ERR_WORKSPACE
+    assert L.z3d_reconstruct_batched(P._h, None, 16, out.data_ptr(), ws.data_ptr(), ws.numel(), None) == _lib.ERR_INVALID
+
+
 def test_host_buffer_api_matches_device_api(plans):
     order, dim = 50, 64
     P = plans(order, dim)
