@@ -261,6 +261,12 @@ def test_latent_scaling_on_device_matches_apply_scaling(plans, tmp_path):
     for i, z in enumerate((0, 7, 39)):
         one = P.reconstruct(dev(M.apply_scaling(z_ind=z))).cpu().numpy()
         assert rel_l2(maps[i], one) < 1e-6
+    # a trajectory of 40 latent coordinates in one launch: routed to the tensor-core synthesis kernel (>= synth_min maps)
+    traj = Z.ReconstructLatents(z_indices=list(range(40)), write=False)
+    assert traj.shape[0] == 40 and 40 >= P.info()["synth_min"] and P.info()["synth"] == 1
+    for z in (0, 7, 39):
+        one = P.reconstruct(dev(M.apply_scaling(z_ind=z)), batched=False).cpu().numpy()
+        assert rel_l2(traj[z], one) < TOL_EXACT
     names = Z.ReconstructLatents(latents=lat[:2])
     assert [n.rsplit("_", 1)[1] for n in names] == ["p0.mrc", "p1.mrc"] and all(__import__("os").path.exists(n) for n in names)
     assert len(jobs) == P.num_moments

@@ -170,10 +170,10 @@ class ZernikeSpherical:
             out.append(name)
         return out
 
-    def ReconstructLatents(self, z_indices=None, latents=None, batch=8, write=True):
+    def ReconstructLatents(self, z_indices=None, latents=None, batch=64, write=True):
         """Maps at MANY latent coordinates of a 3DVA bundle (trajectories / ensembles): the scaling
         ``Omega = [1, z] . Omega_dims`` (zm:78-95) and the synthesis both run on the device, ``batch`` coordinates per
-        launch.  ``z_indices`` picks rows of the bundle's ``latents`` (file names ``<out>_scaled_<z>.mrc`` as zm:2708-2714
+        launch (64 = one tile of the tensor-core synthesis kernel, which ``Plan.reconstruct`` takes from 12 maps on).  ``z_indices`` picks rows of the bundle's ``latents`` (file names ``<out>_scaled_<z>.mrc`` as zm:2708-2714
         writes for a single ``--z_ind``); ``latents`` gives coordinates directly (``<out>_scaled_p<i>.mrc``).
         Returns the file names (``write=True``) or the float32 maps ``[P, N, N, N]``."""
         import torch
