@@ -355,6 +355,8 @@ def run_gpu_arm(args):
     if world > 1:
         from zernike3d_b200.plan import PeerComm
 
+        dist.broadcast(onev, src=0)   # the work-sharded path spreads ONE volume: every rank holds rank 0's volume 0 (the ranks' batches differ)
+
         comm = PeerComm(plan, batch_max=1)
         ref_m = zdist.decompose_work_sharded(plan.decompose, onev, deterministic=True)
         for _ in range(3):
@@ -362,10 +364,11 @@ def run_gpu_arm(args):
         barrier()
         fused_ok = bool(torch.equal(torch.view_as_real(got), torch.view_as_real(ref_m))) and comm.error() == 0
         fused_got = got[0].cpu().numpy()
-        fused_ms = maxreduce(_time_ms(lambda: plan.decompose_allreduce(onev, comm), 20, warm=0))
+        barrier()   # the ranks enter the timed loop together: every call is a rendezvous, a late rank would be charged to the others
+        fused_ms = maxreduce(_time_ms(lambda: plan.decompose_allreduce(onev, comm), 50, warm=3))
     sharded = zdist.decompose_work_sharded(plan.decompose, onev)
     barrier()
-    sharded_ms = maxreduce(_time_ms(lambda: zdist.decompose_work_sharded(plan.decompose, onev), 20, warm=3))
+    sharded_ms = maxreduce(_time_ms(lambda: zdist.decompose_work_sharded(plan.decompose, onev), 50, warm=3))
     single_ms = _time_ms(lambda: plan.decompose(onev), 20)
     plan.decompose(onev)
     single_kernel_ms = plan.last_kernel_ms()
