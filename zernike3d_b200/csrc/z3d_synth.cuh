@@ -147,6 +147,9 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
             if (elect_one()) {
                 const unsigned dl = dlo0 + (unsigned)ts * step;
                 int prev_panel = -1;
+#ifdef Z3D_SYNTH_DEBUG
+                if (!(P.dbg & 1))
+#endif
                 for (int g = 0; g < nseg; ++g) {
                     const int j = T.seg_panel[g], off = T.seg_off[g], cols = T.seg_cols[g];
                     const unsigned d = tmem + dcol0 + (unsigned)((bank * npanel + j) * 32);
@@ -234,6 +237,9 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
             if (t >= G_DG) g_wait_relaxed(gfree0 + 8 * gs, (unsigned)(t / G_DG - 1) & 1);
             float *slot = reinterpret_cast<float *>(gring + (size_t)gs * P.gslot_bytes);
             float *seeds = slot + 40;
+#ifdef Z3D_SYNTH_DEBUG
+            if (P.dbg & 8) { __syncwarp(); if (lane == 0) mbar_arrive(gfull0 + 8 * gs); continue; }
+#endif
             if (lane < 8) slot[lane] = r2;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
@@ -295,6 +301,9 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
             float FA[8], FB[8];
 #pragma unroll
             for (int v = 0; v < 8; ++v) FA[v] = FB[v] = 0.0f;
+#ifdef Z3D_SYNTH_DEBUG
+            if (!(P.dbg & 4))
+#endif
             for (int j = 0; j < npanel; ++j) {
                 float d[16], e[8];
                 const unsigned ta = lane0 + dcol0 + (unsigned)((bank * npanel + j) * 32);
@@ -340,7 +349,11 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
             if (tuse) g_wait_relaxed(tfree0 + 8 * ts, (tuse - 1) & 1);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
+#ifdef Z3D_SYNTH_DEBUG
+                const int len = (P.dbg & 2) ? 0 : task[q].y;
+#else
                 const int len = task[q].y;
+#endif
                 if (len > 0) {
                     const int kh = task[q].w >> 16, srow = task[q].w & 0xffff;
                     const float4 s4 = *reinterpret_cast<const float4 *>(slot + 40 + srow * 8 + 4 * kh);
