@@ -1143,7 +1143,7 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
                 }
                 for (int i = 1; i < hg.nsets; ++i) ordered = ordered && hg.tabs[i].kind >= hg.tabs[i - 1].kind;
                 // its T ring: 128 B per row (the one MN-major layout the tensor core reads for 32-bit operands), in place of the fold rings
-                pl->synth_off_t = (g.off_f + 1023) / 1024 * 1024;
+                pl->synth_off_t = (g.off_g + sy_gring_bytes(g.gslot_bytes) + 1024 + 1023) / 1024 * 1024;   // seed ring, 1 KB of barriers, T ring
                 pl->synth_slots = std::min(G_NS_MAX, ((int)prop.sharedMemPerBlockOptin - pl->synth_off_t - 1024) / (2 * g.tslot_bytes));
                 pl->synth_smem = pl->synth_off_t + 1024 + pl->synth_slots * 2 * g.tslot_bytes;
                 pl->synth = ordered && pl->synth_slots >= G_NTT && !(getenv("Z3D_SYNTH") && atoi(getenv("Z3D_SYNTH")) == 0);
@@ -1611,10 +1611,10 @@ extern "C" int z3d_reconstruct(const z3d_plan *pl, const float *d_moments, int b
 }
 
 // ---- tensor-core batched synthesis (z3d_synth.cuh): tiles of 64 maps, the chunk list in parts so that the partial folds of a part
-// (sets x chunks x 8 KB) stay below ~1.5 GB
+// (sets x chunks x 8 KB) stay below ~3.5 GB (every part is a launch that reloads O' into tensor memory: 3 parts at 128^3 / order 50)
 static int synth_parts(const z3d_plan *pl) {
     const double bytes = (double)pl->devg2.nsets * (double)pl->b_chunks * 2.0 * SM_ROWS * KC * sizeof(float);
-    return std::max(1, (int)std::ceil(bytes / 1.5e9));
+    return std::max(1, (int)std::ceil(bytes / 3.5e9));
 }
 static size_t synth_part_floats(const z3d_plan *pl) {
     const long long per = (pl->b_chunks + synth_parts(pl) - 1) / synth_parts(pl) + 1;

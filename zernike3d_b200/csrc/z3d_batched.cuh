@@ -25,6 +25,9 @@
 //                  the row group's slice of Q) two chunks ahead; 31 producer warps turn them into the T and a operand
 //                  panels (K-major core-matrix layout of the shared-memory descriptors); the same thread issues the MMAs.
 #pragma once
+#if defined(Z3D_SYNTH_DEBUG) || defined(Z3D_WAIT_DIAG)
+#include <cstdio>
+#endif
 #include "z3d_kernels.cuh"
 
 namespace z3d {
@@ -113,6 +116,9 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
                      : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
         if (ok) return;
     }
+#if defined(Z3D_SYNTH_DEBUG) || defined(Z3D_WAIT_DIAG)
+    if ((threadIdx.x & 31) == 0) printf("wait timed out: block (%d,%d) warp %d barrier @%u parity %u\n", blockIdx.x, blockIdx.y, threadIdx.x >> 5, mbar, parity);
+#endif
     __trap();  // never hang the device: a lost completion is a bug, fail the launch instead
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

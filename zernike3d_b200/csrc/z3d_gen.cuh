@@ -134,6 +134,9 @@ __device__ __forceinline__ void g_wait_relaxed(unsigned mbar, unsigned parity) {
         __nanosleep(G_SLEEP_NS);
 #endif
     }
+#if defined(Z3D_SYNTH_DEBUG) || defined(Z3D_WAIT_DIAG)
+    if ((threadIdx.x & 31) == 0) printf("relaxed wait timed out: block (%d,%d) warp %d barrier @%u parity %u\n", blockIdx.x, blockIdx.y, threadIdx.x >> 5, mbar, parity);
+#endif
     __trap();
 }
 

@@ -63,6 +63,15 @@ __global__ void k_prepare_synth(const float *__restrict__ moments, const int *__
 }
 
 // Partial folds of the launch's chunk range: Fs[set][chunk - gbeg][row group A|B][row = (re|im, map)][k]
+//
+// A pipeline STEP is a PAIR of chunks (A = 2s, B = 2s + 1 of the CTA's chunk range): a T row of 128 bytes holds [T_hi A | T_hi B | T_lo A |
+// T_lo B] (8 voxels each), so that per K-step of 8 moment rows ONE N = 32 MMA with O'_hi and ONE N = 16 MMA with O'_lo (-> T_hi A, T_hi B)
+// serve both chunks: half the MMAs and half the hand-overs per voxel of a chunk-per-step pipeline (the MMAs are issue bound at N <= 32).
+// Accumulators: 48 tensor-memory columns per panel, ONE bank - the issuing warp waits per panel until the epilogue team of the previous
+// pair has read that panel (`dfree[j]`), so it re-fills panel 0 while the later panels are still being read.
+constexpr int SY_DG = 24;          // depth of the geometry / seed ring: a common multiple of the agents' chunk strides (3 seed warps, 4 T teams x 2
+                                   // chunks, 2 epilogue teams x 2 chunks), see the note on parity waits in z3d_gen.cuh
+__host__ __device__ constexpr int sy_gring_bytes(int gslot_bytes) { return SY_DG * gslot_bytes; }
 __global__ void __launch_bounds__(GNT, 1)
 k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, int maxcols, int off_ts, int NS, int part, int nparts,
             float *__restrict__ Fs) {
@@ -70,19 +79,20 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int set = blockIdx.y, split = blockIdx.x;
     GenTabs &T = *reinterpret_cast<GenTabs *>(smem + G_OFF_TABS);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + G_OFF_BAR);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + P.off_g + sy_gring_bytes(P.gslot_bytes));   // 1 KB behind the seed ring
     float2 *gds = reinterpret_cast<float2 *>(smem + G_OFF_GD);
     float4 *rks = reinterpret_cast<float4 *>(smem + P.off_rk);
-    // (the analysis kernel's fold rings are not needed: the T ring starts there, on a 1024-byte boundary of the shared-memory WINDOW - the
-    // swizzle of the MN-major layout works on absolute address bits)
+    // (the analysis kernel's fold rings are not needed: the seed ring is twice as deep and the T ring follows it, on a 1024-byte boundary
+    // of the shared-memory WINDOW - the swizzle of the MN-major layout works on absolute address bits)
     off_ts = (int)(((smem_u32(smem) + (unsigned)off_ts + 1023u) & ~1023u) - smem_u32(smem));
     unsigned char *gring = smem + P.off_g, *tring = smem + off_ts;
     const int slot_bytes = 2 * P.tslot_bytes;   // 128 B per row
-    // barriers: gfull[DG] gfree[DG] tfull[NS_MAX] tfree[NS_MAX] dfull[2] dfree[2] oready
-    const unsigned gfull0 = smem_u32(bars), gfree0 = gfull0 + 8 * G_DG, tfull0 = gfree0 + 8 * G_DG, tfree0 = tfull0 + 8 * G_NS_MAX,
-                   dfull0 = tfree0 + 8 * G_NS_MAX, dfree0 = dfull0 + 16, oready = dfree0 + 16;
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + G_OFF_BAR + 8 * (2 * G_DG + 2 * G_NS_MAX + 5));
-    static_assert(8 * (2 * G_DG + 2 * G_NS_MAX + 5) + 4 <= G_OFF_GD - G_OFF_BAR, "barrier block");
+    // barriers: gfull[SY_DG] gfree[SY_DG] tfull[NS_MAX] tfree[NS_MAX] dfree[G_PANELS] dfull[2] oready  (dfull per epilogue team: a parity wait
+    // is only meaningful on a barrier whose every phase the waiter consumes)
+    const unsigned gfull0 = smem_u32(bars), gfree0 = gfull0 + 8 * SY_DG, tfull0 = gfree0 + 8 * SY_DG, tfree0 = tfull0 + 8 * G_NS_MAX,
+                   dfree0 = tfree0 + 8 * G_NS_MAX, dfull0 = dfree0 + 8 * G_PANELS, oready = dfull0 + 16;
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(bars + (2 * SY_DG + 2 * G_NS_MAX + G_PANELS + 3));
+    static_assert(8 * (2 * SY_DG + 2 * G_NS_MAX + G_PANELS + 3) + 4 <= 1024, "barrier block");
     for (int i = tid; i < (int)(sizeof(GenTabs) / 4); i += GNT)
         reinterpret_cast<int *>(smem + G_OFF_TABS)[i] = reinterpret_cast<const int *>(P.tabs + set)[i];
     for (int i = tid; i < P.gd_bytes / 8; i += GNT) gds[i] = P.gd[(size_t)set * (P.gd_bytes / 8) + i];
@@ -90,9 +100,14 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
     for (int i = tid; i < NS * slot_bytes / 16; i += GNT) reinterpret_cast<float4 *>(tring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     const int ncols = T.ncols, nseg = T.nseg, npanel = T.npanel;
+#if defined(Z3D_SYNTH_DEBUG) || defined(Z3D_WAIT_DIAG)
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+        printf("synth: bars @%u gfree0 %u tfull0 %u tfree0 %u dfree0 %u dfull0 %u oready %u | ncols %d nseg %d npanel %d NS %d\n", gfull0, gfree0, tfull0, tfree0, dfree0,
+               dfull0, oready, T.ncols, T.nseg, T.npanel, NS);
+#endif
     for (int i = tid; i < P.rk_bytes / 16; i += GNT) rks[i] = P.rk[(size_t)T.lpar * (P.rk_bytes / 16) + i];
     if (tid == 0) {
-        for (int i = 0; i < G_DG; ++i) {
+        for (int i = 0; i < SY_DG; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gfull0 + 8 * i));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(gfree0 + 8 * i));   // 4 warps of a T team + 4 of an epilogue team
         }
@@ -100,10 +115,9 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(tfull0 + 8 * i));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tfree0 + 8 * i));
         }
-        for (int i = 0; i < 2; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dfull0 + 8 * i));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(dfree0 + 8 * i));
-        }
+        for (int i = 0; i < G_PANELS; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(dfree0 + 8 * i));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dfull0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dfull0 + 8));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(oready));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -116,13 +130,14 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
     __syncthreads();
     tc_fence_after();
     const unsigned tmem = *tmem_slot;
-    const unsigned dcol0 = 512u - 64u * (unsigned)npanel;   // accumulator banks: dcol0 + (bank * npanel + j) * 32 (+ 16: the O'_lo product)
+    const unsigned dcol0 = 512u - 48u * (unsigned)npanel;   // accumulators of panel j: dcol0 + 48 j (+ 32: the O'_lo product, 16 columns)
 
     const int CPR = (P.H + KC - 1) / KC;
     const long long total = (long long)analysis_items(0, P.H, P.H) * CPR;
     const long long gbeg = total * part / nparts, glen = total * (part + 1) / nparts - gbeg;
     const long long cbeg = gbeg + glen * split / P.nsplits, cend = gbeg + glen * (split + 1) / P.nsplits;
     const int nchunk = (int)(cend - cbeg);
+    const int npair = (nchunk + 1) / 2;
 
     if (nchunk == 0) {
         // nothing to do
@@ -131,18 +146,16 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
         const unsigned dlo0 = (smem_u32(smem) + (unsigned)off_ts) >> 4;
         // MN-major B for 32-bit operands exists in ONE shared-memory layout (scripts/experiments/tc_probe6.cu: every other layout type
         // makes the tensor core read zeros): SWIZZLE_128B_BASE32B - rows of 128 B (32 elements along MN), 4 rows = one 512-byte atom,
-        // the 32-byte unit c of row k stored at unit c ^ (k % 4), atoms along K `SBO` apart.  A T row holds [T_hi 8 voxels | T_lo 8
-        // voxels | unused]; an MMA reads 2 atoms = 8 rows.
+        // the 32-byte unit c of row k stored at unit c ^ (k % 4), atoms along K `SBO` apart; an MMA reads 2 atoms = 8 rows.
         const unsigned long long dhi = ((unsigned long long)(512 >> 4) << 32) | (1ull << 46) | ((unsigned long long)(512 >> 4) << 16) | (1ull << 61);
-        const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((16u >> 3) << 17) | ((unsigned)(SM_ROWS >> 4) << 24);
+        const unsigned idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((unsigned)(SM_ROWS >> 4) << 24);
+        const unsigned idesc32 = idesc0 | ((32u >> 3) << 17), idesc16 = idesc0 | ((16u >> 3) << 17);
         const unsigned step = (unsigned)(slot_bytes >> 4);
         int ts = 0;
         unsigned tuse = 0;
         mbar_wait(oready, 0);
-        for (int t = 0; t < nchunk; ++t) {
-            const int bank = t & 1;
+        for (int s = 0; s < npair; ++s) {
             mbar_wait(tfull0 + 8 * ts, tuse & 1);
-            if (t >= 2) mbar_wait(dfree0 + 8 * bank, (unsigned)(t / 2 - 1) & 1);   // the epilogue has read chunk t - 2 out of this bank
             tc_fence_after();
             if (elect_one()) {
                 const unsigned dl = dlo0 + (unsigned)ts * step;
@@ -152,25 +165,32 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
 #endif
                 for (int g = 0; g < nseg; ++g) {
                     const int j = T.seg_panel[g], off = T.seg_off[g], cols = T.seg_cols[g];
-                    const unsigned d = tmem + dcol0 + (unsigned)((bank * npanel + j) * 32);
+                    const unsigned d = tmem + dcol0 + (unsigned)(j * 48);
                     const bool fresh = j != prev_panel;
                     prev_panel = j;
+                    if (fresh && s > 0) {   // the epilogue team of pair s - 1 has read this panel
+                        mbar_wait(dfree0 + 8 * j, (unsigned)(s - 1) & 1);
+                        tc_fence_after();
+                    }
                     for (int ks = 0; ks < cols; ks += 8) {
                         const unsigned r = (unsigned)(off + ks);
                         const unsigned long long b = dhi | (unsigned long long)(dl + r * 8u);   // row r -> atom r / 4 -> 512 B each
                         const unsigned acc = (fresh && ks == 0) ? 0u : 1u;
-                        umma_tf32_ts(d, tmem + r, b, idesc, acc);                            // O'_hi x [T_hi | T_lo]
-                        umma_tf32_ts(d + 16, tmem + (unsigned)ncols + r, b, idesc, acc);     // O'_lo x [T_hi | (T_lo: not used)]
+                        umma_tf32_ts(d, tmem + r, b, idesc32, acc);                              // O'_hi x [T_hi A | T_hi B | T_lo A | T_lo B]
+                        umma_tf32_ts(d + 32, tmem + (unsigned)ncols + r, b, idesc16, acc);       // O'_lo x [T_hi A | T_hi B]
                     }
                 }
+#ifdef Z3D_SYNTH_DEBUG
+                if ((P.dbg & 1) && s > 0) for (int j = 0; j < npanel; ++j) mbar_wait(dfree0 + 8 * j, (unsigned)(s - 1) & 1);
+#endif
                 umma_commit(tfree0 + 8 * ts);
-                umma_commit(dfull0 + 8 * bank);
+                umma_commit(dfull0 + 8 * (s & 1));
             }
             __syncwarp();
             if (++ts == NS) { ts = 0; ++tuse; }
         }
     } else if (warp < G_WARP_SEED0 + G_NSEEDW) {
-        // ---- seed warps: as in k_decompose_gen (lane = (panel j = lane / 8 (+ 4 in the second pass), voxel k = lane % 8))
+        // ---- seed warps: as in k_decompose_gen (lane = (panel j = lane / 8 (+ 4 in the second pass), voxel k = lane % 8)), one chunk at a time
         const int sw = warp - G_WARP_SEED0, k = lane & 7;
         int pm[2], ppz[2], pnl[2], psoff[2], pgd[2];
 #pragma unroll
@@ -233,8 +253,8 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
             const double z = (kk < P.H) ? P.side[kk] : 0.0;
             const double zz = z * z;
             const float r2 = (float)(rho2 + zz), z4 = (float)(4.0 * zz), r4 = r2 * r2;
-            const int gs = t % G_DG;
-            if (t >= G_DG) g_wait_relaxed(gfree0 + 8 * gs, (unsigned)(t / G_DG - 1) & 1);
+            const int gs = t % SY_DG;
+            if (t >= SY_DG) g_wait_relaxed(gfree0 + 8 * gs, (unsigned)(t / SY_DG - 1) & 1);
             float *slot = reinterpret_cast<float *>(gring + (size_t)gs * P.gslot_bytes);
             float *seeds = slot + 40;
 #ifdef Z3D_SYNTH_DEBUG
@@ -272,7 +292,7 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
     } else if (warp < G_WARP_A0) {
         // (no role)
     } else if (warp < G_WARP_T0) {
-        // ---- epilogue teams: thread = row (re|im, map b) = tensor-memory lane; chunk t -> team t & 1 = accumulator bank
+        // ---- epilogue teams: thread = row (re|im, map b) = tensor-memory lane; pair s -> team s & 1
         const int team = (warp - G_WARP_A0) >> 2, quarter = warp & 3;
         const int row = quarter * 32 + lane, reim = row >> 6;
         const unsigned lane0 = tmem + ((unsigned)(32 * quarter) << 16);
@@ -292,46 +312,57 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
             __syncwarp();
             if (lane == 0) mbar_arrive(oready);
         }
-        const int bank = team;
-        for (int t = team; t < nchunk; t += 2) {
-            const int gs = t % G_DG;
-            const float *slot = reinterpret_cast<const float *>(gring + (size_t)gs * P.gslot_bytes);
-            g_wait_relaxed(dfull0 + 8 * bank, (unsigned)(t / 2) & 1);
+        for (int s = team; s < npair; s += 2) {
+            const int t0 = 2 * s;
+            const bool hasB = t0 + 1 < nchunk;
+            g_wait_relaxed(dfull0 + 8 * team, (unsigned)(s >> 1) & 1);
             tc_fence_after();
-            float FA[8], FB[8];
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                if (half == 1 && !hasB) break;
+                const int t = t0 + half, gs = t % SY_DG;
+                const float *slot = reinterpret_cast<const float *>(gring + (size_t)gs * P.gslot_bytes);
+                const bool last_read = half == 1 || !hasB;   // this pass is the last to read the accumulators: release them panel by panel
+                float FA[8], FB[8];
 #pragma unroll
-            for (int v = 0; v < 8; ++v) FA[v] = FB[v] = 0.0f;
+                for (int v = 0; v < 8; ++v) FA[v] = FB[v] = 0.0f;
 #ifdef Z3D_SYNTH_DEBUG
-            if (!(P.dbg & 4))
+                if (!(P.dbg & 4))
 #endif
-            for (int j = 0; j < npanel; ++j) {
-                float d[16], e[8];
-                const unsigned ta = lane0 + dcol0 + (unsigned)((bank * npanel + j) * 32);
-                tmem_ld16(ta, d);
-                tmem_ld8(ta + 16, e);
-                tmem_ld_wait();
-                const float tA = slot[8 + j * 4 + reim], tB = slot[8 + j * 4 + 2 + reim];
+                for (int j = 0; j < npanel; ++j) {
+                    float dh[8], dl[8], e[8];
+                    const unsigned ta = lane0 + dcol0 + (unsigned)(j * 48 + half * 8);
+                    tmem_ld8(ta, dh);            // O'_hi T_hi
+                    tmem_ld8(ta + 16, dl);       // O'_hi T_lo
+                    tmem_ld8(ta + 32, e);        // O'_lo T_hi
+                    tmem_ld_wait();
+                    if (last_read) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(dfree0 + 8 * j);
+                    }
+                    const float tA = slot[8 + j * 4 + reim], tB = slot[8 + j * 4 + 2 + reim];
 #pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    const float o = (d[8 + v] + e[v]) + d[v];   // small terms first
-                    FA[v] = fmaf(tA, o, FA[v]);
-                    FB[v] = fmaf(tB, o, FB[v]);
+                    for (int v = 0; v < 8; ++v) {
+                        const float o = (dl[v] + e[v]) + dh[v];   // small terms first
+                        FA[v] = fmaf(tA, o, FA[v]);
+                        FB[v] = fmaf(tB, o, FB[v]);
+                    }
                 }
+#ifdef Z3D_SYNTH_DEBUG
+                if ((P.dbg & 4) && last_read) { tc_fence_before(); __syncwarp(); if (lane == 0) for (int j = 0; j < npanel; ++j) mbar_arrive(dfree0 + 8 * j); }
+#endif
+                __syncwarp();
+                if (lane == 0) mbar_arrive(gfree0 + 8 * gs);
+                float *dst = Fs + (((size_t)set * glen + (size_t)(cbeg + t - gbeg)) * 2) * (SM_ROWS * KC) + (size_t)row * KC;
+                *reinterpret_cast<float4 *>(dst) = make_float4(FA[0], FA[1], FA[2], FA[3]);
+                *reinterpret_cast<float4 *>(dst + 4) = make_float4(FA[4], FA[5], FA[6], FA[7]);
+                *reinterpret_cast<float4 *>(dst + SM_ROWS * KC) = make_float4(FB[0], FB[1], FB[2], FB[3]);
+                *reinterpret_cast<float4 *>(dst + SM_ROWS * KC + 4) = make_float4(FB[4], FB[5], FB[6], FB[7]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(dfree0 + 8 * bank);
-                mbar_arrive(gfree0 + 8 * gs);
-            }
-            float *dst = Fs + (((size_t)set * glen + (size_t)(cbeg + t - gbeg)) * 2) * (SM_ROWS * KC) + (size_t)row * KC;
-            *reinterpret_cast<float4 *>(dst) = make_float4(FA[0], FA[1], FA[2], FA[3]);
-            *reinterpret_cast<float4 *>(dst + 4) = make_float4(FA[4], FA[5], FA[6], FA[7]);
-            *reinterpret_cast<float4 *>(dst + SM_ROWS * KC) = make_float4(FB[0], FB[1], FB[2], FB[3]);
-            *reinterpret_cast<float4 *>(dst + SM_ROWS * KC + 4) = make_float4(FB[4], FB[5], FB[6], FB[7]);
         }
     } else {
-        // ---- T teams: as in k_decompose_gen
+        // ---- T teams: the recurrences of k_decompose_gen, for the two chunks of a pair; pair s -> team s & 3 -> T slot s % NS
         const int team = (warp - G_WARP_T0) >> 2, u = ((warp - team + 1) & 3) * 32 + lane;
         int4 task[2];
 #pragma unroll
@@ -339,45 +370,51 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
             const int i = u + 128 * q;
             task[q] = i < T.ntask ? P.tasks[(size_t)set * G_TASKS + i] : make_int4(0, 0, 0, 0);
         }
-        for (int t = team; t < nchunk; t += G_NTT) {
-            const int ts = t % NS;
-            const unsigned tuse = (unsigned)(t / NS);
-            const int gs = t % G_DG;
-            const float *slot = reinterpret_cast<const float *>(gring + (size_t)gs * P.gslot_bytes);
+        for (int s = team; s < npair; s += G_NTT) {
+            const int ts = s % NS;
+            const unsigned tuse = (unsigned)(s / NS);
+            const int t0 = 2 * s;
+            const bool hasB = t0 + 1 < nchunk;
             unsigned char *tb = tring + (size_t)ts * slot_bytes;
-            g_wait_relaxed(gfull0 + 8 * gs, (unsigned)(t / G_DG) & 1);
+            g_wait_relaxed(gfull0 + 8 * (t0 % SY_DG), (unsigned)(t0 / SY_DG) & 1);
+            if (hasB) g_wait_relaxed(gfull0 + 8 * ((t0 + 1) % SY_DG), (unsigned)((t0 + 1) / SY_DG) & 1);
             if (tuse) g_wait_relaxed(tfree0 + 8 * ts, (tuse - 1) & 1);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                if (half == 1 && !hasB) break;   // (the B units keep an earlier pair's finite values; the epilogue ignores those columns)
+                const float *slot = reinterpret_cast<const float *>(gring + (size_t)((t0 + half) % SY_DG) * P.gslot_bytes);
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < 2; ++q) {
 #ifdef Z3D_SYNTH_DEBUG
-                const int len = (P.dbg & 2) ? 0 : task[q].y;
+                    const int len = (P.dbg & 2) ? 0 : task[q].y;
 #else
-                const int len = task[q].y;
+                    const int len = task[q].y;
 #endif
-                if (len > 0) {
-                    const int kh = task[q].w >> 16, srow = task[q].w & 0xffff;
-                    const float4 s4 = *reinterpret_cast<const float4 *>(slot + 40 + srow * 8 + 4 * kh);
-                    const float4 r2 = *reinterpret_cast<const float4 *>(slot + 4 * kh);
-                    const float4 *K = rks + task[q].z;
-                    const int row0 = task[q].x;
-                    float4 T1 = make_float4(0.f, 0.f, 0.f, 0.f), T2 = s4;
-                    float4 kc4 = K[0];
+                    if (len > 0) {
+                        const int kh = task[q].w >> 16, srow = task[q].w & 0xffff;
+                        const float4 s4 = *reinterpret_cast<const float4 *>(slot + 40 + srow * 8 + 4 * kh);
+                        const float4 r2 = *reinterpret_cast<const float4 *>(slot + 4 * kh);
+                        const float4 *K = rks + task[q].z;
+                        const int row0 = task[q].x;
+                        float4 T1 = make_float4(0.f, 0.f, 0.f, 0.f), T2 = s4;
+                        float4 kc4 = K[0];
 #pragma unroll 2
-                    for (int i = 0; i < len; ++i) {
-                        const float4 kn = K[i + 1];
-                        float4 Tn, h, l;
-                        Tn.x = fmaf(fmaf(kc4.x, r2.x, kc4.y), T1.x, kc4.z * T2.x);
-                        Tn.y = fmaf(fmaf(kc4.x, r2.y, kc4.y), T1.y, kc4.z * T2.y);
-                        Tn.z = fmaf(fmaf(kc4.x, r2.z, kc4.y), T1.z, kc4.z * T2.z);
-                        Tn.w = fmaf(fmaf(kc4.x, r2.w, kc4.y), T1.w, kc4.z * T2.w);
-                        split4_fast(Tn, h, l);
-                        const int r = row0 + i, k4 = r & 3;
-                        unsigned char *rowp = tb + (size_t)r * 128 + kh * 16;
-                        *reinterpret_cast<float4 *>(rowp + (k4 << 5)) = h;          // unit 0 ^ k4
-                        *reinterpret_cast<float4 *>(rowp + ((k4 ^ 1) << 5)) = l;    // unit 1 ^ k4
-                        T2 = T1;
-                        T1 = Tn;
-                        kc4 = kn;
+                        for (int i = 0; i < len; ++i) {
+                            const float4 kn = K[i + 1];
+                            float4 Tn, h, l;
+                            Tn.x = fmaf(fmaf(kc4.x, r2.x, kc4.y), T1.x, kc4.z * T2.x);
+                            Tn.y = fmaf(fmaf(kc4.x, r2.y, kc4.y), T1.y, kc4.z * T2.y);
+                            Tn.z = fmaf(fmaf(kc4.x, r2.z, kc4.y), T1.z, kc4.z * T2.z);
+                            Tn.w = fmaf(fmaf(kc4.x, r2.w, kc4.y), T1.w, kc4.z * T2.w);
+                            split4_fast(Tn, h, l);
+                            const int r = row0 + i, k4 = r & 3;
+                            unsigned char *rowp = tb + (size_t)r * 128 + kh * 16;
+                            *reinterpret_cast<float4 *>(rowp + ((half ^ k4) << 5)) = h;          // unit (T_hi A | T_hi B) ^ k4
+                            *reinterpret_cast<float4 *>(rowp + (((2 + half) ^ k4) << 5)) = l;    // unit (T_lo A | T_lo B) ^ k4
+                            T2 = T1;
+                            T1 = Tn;
+                            kc4 = kn;
+                        }
                     }
                 }
             }
@@ -385,7 +422,8 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(tfull0 + 8 * ts);
-                mbar_arrive(gfree0 + 8 * gs);
+                mbar_arrive(gfree0 + 8 * (t0 % SY_DG));
+                if (hasB) mbar_arrive(gfree0 + 8 * ((t0 + 1) % SY_DG));
             }
         }
     }
