@@ -162,6 +162,9 @@ class Plan:
         m = self._check_moments(m, "reconstruct")
         B, N = m.shape[0], self.dim
         lo, hi = self._pairs(pairs)
+        if out is not None and (out.dtype != torch.float32 or not out.is_cuda or out.device.index != self.device or not out.is_contiguous()
+                                or tuple(out.shape) != (B, N, N, N)):
+            raise ValueError(f"reconstruct: out must be a contiguous float32 tensor [{B},{N},{N},{N}] on cuda:{self.device}")
         if self._info is None:
             self._info = self.info()
         if batched is None:   # whole maps of a large enough batch: tiles of 64 on the tensor cores (z3d_reconstruct_batched)
