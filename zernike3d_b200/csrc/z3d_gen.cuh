@@ -18,13 +18,15 @@
 //   * MMAs are issued by ONE converged warp through elect.sync (back-to-back UTCHMMA on uniform registers: 23 clk or the tensor
 //     pipe's N / 2 per instruction; an `if (lane == 0)` region costs 64-72 clk per MMA - scripts/experiments/tc_probe4.cu).
 //
-// Roles (32 warps, no block barrier in the loop):
-//   warps 0-3     issue the MMAs of chunk t (segments g = w mod 4) when its T block (tfull) and a panels (afull) are ready; commit -> tfree, afree
-//   warps 4-6     seed warps (chunks t = w-4 mod 3): per chunk the float64 geometry (z, rho^2), the row trig of the set's m
+// Roles (28 warps = 896 threads, no block barrier in the loop):
+//   warp 0        issues the MMAs of chunk t when its T block (tfull) and a panels (afull) are ready; ONE commit per chunk -> tfree (T slot and a-panel slot)
+//   warps 1-3     seed warps (chunks t = w-1 mod 3): per chunk the float64 geometry (z, rho^2), the row trig of the set's m
 //                 (float64 complex powering like exp(1j m phi), zm:2297) and the seeds S_lm of every (panel, l, voxel) -> G ring
-//   warps 8-15    two a-panel teams (chunk t -> team t & 1 -> tensor-memory slot t & 1); a thread owns one row (re/im, volume)
-//   warps 16-31   four T teams (chunk t -> team t & 3); a thread owns up to two (chain, k half) tasks, 4 voxels each
-// All 24 producer warps (8-31) read the accumulators back every BFLUSH_CHUNKS chunks (see z3d_batched.cuh for why).
+//   warps 4-11    two a-panel teams (chunk t -> team t & 1 -> tensor-memory slot t & 1); a thread owns one row (re/im, volume)
+//   warps 12-27   four T teams (chunk t -> team t & 3); a thread owns up to two (chain, k half) tasks, 4 voxels each
+// All 24 producer warps (4-27) read the accumulators back every BFLUSH_CHUNKS chunks (see z3d_batched.cuh for why).
+// (With G_NISS_ > 1 or G_NALT_ = 2 - compile-time variants that were measured and lost - there are more issuing warps, the producers
+// start at warp 8 and the CTA has 32 warps.)
 #pragma once
 #include "z3d_stream.cuh"
 
@@ -72,8 +74,8 @@ constexpr int G_NISSW = G_NISS * G_NALT;  // issuing warps in all
 constexpr int G_WARP_SEED0 = G_NISSW;
 constexpr int G_WARP_A0 = (G_NISSW + G_NSEEDW + 3) / 4 * 4;
 constexpr int G_WARP_T0 = G_WARP_A0 + 4 * G_NAT;
-constexpr int G_NWARP = G_WARP_T0 + 4 * G_NTT;     // 32
-constexpr int GNT = G_NWARP * 32;                  // 1024 threads
+constexpr int G_NWARP = G_WARP_T0 + 4 * G_NTT;     // 28 (32 with more than one issuing warp)
+constexpr int GNT = G_NWARP * 32;                  // 896 threads
 constexpr int G_SEG_PER_ISS = G_SEGS / G_NISS;
 static_assert(G_NWARP - G_WARP_A0 == S_NPW && G_WARP_A0 % 4 == 0 && G_SEGS % G_NISS == 0, "s_flush deals the read-back units over the 24 producer warps");
 constexpr int G_OFF_TABS = 0;      // GenTabs
