@@ -83,3 +83,30 @@ def test_streamed_T_column_set_layout_for_every_order(sms):
         assert widest <= 512 and rows16 % 16 == 0 and maxpanel <= 4 and maxseg <= 8
     assert L.z3d_stream_layout(50, 148, out, 8) == 0 and list(out)[:4] == [1, 37, 4, 12832]
     assert L.z3d_stream_layout(-1, 148, out, 8) == _lib.ERR_INVALID
+
+
+@pytest.mark.parametrize("sms", [148, 132])
+def test_table_free_column_set_layouts_for_every_order(sms):
+    """Host-only planner of the table-free tensor-core kernels (z3d_gen.cuh / z3d_synth.cuh): for every supported order the column sets of
+    the analysis layout (ntile 1) and of the two-tile layout the batched synthesis runs on (ntile 2) pass the planner's self-check
+    (segments of 16..256 columns laid end to end, accumulators + a-panel slots within the 512 tensor-memory columns - which for ntile 2
+    implies the synthesis kernel's budget 2 ncols + 48 npanel <= 512 -, every chain row written exactly twice, every moment owning one
+    column) and sets x splits fit the device."""
+    L = _lib.lib()
+    out = (ctypes.c_int * 11)()
+    for ntile in (1, 2):
+        for order in range(0, 75):
+            assert L.z3d_gen_layout_tiles(order, sms, ntile, out, 11) == 0
+            ok, nsets, nsplits, cols_all, widest, bad, maxpanel, maxseg, maxtask, maxseed, est = list(out)
+            if not ok:          # orders whose sets outnumber the SMs fall back to the per-volume kernels
+                assert order > 40
+                continue
+            nmom = L.z3d_num_moments(order)
+            assert bad == 0, (ntile, order, list(out))
+            assert 1 <= nsets * nsplits <= sms and cols_all >= nmom and cols_all % 16 == 0
+            assert widest % 16 == 0 and widest <= 512 // ntile and 1 <= maxpanel <= 8 and maxseg <= 8 and maxtask <= 256
+            if ntile == 2:
+                assert 2 * widest + 48 * 1 <= 512
+    assert L.z3d_gen_layout_tiles(50, 148, 1, out, 11) == 0 and list(out)[:3] == [1, 37, 4]
+    assert L.z3d_gen_layout_tiles(50, 148, 2, out, 11) == 0 and list(out)[:3] == [1, 74, 2]
+    assert L.z3d_gen_layout_tiles(50, 148, 3, out, 11) == _lib.ERR_INVALID
