@@ -385,7 +385,17 @@ def run_gpu_arm(args):
         m64 = out[:TILE].contiguous()
         rbuf = plan.reconstruct(m64, batched=True)
         recb_ms = maxreduce(_time_ms(lambda: plan.reconstruct(m64, batched=True, out=rbuf), 3, warm=1))
+        import ctypes
+
+        from zernike3d_b200 import _lib as zlib
+
+        lay = (ctypes.c_int * 11)()
+        zlib.lib().z3d_gen_layout_tiles(ORDER, info["sms"], 2, lay, 11)     # host-only planner query: columns over all sets of the layout
+        # executed tensor work per tile: per K-step of 8 moment rows and PAIR of chunks one N = 32 and one N = 16 MMA (M 128, K 8)
+        synth_flops = (lay[3] / 8.0) * (2.0 * 128 * 8 * (32 + 16)) * (info["chunks"] / 2.0)
         recb = {"ms_per_64_maps": recb_ms, "maps_per_s_per_gpu": TILE / (recb_ms * 1e-3), "kernel": "z3d::k_synth_gen + z3d::k_unfold_tile",
+                "executed_tensor_flops_per_tile": synth_flops, "executed_tflops": synth_flops / (recb_ms * 1e-3) / 1e12,
+                "partial_fold_bytes_per_tile": float(info["gen2_sets"]) * info["chunks"] * 2 * 128 * 8 * 4,
                 "speedup_over_per_map_kernel": rec_ms * TILE / recb_ms,
                 "rel_l2_vs_per_map_kernel_map_5": _rel(rbuf[5].cpu().numpy(), plan.reconstruct(m64[5:6], batched=False)[0].cpu().numpy())}
         if rank == 0:
