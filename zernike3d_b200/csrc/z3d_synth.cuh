@@ -317,48 +317,71 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
             const bool hasB = t0 + 1 < nchunk;
             g_wait_relaxed(dfull0 + 8 * team, (unsigned)(s >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                if (half == 1 && !hasB) break;
-                const int t = t0 + half, gs = t % SY_DG;
-                const float *slot = reinterpret_cast<const float *>(gring + (size_t)gs * P.gslot_bytes);
-                const bool last_read = half == 1 || !hasB;   // this pass is the last to read the accumulators: release them panel by panel
-                float FA[8], FB[8];
+            // panel by panel, both chunks of the pair: a panel's accumulators are released to the issuing warp as soon as they have
+            // been read (the next pair's MMAs of that panel wait for exactly this), the class sums of the two chunks stay in registers
+            const int gsA = t0 % SY_DG, gsB = (t0 + 1) % SY_DG;
+            const float *slotA = reinterpret_cast<const float *>(gring + (size_t)gsA * P.gslot_bytes);
+            const float *slotB = reinterpret_cast<const float *>(gring + (size_t)gsB * P.gslot_bytes);
+            float FA0[8], FB0[8], FA1[8], FB1[8];
 #pragma unroll
-                for (int v = 0; v < 8; ++v) FA[v] = FB[v] = 0.0f;
+            for (int v = 0; v < 8; ++v) FA0[v] = FB0[v] = FA1[v] = FB1[v] = 0.0f;
 #ifdef Z3D_SYNTH_DEBUG
-                if (!(P.dbg & 4))
+            if (!(P.dbg & 4))
 #endif
-                for (int j = 0; j < npanel; ++j) {
-                    float dh[8], dl[8], e[8];
-                    const unsigned ta = lane0 + dcol0 + (unsigned)(j * 48 + half * 8);
-                    tmem_ld8(ta, dh);            // O'_hi T_hi
-                    tmem_ld8(ta + 16, dl);       // O'_hi T_lo
-                    tmem_ld8(ta + 32, e);        // O'_lo T_hi
-                    tmem_ld_wait();
-                    if (last_read) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(dfree0 + 8 * j);
-                    }
-                    const float tA = slot[8 + j * 4 + reim], tB = slot[8 + j * 4 + 2 + reim];
+            for (int j = 0; j < npanel; ++j) {
+                const unsigned ta = lane0 + dcol0 + (unsigned)(j * 48);
+                float dh[8], dl[8], e[8];
+                tmem_ld8(ta, dh);            // O'_hi T_hi, chunk A
+                tmem_ld8(ta + 16, dl);       // O'_hi T_lo
+                tmem_ld8(ta + 32, e);        // O'_lo T_hi
+                tmem_ld_wait();
+                {
+                    const float tA = slotA[8 + j * 4 + reim], tB = slotA[8 + j * 4 + 2 + reim];
 #pragma unroll
                     for (int v = 0; v < 8; ++v) {
                         const float o = (dl[v] + e[v]) + dh[v];   // small terms first
-                        FA[v] = fmaf(tA, o, FA[v]);
-                        FB[v] = fmaf(tB, o, FB[v]);
+                        FA0[v] = fmaf(tA, o, FA0[v]);
+                        FB0[v] = fmaf(tB, o, FB0[v]);
                     }
                 }
-#ifdef Z3D_SYNTH_DEBUG
-                if ((P.dbg & 4) && last_read) { tc_fence_before(); __syncwarp(); if (lane == 0) for (int j = 0; j < npanel; ++j) mbar_arrive(dfree0 + 8 * j); }
-#endif
+                if (hasB) {
+                    tmem_ld8(ta + 8, dh);        // chunk B
+                    tmem_ld8(ta + 24, dl);
+                    tmem_ld8(ta + 40, e);
+                    tmem_ld_wait();
+                }
+                tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(gfree0 + 8 * gs);
-                float *dst = Fs + (((size_t)set * glen + (size_t)(cbeg + t - gbeg)) * 2) * (SM_ROWS * KC) + (size_t)row * KC;
-                *reinterpret_cast<float4 *>(dst) = make_float4(FA[0], FA[1], FA[2], FA[3]);
-                *reinterpret_cast<float4 *>(dst + 4) = make_float4(FA[4], FA[5], FA[6], FA[7]);
-                *reinterpret_cast<float4 *>(dst + SM_ROWS * KC) = make_float4(FB[0], FB[1], FB[2], FB[3]);
-                *reinterpret_cast<float4 *>(dst + SM_ROWS * KC + 4) = make_float4(FB[4], FB[5], FB[6], FB[7]);
+                if (lane == 0) mbar_arrive(dfree0 + 8 * j);
+                if (hasB) {
+                    const float tA = slotB[8 + j * 4 + reim], tB = slotB[8 + j * 4 + 2 + reim];
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const float o = (dl[v] + e[v]) + dh[v];
+                        FA1[v] = fmaf(tA, o, FA1[v]);
+                        FB1[v] = fmaf(tB, o, FB1[v]);
+                    }
+                }
+            }
+#ifdef Z3D_SYNTH_DEBUG
+            if (P.dbg & 4) { tc_fence_before(); __syncwarp(); if (lane == 0) for (int j = 0; j < npanel; ++j) mbar_arrive(dfree0 + 8 * j); }
+#endif
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(gfree0 + 8 * gsA);
+                if (hasB) mbar_arrive(gfree0 + 8 * gsB);
+            }
+            float *dst = Fs + (((size_t)set * glen + (size_t)(cbeg + t0 - gbeg)) * 2) * (SM_ROWS * KC) + (size_t)row * KC;
+            *reinterpret_cast<float4 *>(dst) = make_float4(FA0[0], FA0[1], FA0[2], FA0[3]);
+            *reinterpret_cast<float4 *>(dst + 4) = make_float4(FA0[4], FA0[5], FA0[6], FA0[7]);
+            *reinterpret_cast<float4 *>(dst + SM_ROWS * KC) = make_float4(FB0[0], FB0[1], FB0[2], FB0[3]);
+            *reinterpret_cast<float4 *>(dst + SM_ROWS * KC + 4) = make_float4(FB0[4], FB0[5], FB0[6], FB0[7]);
+            if (hasB) {
+                dst += 2 * SM_ROWS * KC;   // the next chunk
+                *reinterpret_cast<float4 *>(dst) = make_float4(FA1[0], FA1[1], FA1[2], FA1[3]);
+                *reinterpret_cast<float4 *>(dst + 4) = make_float4(FA1[4], FA1[5], FA1[6], FA1[7]);
+                *reinterpret_cast<float4 *>(dst + SM_ROWS * KC) = make_float4(FB1[0], FB1[1], FB1[2], FB1[3]);
+                *reinterpret_cast<float4 *>(dst + SM_ROWS * KC + 4) = make_float4(FB1[4], FB1[5], FB1[6], FB1[7]);
             }
         }
     } else {
