@@ -395,7 +395,7 @@ def run_gpu_arm(args):
         synth_flops = (lay[3] / 8.0) * (2.0 * 128 * 8 * (32 + 16)) * (info["chunks"] / 2.0)
         recb = {"ms_per_64_maps": recb_ms, "maps_per_s_per_gpu": TILE / (recb_ms * 1e-3), "kernel": "z3d::k_synth_gen + z3d::k_unfold_tile",
                 "executed_tensor_flops_per_tile": synth_flops, "executed_tflops": synth_flops / (recb_ms * 1e-3) / 1e12,
-                "partial_fold_bytes_per_tile": float(info["gen2_sets"]) * info["chunks"] * 2 * 128 * 8 * 4,
+                "partial_fold_bytes_per_tile": float(info["synth_partial_slots"]) * info["chunks"] * 2 * 128 * 8 * 4,
                 "speedup_over_per_map_kernel": rec_ms * TILE / recb_ms,
                 "rel_l2_vs_per_map_kernel_map_5": _rel(rbuf[5].cpu().numpy(), plan.reconstruct(m64[5:6], batched=False)[0].cpu().numpy())}
         if rank == 0:

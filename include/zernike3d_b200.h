@@ -74,7 +74,8 @@ int z3d_plan_destroy(z3d_plan *plan);
  * sets, 28 depth of the shared-memory T ring, 29 smallest batch routed to it, 30 basis-table level in use (z3d_plan_prepare_tables),
  * 31 columns of the widest set; its two-tile layout (while more than 64 volumes are left, 128 volumes share every generated
  * T block): 32 in use by the analysis (opt-in), 33 column sets, 34 splits, 35 depth of the T ring;
- * tensor-core batched synthesis (z3d_reconstruct_batched): 36 available, 37 smallest batch of maps worth routing to it. */
+ * tensor-core batched synthesis (z3d_reconstruct_batched): 36 available, 37 smallest batch of maps worth routing to it,
+ * 38 stored class-partial slots (column sets, minus one per cluster pair of sets of the same kind). */
 int z3d_plan_info(const z3d_plan *plan, int *info, int n_info);
 
 /* Host-only planner query (no device needed): the column-set layout of the streamed-T batched analysis kernel for `order` on a

@@ -123,7 +123,9 @@ struct z3d_plan {
     int synth_min = 12;          // smallest batch of maps routed to it by the host layer (a tile costs the same whatever it holds)
     int synth_maxcols = 0, synth_off_t = 0, synth_slots = 0, synth_smem = 0;
     int *d_synth_colsrc = nullptr;   // [sets][maxcols] -> moment index or -1
-    KindSets synth_kinds{};
+    KindSets synth_kinds{};         // first partial-fold SLOT of every kind
+    int *d_synth_pairinfo = nullptr; // [sets]: slot << 1 | exchange with the cluster partner (set ^ 1, same kind)
+    int synth_nslots = 0;
     // reduce / prepare tables
     int *d_src = nullptr;        // [2*nmom]  pass*SLOT_WORDS + word
     double *d_scale = nullptr;   // [nmom]    coeff(n) * kappa_lm
@@ -1137,13 +1139,25 @@ extern "C" int z3d_plan_create(int order, int dim, int device, z3d_plan **out) {
                 for (int mu = 0; mu < pl->nmom; ++mu) colsrc[(size_t)hg.colmap[mu].x * pl->synth_maxcols + hg.colmap[mu].y] = mu;
                 UP(colsrc, pl->d_synth_colsrc)
                 bool ordered = true;
+                for (int i = 1; i < hg.nsets; ++i) ordered = ordered && hg.tabs[i].kind >= hg.tabs[i - 1].kind;
+                // CTAs run in clusters of two column sets (2p, 2p + 1): where both are of the same kind, the odd one sends its class
+                // partials to the even one through distributed shared memory and only the sum is stored (one slot for the pair)
+                std::vector<int> pairinfo(hg.nsets, 0), slot_kind;
+                const bool pairs_on = !(getenv("Z3D_SYNTH_PAIRS") && atoi(getenv("Z3D_SYNTH_PAIRS")) == 0);
+                for (int i = 0; i < hg.nsets; ++i) {
+                    const bool second = (i & 1) && pairs_on && hg.tabs[i].kind == hg.tabs[i - 1].kind;
+                    const bool first = !(i & 1) && pairs_on && i + 1 < hg.nsets && hg.tabs[i].kind == hg.tabs[i + 1].kind;
+                    if (!second) slot_kind.push_back(hg.tabs[i].kind);
+                    pairinfo[i] = (((int)slot_kind.size() - 1) << 1) | ((first || second) ? 1 : 0);
+                }
+                pl->synth_nslots = (int)slot_kind.size();
                 for (int k = 0, i = 0; k <= 4; ++k) {
-                    while (i < hg.nsets && hg.tabs[i].kind < k) ++i;
+                    while (i < pl->synth_nslots && slot_kind[i] < k) ++i;
                     pl->synth_kinds.first[k] = i;
                 }
-                for (int i = 1; i < hg.nsets; ++i) ordered = ordered && hg.tabs[i].kind >= hg.tabs[i - 1].kind;
+                UP(pairinfo, pl->d_synth_pairinfo)
                 // its T ring: 128 B per row (the one MN-major layout the tensor core reads for 32-bit operands), in place of the fold rings
-                pl->synth_off_t = (g.off_g + sy_gring_bytes(g.gslot_bytes) + 1024 + 1023) / 1024 * 1024;   // seed ring, 1 KB of barriers, T ring
+                pl->synth_off_t = (g.off_g + sy_gring_bytes(g.gslot_bytes) + 1024 + SY_XBUF_BYTES + 1023) / 1024 * 1024;   // seed ring, 1 KB of barriers, exchange buffers, T ring
                 pl->synth_slots = std::min(G_NS_MAX, ((int)prop.sharedMemPerBlockOptin - pl->synth_off_t - 1024) / (2 * g.tslot_bytes));
                 pl->synth_smem = pl->synth_off_t + 1024 + pl->synth_slots * 2 * g.tslot_bytes;
                 pl->synth = ordered && pl->synth_slots >= G_NTT && !(getenv("Z3D_SYNTH") && atoi(getenv("Z3D_SYNTH")) == 0);
@@ -1301,7 +1315,7 @@ extern "C" int z3d_plan_destroy(z3d_plan *pl) {
 extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
     if (!pl || !info) return fail(Z3D_ERR_INVALID, "z3d_plan_info: NULL argument");
     const long long t_mb = pl->stream ? (long long)((double)pl->b_chunks * (double)pl->devs.trec * 4.0 / 1048576.0) : 0;
-    const int v[38] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
+    const int v[39] = {pl->order, pl->dim, pl->nmom, pl->npass, pl->npass * pl->nsplit, NT, TS, pl->smem_bytes,
                        KC, pl->num_sms, pl->useful_acc, pl->padded_acc,
                        pl->batched ? pl->batched_min : 0, pl->devb[0].ngroups, pl->devb[1].ngroups, pl->batched ? pl->batched_wide : 0,
                        pl->devb[0].nrounds, pl->devb[1].nrounds,
@@ -1316,9 +1330,9 @@ extern "C" int z3d_plan_info(const z3d_plan *pl, int *info, int n) {
                        pl->tables_level, pl->g_maxcols,
                        // its two-tile layout (128 volumes per generated T block): 32 available, 33 column sets, 34 splits, 35 T-ring slots
                        pl->gen2 ? 1 : 0, pl->devg2.nsets, pl->devg2.nsplits, pl->devg2.nslots,
-                       // tensor-core batched synthesis: 36 available, 37 smallest batch of maps the host layer routes to it
-                       pl->synth ? 1 : 0, pl->synth ? pl->synth_min : 0};
-    for (int i = 0; i < n && i < 38; ++i) info[i] = v[i];
+                       // tensor-core batched synthesis: 36 available, 37 smallest batch of maps the host layer routes to it, 38 partial-fold slots
+                       pl->synth ? 1 : 0, pl->synth ? pl->synth_min : 0, pl->synth ? pl->synth_nslots : 0};
+    for (int i = 0; i < n && i < 39; ++i) info[i] = v[i];
     return Z3D_OK;
 }
 
@@ -1613,12 +1627,12 @@ extern "C" int z3d_reconstruct(const z3d_plan *pl, const float *d_moments, int b
 // ---- tensor-core batched synthesis (z3d_synth.cuh): tiles of 64 maps, the chunk list in parts so that the partial folds of a part
 // (sets x chunks x 8 KB) stay below ~3.5 GB (every part is a launch that reloads O' into tensor memory: 3 parts at 128^3 / order 50)
 static int synth_parts(const z3d_plan *pl) {
-    const double bytes = (double)pl->devg2.nsets * (double)pl->b_chunks * 2.0 * SM_ROWS * KC * sizeof(float);
+    const double bytes = (double)pl->synth_nslots * (double)pl->b_chunks * 2.0 * SM_ROWS * KC * sizeof(float);
     return std::max(1, (int)std::ceil(bytes / 3.5e9));
 }
 static size_t synth_part_floats(const z3d_plan *pl) {
     const long long per = (pl->b_chunks + synth_parts(pl) - 1) / synth_parts(pl) + 1;
-    return (size_t)pl->devg2.nsets * (size_t)per * 2 * SM_ROWS * KC;
+    return (size_t)pl->synth_nslots * (size_t)per * 2 * SM_ROWS * KC;
 }
 static size_t synth_op_floats(const z3d_plan *pl) { return (size_t)pl->devg2.nsets * SM_ROWS * 2 * pl->synth_maxcols; }
 
@@ -1651,7 +1665,22 @@ extern "C" int z3d_reconstruct_batched(const z3d_plan *pl, const float *d_moment
         for (int part = 0; part < nparts; ++part) {
             const long long gbeg = pl->b_chunks * part / nparts, glen = pl->b_chunks * (part + 1) / nparts - gbeg;
             if (glen <= 0) continue;
-            k_synth_gen<<<dim3(dp.nsplits, dp.nsets), GNT, pl->synth_smem, st>>>(dp, Op, pl->synth_maxcols, pl->synth_off_t, pl->synth_slots, part, nparts, Fs);
+            {   // clusters of two CTAs along the set dimension (an odd number of sets gets one padding CTA)
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(dp.nsplits, (dp.nsets + 1) / 2 * 2);
+                cfg.blockDim = dim3(GNT);
+                cfg.dynamicSmemBytes = pl->synth_smem;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = 1;
+                attr[0].val.clusterDim.y = 2;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, k_synth_gen, dp, (const float *)Op, pl->synth_maxcols, pl->synth_off_t, pl->synth_slots, part, nparts,
+                                            (const int *)pl->d_synth_pairinfo, Fs));
+            }
             CUDA_TRY(cudaGetLastError());
             k_unfold_tile<<<(unsigned)glen, 2 * SNV * KC, 0, st>>>(Fs, gbeg, glen, pl->synth_kinds, nb, pl->dim, pl->H, d_vol + (size_t)b0 * N3);
             CUDA_TRY(cudaGetLastError());

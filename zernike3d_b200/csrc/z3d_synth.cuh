@@ -62,6 +62,44 @@ __global__ void k_prepare_synth(const float *__restrict__ moments, const int *__
     }
 }
 
+
+// ---- thread-block cluster helpers (pairs of CTAs that hold two column sets of the same kind add their class partials through
+// distributed shared memory before they are stored)
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned mapa_shared(unsigned addr, unsigned rank) {   // the same shared-memory offset in CTA `rank` of the cluster
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(unsigned raddr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(unsigned raddr) {   // arrive on an mbarrier of another CTA of the cluster, releasing this thread's writes
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned mbar, unsigned parity) {   // local mbarrier, acquire at cluster scope (remote writes become visible)
+#pragma unroll 1
+    for (int it = 0; it < (1 << 24); ++it) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (ok) return;
+        __nanosleep(64);
+    }
+#if defined(Z3D_SYNTH_DEBUG) || defined(Z3D_WAIT_DIAG)
+    if ((threadIdx.x & 31) == 0) printf("cluster wait timed out: block (%d,%d) warp %d barrier @%u parity %u\n", blockIdx.x, blockIdx.y, threadIdx.x >> 5, mbar, parity);
+#endif
+    __trap();
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr int SY_XBUF_BYTES = 2 * SM_ROWS * 32 * 4;   // exchange buffers of the two epilogue teams: [team][8 x float4][row]
+
 // Partial folds of the launch's chunk range: Fs[set][chunk - gbeg][row group A|B][row = (re|im, map)][k]
 //
 // A pipeline STEP is a PAIR of chunks (A = 2s, B = 2s + 1 of the CTA's chunk range): a T row of 128 bytes holds [T_hi A | T_hi B | T_lo A |
@@ -74,12 +112,17 @@ constexpr int SY_DG = 24;          // depth of the geometry / seed ring: a commo
 __host__ __device__ constexpr int sy_gring_bytes(int gslot_bytes) { return SY_DG * gslot_bytes; }
 __global__ void __launch_bounds__(GNT, 1)
 k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, int maxcols, int off_ts, int NS, int part, int nparts,
-            float *__restrict__ Fs) {
+            const int *__restrict__ pairinfo /* [sets]: slot << 1 | exchange with the cluster partner */, float *__restrict__ Fs) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int set = blockIdx.y, split = blockIdx.x;
+    if (set >= P.nsets) return;   // (padding CTA of an odd number of sets: its cluster partner does not exchange)
+    const int pinfo = pairinfo[set], slot_id = pinfo >> 1;
+    const bool exch = pinfo & 1;
+    const unsigned crank = cluster_ctarank();   // 0: adds the partner's class partials and stores the sum; 1: sends its own
     GenTabs &T = *reinterpret_cast<GenTabs *>(smem + G_OFF_TABS);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + P.off_g + sy_gring_bytes(P.gslot_bytes));   // 1 KB behind the seed ring
+    float *xbuf = reinterpret_cast<float *>(smem + P.off_g + sy_gring_bytes(P.gslot_bytes) + 1024);   // exchange buffers, SY_XBUF_BYTES
     float2 *gds = reinterpret_cast<float2 *>(smem + G_OFF_GD);
     float4 *rks = reinterpret_cast<float4 *>(smem + P.off_rk);
     // (the analysis kernel's fold rings are not needed: the seed ring is twice as deep and the T ring follows it, on a 1024-byte boundary
@@ -90,9 +133,9 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
     // barriers: gfull[SY_DG] gfree[SY_DG] tfull[NS_MAX] tfree[NS_MAX] dfree[G_PANELS] dfull[2] oready  (dfull per epilogue team: a parity wait
     // is only meaningful on a barrier whose every phase the waiter consumes)
     const unsigned gfull0 = smem_u32(bars), gfree0 = gfull0 + 8 * SY_DG, tfull0 = gfree0 + 8 * SY_DG, tfree0 = tfull0 + 8 * G_NS_MAX,
-                   dfree0 = tfree0 + 8 * G_NS_MAX, dfull0 = dfree0 + 8 * G_PANELS, oready = dfull0 + 16;
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(bars + (2 * SY_DG + 2 * G_NS_MAX + G_PANELS + 3));
-    static_assert(8 * (2 * SY_DG + 2 * G_NS_MAX + G_PANELS + 3) + 4 <= 1024, "barrier block");
+                   dfree0 = tfree0 + 8 * G_NS_MAX, dfull0 = dfree0 + 8 * G_PANELS, oready = dfull0 + 16, xfull0 = oready + 8, xfree0 = xfull0 + 16;
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(bars + (2 * SY_DG + 2 * G_NS_MAX + G_PANELS + 7));
+    static_assert(8 * (2 * SY_DG + 2 * G_NS_MAX + G_PANELS + 7) + 4 <= 1024, "barrier block");
     for (int i = tid; i < (int)(sizeof(GenTabs) / 4); i += GNT)
         reinterpret_cast<int *>(smem + G_OFF_TABS)[i] = reinterpret_cast<const int *>(P.tabs + set)[i];
     for (int i = tid; i < P.gd_bytes / 8; i += GNT) gds[i] = P.gd[(size_t)set * (P.gd_bytes / 8) + i];
@@ -119,6 +162,10 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dfull0));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dfull0 + 8));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(oready));
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(xfull0 + 8 * i));   // the partner's epilogue team (4 warps) has sent a pair
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(xfree0 + 8 * i));   // the partner's epilogue team has read the buffer
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -129,6 +176,7 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (exch) cluster_sync_all();   // the partner's barriers exist before anything is sent (both CTAs of the pair take this branch)
     const unsigned tmem = *tmem_slot;
     const unsigned dcol0 = 512u - 48u * (unsigned)npanel;   // accumulators of panel j: dcol0 + 48 j (+ 32: the O'_lo product, 16 columns)
 
@@ -371,7 +419,41 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
                 mbar_arrive(gfree0 + 8 * gsA);
                 if (hasB) mbar_arrive(gfree0 + 8 * gsB);
             }
-            float *dst = Fs + (((size_t)set * glen + (size_t)(cbeg + t0 - gbeg)) * 2) * (SM_ROWS * KC) + (size_t)row * KC;
+            if (exch) {
+                const int i = s >> 1;   // this team's i-th pair
+                float *xb = xbuf + (size_t)team * (SM_ROWS * 32) + (size_t)row * 4;   // [8 groups of 4 floats][row]
+                if (crank == 1) {   // send: wait until the partner has read this team's previous pair, write into ITS buffer, arrive on ITS barrier
+                    if (i > 0) mbar_wait_cluster(xfree0 + 8 * team, (unsigned)(i - 1) & 1);
+                    const unsigned rb = mapa_shared(smem_u32(xb), 0);
+                    st_cluster_v4(rb + 0 * SM_ROWS * 16, FA0[0], FA0[1], FA0[2], FA0[3]);
+                    st_cluster_v4(rb + 1 * SM_ROWS * 16, FA0[4], FA0[5], FA0[6], FA0[7]);
+                    st_cluster_v4(rb + 2 * SM_ROWS * 16, FB0[0], FB0[1], FB0[2], FB0[3]);
+                    st_cluster_v4(rb + 3 * SM_ROWS * 16, FB0[4], FB0[5], FB0[6], FB0[7]);
+                    st_cluster_v4(rb + 4 * SM_ROWS * 16, FA1[0], FA1[1], FA1[2], FA1[3]);
+                    st_cluster_v4(rb + 5 * SM_ROWS * 16, FA1[4], FA1[5], FA1[6], FA1[7]);
+                    st_cluster_v4(rb + 6 * SM_ROWS * 16, FB1[0], FB1[1], FB1[2], FB1[3]);
+                    st_cluster_v4(rb + 7 * SM_ROWS * 16, FB1[4], FB1[5], FB1[6], FB1[7]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_shared(xfull0 + 8 * team, 0));
+                    continue;   // nothing to store: the partner stores the sum
+                }
+                mbar_wait_cluster(xfull0 + 8 * team, (unsigned)i & 1);
+                {
+                    const float4 a0 = *reinterpret_cast<const float4 *>(xb + 0 * SM_ROWS * 4), a1 = *reinterpret_cast<const float4 *>(xb + 1 * SM_ROWS * 4),
+                                 b0 = *reinterpret_cast<const float4 *>(xb + 2 * SM_ROWS * 4), b1 = *reinterpret_cast<const float4 *>(xb + 3 * SM_ROWS * 4);
+                    FA0[0] += a0.x; FA0[1] += a0.y; FA0[2] += a0.z; FA0[3] += a0.w; FA0[4] += a1.x; FA0[5] += a1.y; FA0[6] += a1.z; FA0[7] += a1.w;
+                    FB0[0] += b0.x; FB0[1] += b0.y; FB0[2] += b0.z; FB0[3] += b0.w; FB0[4] += b1.x; FB0[5] += b1.y; FB0[6] += b1.z; FB0[7] += b1.w;
+                }
+                {
+                    const float4 a0 = *reinterpret_cast<const float4 *>(xb + 4 * SM_ROWS * 4), a1 = *reinterpret_cast<const float4 *>(xb + 5 * SM_ROWS * 4),
+                                 b0 = *reinterpret_cast<const float4 *>(xb + 6 * SM_ROWS * 4), b1 = *reinterpret_cast<const float4 *>(xb + 7 * SM_ROWS * 4);
+                    FA1[0] += a0.x; FA1[1] += a0.y; FA1[2] += a0.z; FA1[3] += a0.w; FA1[4] += a1.x; FA1[5] += a1.y; FA1[6] += a1.z; FA1[7] += a1.w;
+                    FB1[0] += b0.x; FB1[1] += b0.y; FB1[2] += b0.z; FB1[3] += b0.w; FB1[4] += b1.x; FB1[5] += b1.y; FB1[6] += b1.z; FB1[7] += b1.w;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_shared(xfree0 + 8 * team, 1));   // the buffer may be refilled
+            }
+            float *dst = Fs + (((size_t)slot_id * glen + (size_t)(cbeg + t0 - gbeg)) * 2) * (SM_ROWS * KC) + (size_t)row * KC;
             *reinterpret_cast<float4 *>(dst) = make_float4(FA0[0], FA0[1], FA0[2], FA0[3]);
             *reinterpret_cast<float4 *>(dst + 4) = make_float4(FA0[4], FA0[5], FA0[6], FA0[7]);
             *reinterpret_cast<float4 *>(dst + SM_ROWS * KC) = make_float4(FB0[0], FB0[1], FB0[2], FB0[3]);
@@ -453,6 +535,7 @@ k_synth_gen(const __grid_constant__ DevPlanG P, const float *__restrict__ Op, in
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+    if (exch) cluster_sync_all();   // neither CTA of the pair leaves while the other may still write into its shared memory
 }
 
 // Sum of the partial folds over the column sets of every kind, 8-point Walsh-Hadamard transform of the 8 class values, the 8 mirror

@@ -25,7 +25,7 @@ class Plan:
                  "batched_min", "batched_row_groups", "batched_row_groups_wide", "batched_wide_min", "batched_rounds",
                  "batched_rounds_wide", "stream_state", "stream_sets", "stream_splits", "stream_rows16", "stream_table_mib",
                  "chunks", "gen", "gen_sets", "gen_splits", "gen_cols", "gen_slots", "gen_min", "tables_level", "gen_maxcols",
-                 "gen2", "gen2_sets", "gen2_splits", "gen2_slots", "synth", "synth_min")
+                 "gen2", "gen2_sets", "gen2_splits", "gen2_slots", "synth", "synth_min", "synth_partial_slots")
 
     def __init__(self, order: int, dim: int, device: int | None = None):
         if not torch.cuda.is_available():
@@ -53,8 +53,8 @@ class Plan:
 
     # ------------------------------------------------------------------ helpers
     def info(self) -> dict:
-        arr = (ctypes.c_int * 38)()
-        _lib.check(self._L.z3d_plan_info(self._h, arr, 38))
+        arr = (ctypes.c_int * 39)()
+        _lib.check(self._L.z3d_plan_info(self._h, arr, 39))
         return dict(zip(self.INFO_KEYS, list(arr)))
 
     def prepare_tables(self, level: int, max_bytes: int = 0) -> int:
