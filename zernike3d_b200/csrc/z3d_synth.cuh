@@ -6,17 +6,18 @@
 //     G_X[kind][re|im](k) = sum over the (m, pz) panels j of the kind of   trig_X,j[re|im] * out_j[re|im](k),     X = row group A or its transpose B,
 //     out_j[(re|im, b)](k) = sum over the rows of panel j of   O'[(re|im, b)][row] * T[row](k),     O'[re] = w kappa Re O,  O'[im] = - w kappa Im O,
 // and the 8 mirror images of k are the 8-point Walsh-Hadamard transform of the 8 class values (kind, re|im) - k_fold_tile_gen run backwards.
-// out_j is a GEMM over the moment rows: tcgen05.mma kind::tf32 with M = 128 = (re|im) x 64 maps, K = 8 rows per instruction, and N = 16 =
-// the chunk's 8 folded voxels TWICE: the T block of a chunk lies in shared memory as [T_hi k half 0 | T_hi k half 1 | T_lo k half 0 | T_lo
-// k half 1] with one stride, which an MN-major descriptor reads as 4 vectors of 4 voxels - one MMA with A = O'_hi yields O'_hi T_hi in
-// columns 0-7 and O'_hi T_lo in columns 8-15, a second with A = O'_lo adds O'_lo T_hi (3xTF32: the three are summed in the epilogue).
+// out_j is a GEMM over the moment rows: tcgen05.mma kind::tf32 with M = 128 = (re|im) x 64 maps, K = 8 rows per instruction, B = the T block in
+// shared memory, MN-major.  A pipeline step is a PAIR of chunks: a T row of 128 bytes holds [T_hi A | T_hi B | T_lo A | T_lo B] (8 voxels each),
+// so that one N = 32 MMA with A = O'_hi yields O'_hi T_hi and O'_hi T_lo of both chunks and one N = 16 MMA with A = O'_lo adds O'_lo T_hi
+// (3xTF32: the three are summed in the epilogue).
 //   * O' of the CTA's column set stays in TENSOR memory for the whole kernel (columns [0, ncols) hi, [ncols, 2 ncols) lo; the MMA's A operand),
-//   * T is generated exactly as in k_decompose_gen (seed warps, T teams, the same ring and the same plan tables: the two-tile layout of
-//     the analysis kernel, whose sets hold <= 224 columns),
-//   * the accumulators out_j (32 columns per panel, two banks by chunk parity) are read by two epilogue teams (thread = (re|im, map) =
-//     tensor-memory lane), multiplied by the row trig of the chunk and summed over the set's panels; the sets of one kind add up in
-//     k_unfold_tile, which also applies the Walsh-Hadamard transform and writes the 16 images.  No read-back interval: an accumulator lives
-//     for one chunk.
+//   * T is generated exactly as in k_decompose_gen (seed warps, T teams, the same plan tables: the two-tile layout of the analysis kernel,
+//     whose sets hold <= 224 columns),
+//   * the accumulators out_j (48 columns per panel, one bank, released to the issuing warp panel by panel) are read by two epilogue teams
+//     (thread = (re|im, map) = tensor-memory lane), multiplied by the row trig of the chunk and summed over the set's panels,
+//   * CTAs run in thread-block clusters of two column sets: where both are of the same kind the odd CTA sends its class partials to the even
+//     one through distributed shared memory and only the sum is stored; the stored partials of one kind add up in k_unfold_tile, which also
+//     applies the Walsh-Hadamard transform and writes the 16 images.  No read-back interval: an accumulator lives for one chunk pair.
 // Roles (28 warps): warp 0 issues, warps 1-3 seeds, warps 4-11 two epilogue teams, warps 12-27 four T teams.
 #pragma once
 #include "z3d_gen.cuh"
