@@ -184,7 +184,9 @@ int z3d_crop_bin(const float *d_in, int batch, int n_in, int cz, int cy, int cx,
 /* Host-buffer convenience calls: the same operations for callers that hold numpy / C arrays, the way
  * zm's Decompose(volume, ...) receives `mrc.data` and Reconstruct() returns a host map.  They stage
  * through pinned memory owned by the plan, overlap H2D copies with compute in chunks of volumes, and
- * return after the results are in the host buffers.  Not thread-safe per plan. */
+ * return after the results are in the host buffers.  Not thread-safe per plan.  z3d_reconstruct_host sends staged groups of at
+ * least z3d_plan_info entry 37 maps through the tensor-core synthesis kernel (z3d_reconstruct_batched; its workspace is allocated
+ * by the plan on first use). */
 int z3d_decompose_host(z3d_plan *plan, const float *h_vol, int batch, float *h_moments);
 int z3d_reconstruct_host(z3d_plan *plan, const float *h_moments, int batch, float *h_vol);
 

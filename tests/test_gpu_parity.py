@@ -562,6 +562,12 @@ def test_host_buffer_api_matches_device_api(plans):
     mh = P.decompose_host(torch.from_numpy(vols).pin_memory())
     md = P.decompose(dev(vols)).cpu().numpy()
     assert np.array_equal(mh, md)
+    # ... and the host synthesis call takes the tensor-core kernel for groups of >= synth_min maps (z3d_reconstruct_batched)
+    rh = P.reconstruct_host(mh)
+    rd = P.reconstruct(dev(mh), batched=True).cpu().numpy()
+    assert rh.shape == (40, 32, 32, 32) and np.array_equal(rh[:32], rd[:32])      # the first staged group of 32 = the same tile
+    for i in (33, 39):
+        assert rel_l2(rh[i], rd[i]) < TOL_EXACT                                     # (the remaining 8 go through the per-map kernel)
 
 
 def test_error_paths(plans):

@@ -139,6 +139,8 @@ struct z3d_plan {
     float *d_stage_vol[2] = {nullptr, nullptr};
     float *d_stage_mom[2] = {nullptr, nullptr};
     void *d_stage_ws[2] = {nullptr, nullptr};
+    void *d_stage_synth_ws = nullptr;   // workspace of the tensor-core synthesis kernel for z3d_reconstruct_host (allocated on first use)
+    size_t stage_synth_bytes = 0;
     int stage_batch = 0;
     bool staged_ok = false;
     // optional per-kernel timing (bench.py roofline): events around the dominant kernel of the last call
@@ -1794,6 +1796,9 @@ static void free_staging(z3d_plan *pl) {
         pl->d_stage_ws[i] = nullptr;
         pl->ev_in[i] = pl->ev_done[i] = nullptr;
     }
+    if (pl->d_stage_synth_ws) cudaFree(pl->d_stage_synth_ws);
+    pl->d_stage_synth_ws = nullptr;
+    pl->stage_synth_bytes = 0;
     if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
     if (pl->s_comp) cudaStreamDestroy(pl->s_comp);
     pl->s_copy = pl->s_comp = nullptr;
@@ -1897,8 +1902,21 @@ extern "C" int z3d_reconstruct_host(z3d_plan *pl, const float *h_mom, int batch,
                                  (size_t)nb * pl->nmom * 2 * sizeof(float), cudaMemcpyHostToDevice, pl->s_copy));
         HOST_TRY(cudaEventRecord(pl->ev_in[stage], pl->s_copy));
         HOST_TRY(cudaStreamWaitEvent(pl->s_comp, pl->ev_in[stage], 0));
-        rc = z3d_reconstruct(pl, pl->d_stage_mom[stage], nb, 0, pl->H, pl->d_stage_vol[stage], pl->d_stage_ws[stage],
-                             z3d_workspace_bytes(pl, gb), pl->s_comp);
+        if (pl->synth && nb >= pl->synth_min) {   // a group of maps worth a tile of the tensor-core synthesis kernel
+            const size_t need = z3d_reconstruct_batched_workspace_bytes(pl, nb);
+            if (pl->stage_synth_bytes < need) {
+                HOST_TRY(cudaStreamSynchronize(pl->s_comp));
+                if (pl->d_stage_synth_ws) cudaFree(pl->d_stage_synth_ws);
+                pl->d_stage_synth_ws = nullptr;
+                pl->stage_synth_bytes = 0;
+                HOST_TRY(cudaMalloc(&pl->d_stage_synth_ws, need));
+                pl->stage_synth_bytes = need;
+            }
+            rc = z3d_reconstruct_batched(pl, pl->d_stage_mom[stage], nb, pl->d_stage_vol[stage], pl->d_stage_synth_ws, pl->stage_synth_bytes, pl->s_comp);
+        } else {
+            rc = z3d_reconstruct(pl, pl->d_stage_mom[stage], nb, 0, pl->H, pl->d_stage_vol[stage], pl->d_stage_ws[stage],
+                                 z3d_workspace_bytes(pl, gb), pl->s_comp);
+        }
         if (rc) return host_call_fail(pl, rc);
         HOST_TRY(cudaMemcpyAsync(h_vol + (size_t)b0 * N3, pl->d_stage_vol[stage], (size_t)nb * N3 * sizeof(float),
                                  cudaMemcpyDeviceToHost, pl->s_comp));
