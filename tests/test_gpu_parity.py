@@ -543,6 +543,23 @@ def test_batched_synthesis_error_paths(plans):
     rc = L.z3d_reconstruct_batched(P._h, m.data_ptr(), 16, out.data_ptr(), ws.data_ptr(), ws.numel(), None)
     assert rc == _lib.ERR_WORKSPACE
     assert L.z3d_reconstruct_batched(P._h, None, 16, out.data_ptr(), ws.data_ptr(), ws.numel(), None) == _lib.ERR_INVALID
+    # guard bands around the output and the workspace stay untouched (compute-sanitizer is closed on the GPU pool: an own bounds check)
+    for order, dim, B in ((10, 16, 16), (12, 24, 70), (20, 32, 13)):
+        P = plans(order, dim)
+        m = torch.randn((B, P.num_moments), dtype=torch.complex64, device="cuda")
+        need = L.z3d_reconstruct_batched_workspace_bytes(P._h, B)
+        G = 1 << 16
+        ws = torch.full((need + 2 * G,), 0x5A, dtype=torch.uint8, device="cuda")
+        n_out = B * dim ** 3
+        out = torch.full((n_out + 2 * G,), -7.5, dtype=torch.float32, device="cuda")
+        rc = L.z3d_reconstruct_batched(P._h, m.data_ptr(), B, out.data_ptr() + 4 * G, ws.data_ptr() + G, need, None)
+        torch.cuda.synchronize()
+        assert rc == 0
+        assert bool((ws[:G] == 0x5A).all()) and bool((ws[G + need:] == 0x5A).all())
+        assert bool((out[:G] == -7.5).all()) and bool((out[G + n_out:] == -7.5).all())
+        body = out[G:G + n_out].view(B, dim, dim, dim)
+        assert bool(torch.isfinite(body).all()) and not bool((body == -7.5).any())          # every voxel written
+        assert rel_l2(body[B - 1].cpu().numpy(), P.reconstruct(m[B - 1], batched=False).cpu().numpy()) < TOL_EXACT_BATCHED
 
 
 def test_host_buffer_api_matches_device_api(plans):
@@ -568,6 +585,29 @@ def test_host_buffer_api_matches_device_api(plans):
     assert rh.shape == (40, 32, 32, 32) and np.array_equal(rh[:32], rd[:32])      # the first staged group of 32 = the same tile
     for i in (33, 39):
         assert rel_l2(rh[i], rd[i]) < TOL_EXACT                                     # (the remaining 8 go through the per-map kernel)
+
+
+def test_guard_bands_around_analysis_buffers(plans):
+    """compute-sanitizer is closed on the GPU pool: an own bounds check of the global writes of the analysis kernels (per-volume and
+    table-free tensor-core path) - guard bands around the workspace and the moments stay untouched."""
+    from zernike3d_b200 import _lib
+
+    L = _lib.lib()
+    for order, dim, B in ((10, 16, 3), (10, 16, 9), (12, 24, 70), (20, 32, 13), (25, 20, 8)):
+        P = plans(order, dim)
+        vols = dev(np.stack([volume(40 + i, dim) for i in range(B)]))
+        need = L.z3d_workspace_bytes(P._h, B)
+        G = 1 << 16
+        ws = torch.full((need + 2 * G,), 0x5A, dtype=torch.uint8, device="cuda")
+        n_out = B * P.num_moments * 2
+        out = torch.full((n_out + 2 * G,), -7.5, dtype=torch.float32, device="cuda")
+        rc = L.z3d_decompose(P._h, vols.data_ptr(), B, 0, P.half, out.data_ptr() + 4 * G, ws.data_ptr() + G, need, None)
+        torch.cuda.synchronize()
+        assert rc == 0
+        assert bool((ws[:G] == 0x5A).all()) and bool((ws[G + need:] == 0x5A).all())
+        assert bool((out[:G] == -7.5).all()) and bool((out[G + n_out:] == -7.5).all())
+        got = torch.view_as_complex(out[G:G + n_out].view(B, P.num_moments, 2))
+        assert torch.equal(torch.view_as_real(got), torch.view_as_real(P.decompose(vols)))
 
 
 def test_error_paths(plans):
