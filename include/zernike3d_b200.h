@@ -190,6 +190,13 @@ int z3d_crop_bin(const float *d_in, int batch, int n_in, int cz, int cy, int cx,
 int z3d_decompose_host(z3d_plan *plan, const float *h_vol, int batch, float *h_moments);
 int z3d_reconstruct_host(z3d_plan *plan, const float *h_moments, int batch, float *h_vol);
 
+/* Streaming form of z3d_decompose_host for ensembles that arrive batch after batch: _submit enqueues the copies and kernels of one
+ * batch and returns; the next batch's host-to-device copies then overlap this batch's last kernels and its device-to-host copy.
+ * Both host buffers must stay valid (and h_moments unread) until z3d_host_wait returns.  Pinned host memory is needed for the
+ * copies to be asynchronous. */
+int z3d_decompose_host_submit(z3d_plan *plan, const float *h_vol, int batch, float *h_moments);
+int z3d_host_wait(z3d_plan *plan);
+
 /* Number of kernels launched by this library since load (all plans, all threads); bench.py reports
  * the difference across its timed region as "gpu_launches". */
 unsigned long long z3d_launch_count(void);

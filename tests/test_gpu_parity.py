@@ -579,6 +579,17 @@ def test_host_buffer_api_matches_device_api(plans):
     mh = P.decompose_host(torch.from_numpy(vols).pin_memory())
     md = P.decompose(dev(vols)).cpu().numpy()
     assert np.array_equal(mh, md)
+    # streaming form: two batches submitted back to back, one wait; identical to the blocking call
+    pin = torch.from_numpy(vols).pin_memory()
+    o1 = torch.empty((40, P.num_moments), dtype=torch.complex64).pin_memory()
+    o2 = torch.empty((25, P.num_moments), dtype=torch.complex64).pin_memory()
+    pin2 = torch.from_numpy(np.ascontiguousarray(vols[:25][::-1])).pin_memory()
+    P.decompose_host_submit(pin, o1)
+    P.decompose_host_submit(pin2, o2)
+    P.host_wait()
+    assert np.array_equal(o1.numpy(), md) and np.array_equal(o2.numpy(), md[:25][::-1])
+    with pytest.raises(ValueError):
+        P.decompose_host_submit(pin, o2)
     # ... and the host synthesis call takes the tensor-core kernel for groups of >= synth_min maps (z3d_reconstruct_batched)
     rh = P.reconstruct_host(mh)
     rd = P.reconstruct(dev(mh), batched=True).cpu().numpy()

@@ -78,6 +78,8 @@ def lib() -> ctypes.CDLL:
     L.z3d_invariants.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p]
     L.z3d_scale_moments.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
     L.z3d_decompose_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    L.z3d_decompose_host_submit.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    L.z3d_host_wait.argtypes = [c_void_p]
     L.z3d_reconstruct_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     L.z3d_launch_count.restype = ctypes.c_ulonglong
     L.z3d_profile_enable.argtypes = [c_void_p, c_int]
@@ -99,5 +101,5 @@ EXPORTS = [
     "z3d_reconstruct", "z3d_invariants", "z3d_decompose_host", "z3d_reconstruct_host", "z3d_launch_count",
     "z3d_fma_peak", "z3d_profile_enable", "z3d_profile_last_ms", "z3d_decompose_part", "z3d_comm_create", "z3d_comm_connect", "z3d_comm_destroy", "z3d_comm_error",
     "z3d_decompose_allreduce", "z3d_scale_moments", "z3d_stream_layout", "z3d_zcc", "z3d_crop_bin", "z3d_gen_layout", "z3d_gen_layout_tiles",
-    "z3d_plan_prepare_tables", "z3d_tf32_peak", "z3d_reconstruct_batched", "z3d_reconstruct_batched_workspace_bytes",
+    "z3d_plan_prepare_tables", "z3d_tf32_peak", "z3d_reconstruct_batched", "z3d_reconstruct_batched_workspace_bytes", "z3d_decompose_host_submit", "z3d_host_wait",
 ]

@@ -141,7 +141,7 @@ struct z3d_plan {
     void *d_stage_ws[2] = {nullptr, nullptr};
     void *d_stage_synth_ws = nullptr;   // workspace of the tensor-core synthesis kernel for z3d_reconstruct_host (allocated on first use)
     size_t stage_synth_bytes = 0;
-    int stage_batch = 0;
+    int stage_batch = 0, stage_next = 0;
     bool staged_ok = false;
     // optional per-kernel timing (bench.py roofline): events around the dominant kernel of the last call
     bool profiling = false;
@@ -1859,15 +1859,15 @@ static int host_call_fail(z3d_plan *pl, int rc) {
             return host_call_fail(pl, fail(Z3D_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__)); \
     } while (0)
 
-extern "C" int z3d_decompose_host(z3d_plan *pl, const float *h_vol, int batch, float *h_mom) {
-    if (!pl || !h_vol || !h_mom || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_decompose_host: bad arguments");
-    USE_DEVICE(pl->device);
+// enqueue the staged groups of one host-buffer analysis call; the stage counter lives in the plan so that consecutive submissions keep
+// alternating the two staging buffers
+static int decompose_host_enqueue(z3d_plan *pl, const float *h_vol, int batch, float *h_mom) {
     int rc = ensure_staging(pl);
     if (rc) return rc;
     const size_t N3 = (size_t)pl->dim * pl->dim * pl->dim;
     const int gb = pl->stage_batch;
-    int stage = 0;
-    for (int b0 = 0; b0 < batch; b0 += gb, stage ^= 1) {
+    for (int b0 = 0; b0 < batch; b0 += gb, pl->stage_next ^= 1) {
+        const int stage = pl->stage_next;
         const int nb = std::min(gb, batch - b0);
         // the stage's previous compute + D2H must be finished before its input buffer is overwritten
         HOST_TRY(cudaStreamWaitEvent(pl->s_copy, pl->ev_done[stage], 0));
@@ -1882,9 +1882,30 @@ extern "C" int z3d_decompose_host(z3d_plan *pl, const float *h_vol, int batch, f
                                  (size_t)nb * pl->nmom * 2 * sizeof(float), cudaMemcpyDeviceToHost, pl->s_comp));
         HOST_TRY(cudaEventRecord(pl->ev_done[stage], pl->s_comp));
     }
+    return Z3D_OK;
+}
+
+extern "C" int z3d_host_wait(z3d_plan *pl) {
+    if (!pl) return fail(Z3D_ERR_INVALID, "z3d_host_wait: plan is NULL");
+    if (!pl->staged_ok) return Z3D_OK;
+    USE_DEVICE(pl->device);
     HOST_TRY(cudaStreamSynchronize(pl->s_comp));
     HOST_TRY(cudaStreamSynchronize(pl->s_copy));
     return Z3D_OK;
+}
+
+extern "C" int z3d_decompose_host(z3d_plan *pl, const float *h_vol, int batch, float *h_mom) {
+    if (!pl || !h_vol || !h_mom || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_decompose_host: bad arguments");
+    USE_DEVICE(pl->device);
+    const int rc = decompose_host_enqueue(pl, h_vol, batch, h_mom);
+    if (rc) return rc;
+    return z3d_host_wait(pl);
+}
+
+extern "C" int z3d_decompose_host_submit(z3d_plan *pl, const float *h_vol, int batch, float *h_mom) {
+    if (!pl || !h_vol || !h_mom || batch < 1) return fail(Z3D_ERR_INVALID, "z3d_decompose_host_submit: bad arguments");
+    USE_DEVICE(pl->device);
+    return decompose_host_enqueue(pl, h_vol, batch, h_mom);
 }
 
 extern "C" int z3d_reconstruct_host(z3d_plan *pl, const float *h_mom, int batch, float *h_vol) {

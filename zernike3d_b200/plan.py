@@ -242,6 +242,25 @@ class Plan:
                                               ctypes.c_void_p(o.ctypes.data)))
         return out[0] if single else out
 
+    def decompose_host_submit(self, vol, out) -> None:
+        """Streaming form of :meth:`decompose_host` (``z3d_decompose_host_submit``): enqueue one batch and return; ``vol`` (float32
+        ``[B, N, N, N]``) and ``out`` (complex64 ``[B, num_moments]``) must be contiguous pinned tensors / arrays that stay alive and
+        untouched until :meth:`host_wait`.  The next batch's copies overlap this batch's last kernels."""
+        v = vol.numpy() if isinstance(vol, torch.Tensor) else vol
+        o = out.numpy() if isinstance(out, torch.Tensor) else out
+        if v.dtype != np.float32 or not v.flags.c_contiguous or v.ndim != 4 or tuple(v.shape[1:]) != (self.dim,) * 3:
+            raise ValueError(f"decompose_host_submit: need contiguous float32 volumes [B,{self.dim},{self.dim},{self.dim}]")
+        if o.dtype != np.complex64 or not o.flags.c_contiguous or tuple(o.shape) != (v.shape[0], self.num_moments):
+            raise ValueError(f"decompose_host_submit: need a contiguous complex64 output [{v.shape[0]},{self.num_moments}]")
+        self._pending = getattr(self, "_pending", [])
+        self._pending.append((vol, out))
+        _lib.check(self._L.z3d_decompose_host_submit(self._h, ctypes.c_void_p(v.ctypes.data), v.shape[0], ctypes.c_void_p(o.ctypes.data)))
+
+    def host_wait(self) -> None:
+        """Wait for every submitted host-buffer batch (``z3d_host_wait``)."""
+        _lib.check(self._L.z3d_host_wait(self._h))
+        self._pending = []
+
     def reconstruct_host(self, moments, out=None):
         m = moments.numpy() if isinstance(moments, torch.Tensor) else np.asarray(moments)
         single = m.ndim == 1
