@@ -1290,7 +1290,10 @@ extern "C" int z3d_gen_layout_tiles(int order, int num_sms, int ntile, int *out,
 extern "C" int z3d_plan_destroy(z3d_plan *pl) {
     if (!pl) return Z3D_OK;
     DeviceGuard _guard(pl->device);
+    if (pl->s_comp) cudaStreamSynchronize(pl->s_comp);   // submitted host-buffer batches (z3d_decompose_host_submit) may still be in flight
+    if (pl->s_copy) cudaStreamSynchronize(pl->s_copy);
     for (void *p : pl->owned) cudaFree(p);
+    if (pl->d_stage_synth_ws) cudaFree(pl->d_stage_synth_ws);
     if (pl->d_Rt) cudaFree(pl->d_Rt);
     if (pl->d_Qt) cudaFree(pl->d_Qt);
     if (pl->d_trig) cudaFree(pl->d_trig);
