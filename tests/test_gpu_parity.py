@@ -292,6 +292,26 @@ def test_zcc_on_device_matches_the_host_curve(plans):
     assert same.shape == (order + 1,) and np.allclose(same, 1.0, atol=1e-6)
 
 
+def test_zcc_and_latent_scaling_on_device_against_reference_run_fixture(plans):
+    """z3d_zcc and z3d_scale_moments against tests/golden/ref_zcc_scaling.npz: curves from the reference's own calc_ZCC statements
+    (moment_analysis_3dva.py:402-421) and moments scaled by the reference's own Moments.apply_scaling (zm:78-95)."""
+    g = golden("zcc_scaling")
+    P = plans(int(g["order"]), 64)
+    sets = dev(np.asarray(g["moment_sets"], np.complex64))
+    ia = [int(i) for i, _ in g["pairs"]]
+    ib = [int(j) for _, j in g["pairs"]]
+    curves = P.zcc(sets[ia].contiguous(), sets[ib].contiguous()).cpu().numpy()
+    assert curves.shape == (len(ia), int(g["order"]) + 1)
+    assert np.allclose(curves, g["zcc"], rtol=3e-6, atol=1e-7)
+    b = golden("3dva_d24_o12")
+    Pb = plans(int(b["order"]), int(b["dim"]))
+    zs = [int(z) for z in g["scaling_z"]]
+    lat = np.asarray(b["latents"], np.float32)[zs]
+    got = Pb.scale_moments(dev(np.asarray(b["moments"], np.complex64)), dev(lat)).cpu().numpy()
+    for k in range(len(zs)):
+        assert rel_l2(got[k], g["scaled"][k]) < 1e-6
+
+
 @pytest.mark.parametrize("n,crop,bin_,center", [(32, None, 2, None), (32, 20, None, (14, 16, 17)), (40, 24, 2, (20, 19, 21)),
                                                   (33, None, 3, None), (64, 48, 1.5, (30, 33, 32)), (31, 17, 2.5, (15, 15, 16))])
 def test_crop_bin_on_device_is_bit_identical_to_the_host_path(n, crop, bin_, center):

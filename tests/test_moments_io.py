@@ -152,3 +152,31 @@ def test_zcc_curve_matches_the_reference_formula():
         want.append(np.sum(_sum) / np.sqrt(np.sum(np.abs(xs) ** 2) * np.sum(np.abs(ys) ** 2)))
     assert got.shape == (order + 1,) and np.allclose(got, want, rtol=1e-6)
     assert np.allclose(A.zcc(A), 1.0, atol=1e-6)
+
+
+def test_zcc_and_latent_scaling_against_reference_run_fixture():
+    """Moments.zcc / Moments.apply_scaling against tests/golden/ref_zcc_scaling.npz: curves produced by the reference's OWN calc_ZCC statements
+    (moment_analysis_3dva.py:402-421, executed unchanged by oracle/make_zcc_golden.py) and maps of moments scaled by the reference's own
+    Moments.apply_scaling (zm:78-95)."""
+    from conftest import golden
+    from zernike3d_b200.moments import Moments
+
+    g = golden("zcc_scaling")
+    sets = np.asarray(g["moment_sets"], np.complex64)
+    M = Moments(quiet=True)
+    for v in sets:
+        M.from_array(v)
+        M.add_dimension()
+    for (i, j), want in zip(g["pairs"], g["zcc"]):
+        got = M.zcc(M, int(i), int(j))
+        assert got.shape == (int(g["order"]) + 1,) and np.allclose(got, want, rtol=2e-6, atol=1e-7)
+    b = golden("3dva_d24_o12")
+    B = Moments(quiet=True)
+    for v in np.asarray(b["moments"], np.complex64):
+        B.from_array(v)
+        B.add_dimension()
+    B.latents = np.asarray(b["latents"], np.float32)
+    B.stats(quiet=True)
+    for z, want in zip(g["scaling_z"], g["scaled"]):
+        got = np.asarray(B.apply_scaling(z_ind=int(z)))
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-6
